@@ -1,0 +1,75 @@
+// Host-side eigen-check of the block-tridiagonal Lanczos matrix T (no CUDA in this file).
+//
+// Replaces, on the host and with the same inputs/outputs, the reference's per-check sequence
+//     D,V = dsbev('V','L',T); D,V = sort_eig_abs(D,V,k); check_convergence(Bi,V,b,k,tol)
+// (Julia/common.jl:36-65, called from RBL_gpu.jl:186-192).  dsbev computes ALL N eigenvectors in
+// O(N^3); here only what the decision needs is computed, by spectrum slicing on the band matrix:
+// Sturm counts from a row-wise elimination with pairwise pivoting (leading-principal-minor signs),
+// inverse / Rayleigh-quotient iteration with the same factorisation for the vectors.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace rbl {
+
+// Symmetric band matrix, half-bandwidth kd, stored as full band rows: F[r*(2kd+1) + (c - r + kd)].
+struct BandSym {
+    int64_t N = 0;
+    int kd = 0;
+    std::vector<double> F;
+    double norm_inf = 0.0;
+
+    void reset(int64_t n, int kd_);
+    inline double& at(int64_t r, int64_t c) { return F[(size_t)r * (2 * kd + 1) + (size_t)(c - r + kd)]; }
+    inline double at(int64_t r, int64_t c) const { return F[(size_t)r * (2 * kd + 1) + (size_t)(c - r + kd)]; }
+    void set_sym(int64_t r, int64_t c, double v) { at(r, c) = v; at(c, r) = v; }
+    void from_lapack_lower(int64_t n, int kd_, const double* ab);  // (kd+1) x N column-major
+    void update_norm();
+    void matvec(const double* x, double* y) const;
+};
+
+// LU of (T - x I) by row-wise elimination with pairwise pivoting; also yields the Sturm count.
+struct BandLU {
+    int64_t N = 0;
+    int kd = 0;
+    std::vector<double> U;    // N x (2kd+1): row i holds columns i .. i+2kd
+    std::vector<double> L;    // N x kd multipliers
+    std::vector<uint8_t> sw;  // N x kd swap flags
+    std::vector<double> w;
+    int64_t nneg = 0;         // number of eigenvalues of T below the shift
+    void factor(const BandSym& T, double shift);
+    void solve(double* v) const;
+};
+
+struct TopKResult {
+    bool converged = false;
+    int64_t N = 0;
+    std::vector<double> d;      // k eigenvalues, descending |lambda|
+    std::vector<double> s;      // N x k column-major eigenvectors (same order)
+    std::vector<double> resid;  // k residual bounds ||B_i s_last||
+    bool have_all = false;      // d/s/resid hold all k pairs (full check ran)
+    int factorizations = 0;
+};
+
+// Stateful checker: keeps a "witness" Ritz pair between checks so that the common (not yet
+// converged) case costs a handful of band factorisations instead of a full eigensolve.
+class BandTopK {
+public:
+    int threads = 1;
+    int verbose = 0;
+    int64_t total_factorizations = 0;
+    int full_checks = 0;
+
+    // T: current N x N band matrix; bi: b x b upper-triangular B_i row-major (bi[r*b+c]); k wanted.
+    // force_full: compute all k pairs even when a witness already proves non-convergence.
+    TopKResult check(const BandSym& T, const double* bi, int b, int64_t k, double tol, bool force_full);
+    void reset() { wit_.clear(); wit_theta_ = 0; }
+
+private:
+    std::vector<double> wit_;
+    double wit_theta_ = 0;
+};
+
+int64_t band_count_below(const BandSym& T, double x);
+
+}  // namespace rbl

@@ -1,0 +1,407 @@
+// extern "C" entry points declared in include/rbl_b200.h.
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "partition.h"
+#include "solver.h"
+
+using namespace rbl;
+
+static thread_local std::string g_err;
+
+template <typename F>
+static int guarded(F&& f) {
+    try {
+        return f();
+    } catch (const Error& e) {
+        g_err = e.what();
+        return e.status;
+    } catch (const std::bad_alloc&) {
+        g_err = "host out of memory";
+        return RBL_OOM;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return RBL_INVALID;
+    }
+}
+
+static void need_device() {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        throw Error(RBL_NO_DEVICE, "no CUDA device visible: rbl_b200 has no CPU fallback");
+}
+
+extern "C" {
+
+const char* rbl_last_error(void) { return g_err.c_str(); }
+const char* rbl_version(void) { return "rbl_b200 0.1 (sm_100a)"; }
+int rbl_device_count(void) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) return 0;
+    return ndev;
+}
+int rbl_options_default(rbl_options* opts) {
+    if (!opts) return RBL_INVALID;
+    default_options(opts);
+    return RBL_OK;
+}
+
+int rbl_create(int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+               int index_base, const rbl_options* opts, rbl_handle** out) {
+    return guarded([&] {
+        if (!out) throw Error(RBL_INVALID, "rbl_create: out is null");
+        *out = handle_create(n, 0, n, nnz, colptr, rowval, nzval, index_base, 0, 1, nullptr, opts);
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_create_dense(int64_t n, const double* a, const rbl_options* opts, rbl_handle** out) {
+    return guarded([&] {
+        if (!out || !a || n <= 0) throw Error(RBL_INVALID, "rbl_create_dense: bad arguments");
+        if (n * n >= ((int64_t)1 << 31)) throw Error(RBL_INVALID, "rbl_create_dense: n*n must be < 2^31");
+        std::vector<int64_t> rp((size_t)n + 1), ci((size_t)n * n);
+        std::vector<double> v((size_t)n * n);
+        for (int64_t r = 0; r <= n; ++r) rp[r] = r * n;
+        for (int64_t r = 0; r < n; ++r)
+            for (int64_t c = 0; c < n; ++c) {
+                ci[(size_t)r * n + c] = c;
+                v[(size_t)r * n + c] = a[(size_t)c * n + r];  // row r of the column-major matrix
+            }
+        *out = handle_create(n, 0, n, n * n, rp.data(), ci.data(), v.data(), 0, 0, 1, nullptr, opts);
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_nccl_unique_id(void* uid128) {
+    return guarded([&] {
+        std::string err;
+        if (!uid128 || !Comm::unique_id(uid128, err)) throw Error(RBL_NCCL_ERROR, err.empty() ? "null uid" : err);
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_create_sharded(int64_t n, int64_t row0, int64_t nloc, int64_t nnz_loc, const int64_t* rowptr,
+                       const int64_t* colidx_global, const double* vals, int index_base, int rank, int world,
+                       const void* nccl_uid, const rbl_options* opts, rbl_handle** out) {
+    return guarded([&] {
+        if (!out) throw Error(RBL_INVALID, "rbl_create_sharded: out is null");
+        if (world < 1 || rank < 0 || rank >= world) throw Error(RBL_INVALID, "rbl_create_sharded: bad rank/world");
+        if (world > 1 && !nccl_uid) throw Error(RBL_INVALID, "rbl_create_sharded: nccl_uid is null");
+        *out = handle_create(n, row0, nloc, nnz_loc, rowptr, colidx_global, vals, index_base, rank, world, nccl_uid, opts);
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_destroy(rbl_handle* h) {
+    delete h;
+    return RBL_OK;
+}
+
+int rbl_solve(rbl_handle* h, int64_t k, int64_t b, const double* omega, double* d_out, void* v_out, rbl_stats* stats) {
+    return guarded([&] {
+        if (!h) throw Error(RBL_INVALID, "rbl_solve: null handle");
+        return solve(h, k, b, omega, false, d_out, v_out, false, stats);
+    });
+}
+
+int rbl_solve_device(rbl_handle* h, int64_t k, int64_t b, const void* omega_dev, double* d_out, void* v_dev,
+                     rbl_stats* stats) {
+    return guarded([&] {
+        if (!h) throw Error(RBL_INVALID, "rbl_solve_device: null handle");
+        return solve(h, k, b, (const double*)omega_dev, true, d_out, v_dev, true, stats);
+    });
+}
+
+int rbl_query_memory(int device, int64_t* free_bytes, int64_t* total_bytes) {
+    return guarded([&] {
+        need_device();
+        if (device >= 0) RBL_CUDA(cudaSetDevice(device));
+        size_t f = 0, t = 0;
+        RBL_CUDA(cudaMemGetInfo(&f, &t));
+        if (free_bytes) *free_bytes = (int64_t)f;
+        if (total_bytes) *total_bytes = (int64_t)t;
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_buffer_blocks(rbl_handle* h, int64_t b, int64_t* blocks_out) {
+    return guarded([&] {
+        if (!h || !blocks_out || b < 1 || b > 32) throw Error(RBL_INVALID, "rbl_buffer_blocks: bad arguments");
+        RBL_CUDA(cudaSetDevice(h->device));
+        size_t f = 0, t = 0;
+        RBL_CUDA(cudaMemGetInfo(&f, &t));
+        const int B = padded_block((int)b);
+        const size_t ssz = h->opt.precision == RBL_PRECISION_MIXED ? 4 : 8;
+        const double fixed = 3.0 * (double)(h->nloc + h->n_halo) * B * 8 + (double)((size_t)64 << 20);
+        const double per_block = (double)h->nloc * B * ssz + (double)B * 2 * B * ssz;
+        double fit = (0.92 * (double)f - fixed) / per_block;
+        *blocks_out = fit > 0 ? (int64_t)fit : 0;
+        return (int)RBL_OK;
+    });
+}
+
+// ---- kernel-level exports (host in, host out) ------------------------------------------------------
+int rbl_spmm(rbl_handle* h, int64_t b, const double* q, double* u) {
+    return guarded([&] {
+        if (!h || !q || !u || b < 1 || b > 32) throw Error(RBL_INVALID, "rbl_spmm: bad arguments");
+        if (h->world != 1) throw Error(RBL_INVALID, "rbl_spmm: single-GPU handles only");
+        RBL_CUDA(cudaSetDevice(h->device));
+        const int B = padded_block((int)b);
+        const int64_t n = h->nloc;
+        std::vector<double> qp((size_t)n * B, 0.0), up((size_t)n * B);
+        for (int64_t r = 0; r < n; ++r)
+            for (int c = 0; c < b; ++c) qp[(size_t)r * B + c] = q[(size_t)r * b + c];
+        DevBuf<double> dq, du;
+        dq.alloc(qp.size());
+        du.alloc(up.size());
+        RBL_CUDA(cudaMemcpy(dq.p, qp.data(), qp.size() * 8, cudaMemcpyHostToDevice));
+        launch_spmm(B, n, h->d_rowptr.p, h->d_colidx.p, h->d_vals.p, dq.p, du.p, h->opt.op, h->opt.sigma, h->stream);
+        RBL_CUDA(cudaStreamSynchronize(h->stream));
+        RBL_CUDA(cudaMemcpy(up.data(), du.p, up.size() * 8, cudaMemcpyDeviceToHost));
+        for (int64_t r = 0; r < n; ++r)
+            for (int c = 0; c < b; ++c) u[(size_t)r * b + c] = up[(size_t)r * B + c];
+        return (int)RBL_OK;
+    });
+}
+
+namespace {
+struct PadBlock {
+    std::vector<double> host;
+    DevBuf<double> dev;
+    void upload(int64_t n, int b, int B, const double* src) {
+        host.assign((size_t)n * B, 0.0);
+        for (int64_t r = 0; r < n; ++r)
+            for (int c = 0; c < b; ++c) host[(size_t)r * B + c] = src[(size_t)r * b + c];
+        dev.alloc(host.size());
+        RBL_CUDA(cudaMemcpy(dev.p, host.data(), host.size() * 8, cudaMemcpyHostToDevice));
+    }
+    void download(int64_t n, int b, int B, double* dst) {
+        RBL_CUDA(cudaMemcpy(host.data(), dev.p, host.size() * 8, cudaMemcpyDeviceToHost));
+        for (int64_t r = 0; r < n; ++r)
+            for (int c = 0; c < b; ++c) dst[(size_t)r * b + c] = host[(size_t)r * B + c];
+    }
+};
+}  // namespace
+
+int rbl_gram(int64_t n, int64_t b, const double* x, const double* y, double* cout) {
+    return guarded([&] {
+        need_device();
+        if (!x || !y || !cout || b < 1 || b > 32 || n < 1) throw Error(RBL_INVALID, "rbl_gram: bad arguments");
+        const int B = padded_block((int)b);
+        PadBlock X, Y;
+        X.upload(n, (int)b, B, x);
+        Y.upload(n, (int)b, B, y);
+        const int grid = rowop_grid(B, n);
+        DevBuf<double> part, G;
+        part.alloc((size_t)grid * B * B);
+        G.alloc((size_t)B * B);
+        RowOpArgs a;
+        a.n = n; a.y = Y.dev.p; a.gram_z = X.dev.p; a.do_gram = 1; a.partials = part.p;
+        launch_rowop(B, a, grid, 0);
+        launch_reduce_partials(part.p, grid, B * B, G.p, 0);
+        RBL_CUDA(cudaDeviceSynchronize());
+        std::vector<double> g((size_t)B * B);
+        RBL_CUDA(cudaMemcpy(g.data(), G.p, g.size() * 8, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < b; ++r)
+            for (int c = 0; c < b; ++c) cout[(size_t)r * b + c] = g[(size_t)r * B + c];
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_block_qr(int64_t n, int64_t b, double* u, double* r_out, int32_t* deflated_out) {
+    return guarded([&] {
+        need_device();
+        if (!u || !r_out || b < 1 || b > 32 || n < 1) throw Error(RBL_INVALID, "rbl_block_qr: bad arguments");
+        const int B = padded_block((int)b);
+        PadBlock U;
+        U.upload(n, (int)b, B, u);
+        const int grid = rowop_grid(B, n);
+        DevBuf<double> part, G;
+        DevBuf<QrState> qr;
+        part.alloc((size_t)grid * B * B);
+        G.alloc((size_t)B * B);
+        qr.alloc(1);
+        RBL_CUDA(cudaMemset(qr.p, 0, sizeof(QrState)));
+        RowOpArgs g0;
+        g0.n = n; g0.y = U.dev.p; g0.do_gram = 1; g0.partials = part.p;
+        launch_rowop(B, g0, grid, 0);
+        RowOpArgs a;
+        a.n = n; a.y = U.dev.p; a.rinv = qr.p->Rinv; a.write_y = 1; a.do_gram = 1; a.partials = part.p;
+        for (int pass = 1; pass <= 3; ++pass) {
+            launch_reduce_partials(part.p, grid, B * B, G.p, 0);
+            launch_chol(B, G.p, qr.p, pass, n, 1, 1e-12, 0);
+            RowOpArgs ap = a;
+            if (pass == 3) { ap.skip_flag = &qr.p->need_more; ap.do_gram = 0; ap.partials = nullptr; }
+            launch_rowop(B, ap, grid, 0);
+        }
+        RBL_CUDA(cudaDeviceSynchronize());
+        U.download(n, (int)b, B, u);
+        std::unique_ptr<QrState> hq(new QrState);
+        RBL_CUDA(cudaMemcpy(hq.get(), qr.p, sizeof(QrState), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < b; ++r)
+            for (int c = 0; c < b; ++c) r_out[(size_t)r * b + c] = hq->R[(size_t)r * B + c];
+        if (deflated_out)
+            for (int c = 0; c < b; ++c) deflated_out[c] = hq->deflated[c];
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qbuf, double* w0, double* w1,
+               void* c_out, int impl) {
+    return guarded([&] {
+        (void)impl;
+        need_device();
+        if (!qbuf || !w0 || !w1 || b < 1 || b > 32 || n < 1 || m < 1) throw Error(RBL_INVALID, "rbl_reorth: bad arguments");
+        const int B = padded_block((int)b);
+        const size_t ssz = storage_fp32 ? 4 : 8;
+        // pad the stored blocks
+        std::vector<unsigned char> hb((size_t)m * n * B * ssz, 0);
+        for (int64_t j = 0; j < m; ++j)
+            for (int64_t r = 0; r < n; ++r)
+                for (int c = 0; c < b; ++c) {
+                    const size_t s = ((size_t)j * n + r) * b + c, d = ((size_t)j * n + r) * B + c;
+                    if (storage_fp32) ((float*)hb.data())[d] = ((const float*)qbuf)[s];
+                    else ((double*)hb.data())[d] = ((const double*)qbuf)[s];
+                }
+        DevBuf<unsigned char> dbuf, dC, dpart;
+        dbuf.alloc(hb.size());
+        RBL_CUDA(cudaMemcpy(dbuf.p, hb.data(), hb.size(), cudaMemcpyHostToDevice));
+        PadBlock W0, W1;
+        W0.upload(n, (int)b, B, w0);
+        W1.upload(n, (int)b, B, w1);
+        ReorthPlan p = reorth_plan(B, storage_fp32, n, m);
+        dC.alloc((size_t)m * B * 2 * B * ssz);
+        dpart.alloc(p.partial_elems * ssz);
+        launch_reorth_gram(p, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, 0);
+        launch_reorth_update(p, dbuf.p, n * B, dC.p, W0.dev.p, W1.dev.p, nullptr, 0);
+        RBL_CUDA(cudaDeviceSynchronize());
+        W0.download(n, (int)b, B, w0);
+        W1.download(n, (int)b, B, w1);
+        if (c_out) {
+            std::vector<unsigned char> hc((size_t)m * B * 2 * B * ssz);
+            RBL_CUDA(cudaMemcpy(hc.data(), dC.p, hc.size(), cudaMemcpyDeviceToHost));
+            for (int64_t j = 0; j < m; ++j)
+                for (int c = 0; c < b; ++c)
+                    for (int t = 0; t < 2 * b; ++t) {
+                        const int tt = t < b ? t : (B + (t - (int)b));
+                        const size_t s = ((size_t)j * B + c) * 2 * B + tt, d = ((size_t)j * b + c) * 2 * b + t;
+                        if (storage_fp32) ((float*)c_out)[d] = ((float*)hc.data())[s];
+                        else ((double*)c_out)[d] = ((double*)hc.data())[s];
+                    }
+        }
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_ritz(int64_t n, int64_t b, int64_t m, int64_t k, int storage_fp32, const void* qbuf, const double* s,
+             void* v_out) {
+    return guarded([&] {
+        need_device();
+        if (!qbuf || !s || !v_out || b < 1 || b > 32 || n < 1 || m < 1 || k < 1) throw Error(RBL_INVALID, "rbl_ritz: bad arguments");
+        const int B = padded_block((int)b);
+        const size_t ssz = storage_fp32 ? 4 : 8;
+        const int kpad = (int)((k + 15) / 16 * 16);
+        std::vector<unsigned char> hb((size_t)m * n * B * ssz, 0), hs((size_t)m * B * kpad * ssz, 0);
+        for (int64_t j = 0; j < m; ++j)
+            for (int64_t r = 0; r < n; ++r)
+                for (int c = 0; c < b; ++c) {
+                    const size_t so = ((size_t)j * n + r) * b + c, d = ((size_t)j * n + r) * B + c;
+                    if (storage_fp32) ((float*)hb.data())[d] = ((const float*)qbuf)[so];
+                    else ((double*)hb.data())[d] = ((const double*)qbuf)[so];
+                }
+        for (int64_t j = 0; j < m; ++j)
+            for (int c = 0; c < b; ++c)
+                for (int64_t t = 0; t < k; ++t) {
+                    const double v = s[((size_t)j * b + c) * k + t];
+                    const size_t d = ((size_t)j * B + c) * kpad + t;
+                    if (storage_fp32) ((float*)hs.data())[d] = (float)v;
+                    else ((double*)hs.data())[d] = v;
+                }
+        DevBuf<unsigned char> dbuf, dS, dV;
+        dbuf.alloc(hb.size());
+        dS.alloc(hs.size());
+        dV.alloc((size_t)n * k * ssz);
+        RBL_CUDA(cudaMemcpy(dbuf.p, hb.data(), hb.size(), cudaMemcpyHostToDevice));
+        RBL_CUDA(cudaMemcpy(dS.p, hs.data(), hs.size(), cudaMemcpyHostToDevice));
+        launch_ritz(B, storage_fp32, n, m, (int)k, kpad, dbuf.p, n * B, dS.p, dV.p, n, storage_fp32, 0);
+        RBL_CUDA(cudaDeviceSynchronize());
+        RBL_CUDA(cudaMemcpy(v_out, dV.p, (size_t)n * k * ssz, cudaMemcpyDeviceToHost));
+        return (int)RBL_OK;
+    });
+}
+
+// ---- host-only exports -----------------------------------------------------------------------------
+int rbl_band_eig_topk(int64_t N, int64_t kd, const double* ab, int64_t k, const double* bi, int64_t b, double tol,
+                      int threads, double* d_out, double* s_out, double* resid_out, int32_t* converged_out) {
+    return guarded([&] {
+        if (N < 1 || kd < 0 || !ab || k < 1 || k > N) throw Error(RBL_INVALID, "rbl_band_eig_topk: bad arguments");
+        BandSym T;
+        T.from_lapack_lower(N, (int)kd, ab);
+        BandTopK chk;
+        chk.threads = threads > 0 ? threads : 1;
+        std::vector<double> bir;
+        if (bi) {  // column-major in, row-major inside
+            bir.resize((size_t)b * b);
+            for (int r = 0; r < b; ++r)
+                for (int c = 0; c < b; ++c) bir[(size_t)r * b + c] = bi[(size_t)c * b + r];
+        }
+        TopKResult r = chk.check(T, bi ? bir.data() : nullptr, (int)b, k, tol, true);
+        if (!r.have_all) throw Error(RBL_BREAKDOWN, "rbl_band_eig_topk: could not isolate k eigenpairs");
+        for (int64_t j = 0; j < k; ++j) {
+            if (d_out) d_out[j] = r.d[j];
+            if (resid_out) resid_out[j] = r.resid[j];
+        }
+        if (s_out) std::memcpy(s_out, r.s.data(), (size_t)N * k * sizeof(double));
+        if (converged_out) *converged_out = r.converged ? 1 : 0;
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_band_count_below(int64_t N, int64_t kd, const double* ab, double x, int64_t* count_out) {
+    return guarded([&] {
+        if (N < 1 || kd < 0 || !ab || !count_out) throw Error(RBL_INVALID, "rbl_band_count_below: bad arguments");
+        BandSym T;
+        T.from_lapack_lower(N, (int)kd, ab);
+        *count_out = band_count_below(T, x);
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_partition_rows(int64_t n, int world, int64_t* row_starts_out) {
+    return guarded([&] {
+        if (n < 0 || world < 1 || !row_starts_out) throw Error(RBL_INVALID, "rbl_partition_rows: bad arguments");
+        partition_rows(n, world, row_starts_out);
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_halo_plan(int64_t n, int world, const int64_t* row_starts, int rank, int64_t nloc, int64_t nnz_loc,
+                  const int64_t* rowptr, const int64_t* colidx_global, int64_t* n_halo_out, int64_t* halo_cols_out,
+                  int64_t* halo_owner_ptr_out, int32_t* colidx_local_out) {
+    return guarded([&] {
+        if (!row_starts || !rowptr || (nnz_loc > 0 && !colidx_global) || !n_halo_out || rank < 0 || rank >= world)
+            throw Error(RBL_INVALID, "rbl_halo_plan: bad arguments");
+        HaloPlan p;
+        if (!halo_plan(n, world, row_starts, rank, nloc, nnz_loc, rowptr, colidx_global, 0, p))
+            throw Error(RBL_INVALID, "rbl_halo_plan: bad column index or row range");
+        *n_halo_out = (int64_t)p.halo_cols.size();
+        if (halo_cols_out) std::memcpy(halo_cols_out, p.halo_cols.data(), p.halo_cols.size() * 8);
+        if (halo_owner_ptr_out) std::memcpy(halo_owner_ptr_out, p.halo_owner_ptr.data(), p.halo_owner_ptr.size() * 8);
+        if (colidx_local_out) std::memcpy(colidx_local_out, p.colidx_local.data(), p.colidx_local.size() * 4);
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_microbench(int which, int64_t size, int iters, double* result_out) {
+    return guarded([&] {
+        need_device();
+        if (!result_out) throw Error(RBL_INVALID, "rbl_microbench: null result");
+        *result_out = microbench(which, size, iters);
+        if (*result_out < 0) throw Error(RBL_CUDA_ERROR, "rbl_microbench failed");
+        return (int)RBL_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// Device kernels of the RBL hot path (sm_100a) - launch interface.  See DESIGN.md section 4.
+//
+// HBM layout: every dense block is ROW-major [rows][B] with B in {4,8,16,32}
+// (the caller's b is zero-padded up to B; padded columns behave as deflated columns).  The Krylov
+// buffer is a slab of `m` such blocks, stored as float (mixed precision) or double.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace rbl {
+
+inline int padded_block(int b) { return b <= 4 ? 4 : (b <= 8 ? 8 : (b <= 16 ? 16 : 32)); }
+
+// ---- K1 block SpMM ------------------------------------------------------------------------------
+// U[r,:] = sum_p vals[p] * Q[colidx[p],:]   (op 0)      replaces mul!(U,Ag,Qg_d)  RBL_gpu.jl:152,176
+// U[r,:] = sigma*Q[r,:] - (that sum)        (op 1)
+void launch_spmm(int B, int64_t nrows, const int* rowptr, const int* colidx, const double* vals, const double* Q,
+                 double* U, int op, double sigma, cudaStream_t st);
+
+// ---- K2/K3/K4 fused row-wise block operations on fp64 blocks --------------------------------------
+// For every row r of Y (n x B, fp64):
+//     y <- y - x1[r,:] * M1 - x2[r,:] * M2        (either may be absent; M row-major B x B, device)
+//     y <- y * Rinv                               (upper triangular right-multiply, if rinv != null)
+//     Y[r,:] <- y                                 (if write_y)
+//     store[r,:] <- (float|double) y              (Krylov-buffer copy, if store != null)
+//     G += z[r,:]' * y                            (z = gram_z if given, else y itself; if partials != null)
+// G partials are written per CTA to partials[cta][B*B]; reduce with launch_reduce_partials.
+struct RowOpArgs {
+    int64_t n = 0;
+    double* y = nullptr;
+    const double* x1 = nullptr;
+    const double* m1 = nullptr;
+    int m1_transposed = 0;        // use M1' (U -= Q_{i-1} * B_{i-1}')          RBL_gpu.jl:177
+    const double* x2 = nullptr;
+    const double* m2 = nullptr;
+    const double* rinv = nullptr;
+    const int* skip_flag = nullptr;  // device flag: kernel is a no-op when *skip_flag == 0 (optional 3rd QR pass)
+    int write_y = 0;
+    void* store = nullptr;
+    int store_fp32 = 0;
+    const double* gram_z = nullptr;
+    int do_gram = 0;
+    double* partials = nullptr;   // [grid][B*B]
+};
+int rowop_grid(int B, int64_t n);
+void launch_rowop(int B, const RowOpArgs& a, int grid, cudaStream_t st);
+// out[e] = sum_p partials[p][e], e < count   (fixed order: deterministic)
+void launch_reduce_partials(const double* partials, int nparts, int count, double* out, cudaStream_t st);
+
+// ---- block-QR small step (single CTA) -----------------------------------------------------------
+struct QrState {             // lives in device memory
+    double R[32 * 32];       // accumulated R (row-major B x B)
+    double Rinv[32 * 32];    // inverse of the current pass' triangular factor
+    double ref;              // running norm scale for the deflation test
+    int deflated[32];
+    int need_more;           // 1: a further re-orthogonalisation pass is required
+    int ndeflated;
+    int bad;                 // non-finite input seen
+};
+// pass 1: shifted Cholesky of G (+ exact-zero column deflation); pass >= 2: plain Cholesky with
+// deflation of columns whose accumulated R_jj <= defl_rel * ref.  `nrows_global` enters the shift.
+void launch_chol(int B, const double* G, QrState* st, int pass, int64_t nrows_global, int reset_ref, double defl_rel,
+                 cudaStream_t stream);
+
+// ---- K5 partial (full) re-orthogonalisation against the Krylov buffer ----------------------------
+// gram:   C[(j*B+c), t] = sum_r buf_j[r,c] * W[r,t],  W = [w0 | w1] (fp64 active blocks), t < 2B
+// update: w0 -= sum_j buf_j * C_j[:, 0:B],  w1 -= sum_j buf_j * C_j[:, B:2B]; optionally refresh the
+//         buffer copy of w1 (copyto!(Qgpu[i-1],Qg1), RBL_gpu.jl:76).
+// C and the partials are float when the buffer is float, else double.
+struct ReorthPlan {
+    int B = 0, fp32 = 0;
+    int64_t n = 0, m = 0;
+    int chunks = 0, ranges = 0, jt = 0;
+    size_t partial_elems = 0;   // elements of the partials array needed
+};
+ReorthPlan reorth_plan(int B, int fp32, int64_t n, int64_t m);
+size_t reorth_max_partial_elems(int B, int fp32, int64_t n, int64_t m_cap);
+void launch_reorth_gram(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, const double* w0,
+                        const double* w1, void* partials, void* C, cudaStream_t st);
+void launch_reorth_gram_reduce(const ReorthPlan& p, const void* partials, void* C, cudaStream_t st);
+void launch_reorth_update(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, const void* C, double* w0,
+                          double* w1, void* store_w1, cudaStream_t st);
+
+// ---- K6 Ritz vectors -----------------------------------------------------------------------------
+// V[:, t] = sum_j buf_j * S[(j*B .. j*B+B), t];  S device, row-major (m*B) x kpad in the buffer's type;
+// V column-major n x k (ldv), float or double as the buffer.                  RBL_gpu.jl:106-132
+void launch_ritz(int B, int fp32, int64_t n, int64_t m, int k, int kpad, const void* buf, int64_t block_stride_elems,
+                 const void* S, void* V, int64_t ldv, int v_fp32, cudaStream_t st);
+
+// ---- layout / conversion helpers -------------------------------------------------------------------
+// column-major n x b (ld) fp64  ->  row-major n x B fp64 (zero padded)
+void launch_colmajor_to_block(int B, int64_t n, int b, const double* src, int64_t ld, double* dst, cudaStream_t st);
+void launch_block_to_colmajor(int B, int64_t n, int b, const double* src, double* dst, int64_t ld, cudaStream_t st);
+void launch_store_block(int B, int64_t n, const double* src, void* dst, int fp32, cudaStream_t st);
+void launch_load_block(int B, int64_t n, const void* src, int fp32, double* dst, cudaStream_t st);
+void launch_randn(int64_t count, uint64_t seed, uint64_t offset, double* dst, cudaStream_t st);
+void launch_convert_s(int64_t count, const double* src, void* dst, int fp32, cudaStream_t st);
+void launch_gather_rows(int B, int64_t nrows, const int* rows, const double* src, double* dst, cudaStream_t st);
+
+// ---- micro-benchmarks ------------------------------------------------------------------------------
+double microbench(int which, int64_t size, int iters);
+
+}  // namespace rbl

@@ -1,0 +1,105 @@
+// Device-resident driver of the RBL iteration (replaces RBL_gpu / lanczos_iteration / recover_eigvec,
+// Julia/RBL_gpu.jl:134-221).  Host side of the C ABI in include/rbl_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rbl_b200.h"
+#include "band_eig.h"
+#include "comm.h"
+#include "kernels.h"
+
+namespace rbl {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+
+#define RBL_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            throw ::rbl::Error(e__ == cudaErrorMemoryAllocation ? RBL_OOM : RBL_CUDA_ERROR,         \
+                               std::string(#call) + ": " + cudaGetErrorString(e__) + " at " +      \
+                                   __FILE__ + ":" + std::to_string(__LINE__));                      \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t count = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void alloc(size_t n) {
+        release();
+        count = n;
+        if (n) RBL_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        count = 0;
+    }
+};
+
+template <typename T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t count = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    ~PinnedBuf() { release(); }
+    void alloc(size_t n) {
+        release();
+        count = n;
+        if (n) RBL_CUDA(cudaMallocHost((void**)&p, n * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        count = 0;
+    }
+};
+
+}  // namespace rbl
+
+struct rbl_handle {
+    rbl_options opt{};
+    int device = 0;
+    int64_t n = 0;      // global order
+    int64_t row0 = 0;   // first owned row
+    int64_t nloc = 0;   // owned rows
+    int64_t nnz = 0;    // local nonzeros
+    int64_t n_halo = 0;
+    int rank = 0, world = 1;
+    rbl::DevBuf<int> d_rowptr, d_colidx;
+    rbl::DevBuf<double> d_vals;
+    // halo exchange plan
+    std::vector<int64_t> halo_owner_ptr;  // world+1: halo rows received from each owner
+    std::vector<int64_t> send_ptr;        // world+1: rows sent to each peer
+    rbl::DevBuf<int> d_send_rows;         // local row indices, grouped by peer
+    rbl::Comm comm;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> event_pool;
+    double t_h2d_create = 0.0;
+    ~rbl_handle();
+};
+
+namespace rbl {
+
+rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, const int64_t* rowptr,
+                          const int64_t* colidx, const double* vals, int index_base, int rank, int world,
+                          const void* nccl_uid, const rbl_options* opts);
+int solve(rbl_handle* h, int64_t k, int64_t b, const double* omega, bool omega_on_device, double* d_out, void* v_out,
+          bool v_on_device, rbl_stats* stats);
+void default_options(rbl_options* o);
+
+}  // namespace rbl

@@ -1,0 +1,184 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol; host-only entry points
+(band eigen-check, partition / halo plan) against SciPy / the NumPy oracle; no device compute calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from scipy.linalg import eig_banded
+
+from oracle import matrices, partition_oracle, rbl_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(rbl):
+    hdr = open(os.path.join(ROOT, "include", "rbl_b200.h")).read()
+    declared = set(re.findall(r"\b(rbl_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"rbl_options_default" if False else ""}
+    L = rbl.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in rbl_b200.h but not exported"
+    assert declared >= set(rbl.binding.SIGNATURES), "binding lists a symbol the header does not declare"
+
+
+def test_struct_sizes_match_header(rbl):
+    import ctypes as C
+    assert C.sizeof(rbl.RblOptions) == 8 + 8 + 4 * 4 + 8 + 4 * 6 + 4 * 7 + 4  # incl. tail padding to 8
+    o = rbl.binding.default_options()
+    assert (o.max_kryl_sz, o.tol, o.reorth_period, o.check_period) == (1200, 1e-7, 2, 4)  # RBL_gpu.jl:211,189,164,186
+    assert o.precision == 0 and o.op == 0
+
+
+def test_no_device_is_a_loud_error(rbl):
+    if rbl.lib().rbl_device_count() > 0:
+        pytest.skip("a device is present")
+    A = matrices.laplacian_2d(8)
+    with pytest.raises(rbl.RblError) as e:
+        rbl.RBL_gpu(A, 2, 2)
+    assert e.value.status == 7  # RBL_NO_DEVICE: no CPU fallback
+
+
+def test_rejects_bad_arguments(rbl):
+    import ctypes as C
+    L = rbl.lib()
+    h = C.c_void_p()
+    rp = np.array([0, 1], dtype=np.int64)
+    assert L.rbl_create(0, 0, rp.ctypes.data_as(C.POINTER(C.c_int64)), None, None, 0, None, C.byref(h)) == 4
+    assert L.rbl_create(1 << 31, 1, rp.ctypes.data_as(C.POINTER(C.c_int64)), rp.ctypes.data_as(C.POINTER(C.c_int64)),
+                        np.zeros(1).ctypes.data_as(C.POINTER(C.c_double)), 0, None, C.byref(h)) == 4
+    assert b"2^31" in L.rbl_last_error()
+
+
+def _band(M, kd):
+    N = M.shape[0]
+    ab = np.zeros((kd + 1, N))
+    for d in range(kd + 1):
+        ab[d, :N - d] = np.diag(M, -d)
+    return ab
+
+
+def _topk_ref(ab, k):
+    w = eig_banded(ab, lower=True, eigvals_only=True)
+    return w[np.argsort(-np.abs(w), kind="stable")][:k]
+
+
+@pytest.mark.parametrize("N,kd,k,seed", [(40, 2, 5, 0), (200, 4, 16, 1), (600, 16, 60, 2), (333, 5, 333 // 3, 3)])
+def test_band_eig_topk_random(rbl, N, kd, k, seed):
+    rng = np.random.default_rng(seed)
+    M = np.zeros((N, N))
+    for d in range(kd + 1):
+        v = rng.standard_normal(N - d)
+        M += np.diag(v, d) + (np.diag(v, -d) if d else 0)
+    ab = _band(M, kd)
+    D, S, res, conv = rbl.band_eig_topk(ab, k, threads=2)
+    ref = _topk_ref(ab, k)
+    sc = np.max(np.abs(ref))
+    assert np.max(np.abs(np.abs(D) - np.abs(ref))) < 1e-12 * sc
+    assert np.all(np.abs(D)[:-1] >= np.abs(D)[1:] - 1e-12 * sc)          # descending |lambda| (RBL.jl:116)
+    assert np.max(np.linalg.norm(M @ S - S * D[None, :], axis=0)) < 1e-11 * sc
+    assert np.max(np.abs(S.T @ S - np.eye(k))) < 1e-8
+
+
+def test_band_eig_multiplicities_and_zero_rows(rbl):
+    rng = np.random.default_rng(5)
+    kd = 4
+    blk = rng.standard_normal((50, 50))
+    blk = np.triu(np.tril(blk + blk.T, kd), -kd)
+    M = np.zeros((230, 230))
+    for i in range(4):
+        M[i * 50:(i + 1) * 50, i * 50:(i + 1) * 50] = blk          # every eigenvalue 4-fold; trailing rows zero
+    ab = _band(M, kd)
+    D, S, res, conv = rbl.band_eig_topk(ab, 24)
+    ref = _topk_ref(ab, 24)
+    assert np.max(np.abs(np.sort(np.abs(D)) - np.sort(np.abs(ref)))) < 1e-12 * np.max(np.abs(ref))
+    assert np.max(np.abs(S.T @ S - np.eye(24))) < 1e-9
+    assert np.max(np.linalg.norm(M @ S - S * D[None, :], axis=0)) < 1e-11 * np.max(np.abs(ref))
+
+
+def test_band_count_is_sturm_count(rbl):
+    rng = np.random.default_rng(9)
+    N, kd = 150, 6
+    M = np.zeros((N, N))
+    for d in range(kd + 1):
+        v = rng.standard_normal(N - d)
+        M += np.diag(v, d) + (np.diag(v, -d) if d else 0)
+    ab = _band(M, kd)
+    w = np.linalg.eigvalsh(M)
+    for x in np.r_[np.linspace(w[0] - 1, w[-1] + 1, 23), 0.5 * (w[10] + w[11])]:
+        assert rbl.band_count_below(ab, float(x)) == int(np.sum(w < x))
+
+
+def test_check_decision_matches_dsbev_on_lanczos_T(rbl):
+    """Same accept/reject decision as dsbev + sort_eig_abs + check_convergence (common.jl:36-65) at every
+    check of an oracle run, on the oracle's own T and B_i."""
+    N, k, b = 24, 5, 3
+    A = matrices.shifted(matrices.laplacian_2d(N), 8.0)
+    Om = np.random.default_rng(11).standard_normal((N * N, b))
+    Q = []
+    Qi = np.linalg.qr(A @ Om)[0]
+    # replay lanczos_iteration and intercept every check
+    decisions = []
+    orig = rbl_oracle.check_convergence
+
+    def spy(Bi, V, bb, kk, tol):
+        ok = orig(Bi, V, bb, kk, tol)
+        decisions.append((Bi.copy(), ok))
+        return ok
+
+    rbl_oracle.check_convergence = spy
+    try:
+        Ts = []
+        orig_dsbev = rbl_oracle.dsbev
+
+        def spy_dsbev(T):
+            Ts.append(T.copy())
+            return orig_dsbev(T)
+
+        rbl_oracle.dsbev = spy_dsbev
+        rbl_oracle.lanczos_iteration(A, k, b, 1400, Qi, Q)
+    finally:
+        rbl_oracle.check_convergence = orig
+        rbl_oracle.dsbev = orig_dsbev
+    assert len(Ts) == len(decisions) and decisions[-1][1]
+    for T, (Bi, ok) in zip(Ts, decisions):
+        D, S, res, conv = rbl.band_eig_topk(T, k, Bi=Bi, tol=1e-7)
+        w, z = orig_dsbev(T)
+        Dr, Vr = rbl_oracle.sort_eig_abs(w, z, k)
+        assert np.max(np.abs(D - Dr[::-1])) < 1e-11 * 8
+        rr = rbl_oracle.residual_bounds(Bi, Vr, b)[::-1]
+        # decisions agree unless a residual bound sits within rounding of the tolerance
+        if np.min(np.abs(rr - 1e-7)) > 1e-9:
+            assert conv == ok
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_partition_and_halo_plan_bit_exact(rbl, world):
+    A = matrices.laplacian_3d(9).tocsr()
+    A.sort_indices()
+    n = A.shape[0]
+    rs = rbl.partition_rows(n, world)
+    assert np.array_equal(rs, partition_oracle.partition_rows(n, world))
+    for rank in range(world):
+        Al = A[rs[rank]:rs[rank + 1], :]
+        halo, optr, loc = rbl.halo_plan(n, world, rs, rank, Al.indptr, Al.indices)
+        h2, o2, l2 = partition_oracle.halo_plan(n, world, rs, rank, Al.indptr, Al.indices)
+        assert np.array_equal(halo, h2) and np.array_equal(optr, o2) and np.array_equal(loc, l2)
+        # the plan reproduces the SpMM: local rows times [own | halo] rows of Q equals the global product
+        Q = np.random.default_rng(rank).standard_normal((n, 4))
+        Qext = np.vstack([Q[rs[rank]:rs[rank + 1]], Q[halo]])
+        Aloc = sp.csr_matrix((Al.data, loc, Al.indptr), shape=(Al.shape[0], Qext.shape[0]))
+        assert np.array_equal(Aloc @ Qext, (A @ Q)[rs[rank]:rs[rank + 1]]) or np.allclose(Aloc @ Qext, (A @ Q)[rs[rank]:rs[rank + 1]], rtol=0, atol=1e-13)
+
+
+def test_halo_plan_random_sparsity(rbl):
+    A = matrices.erdos_renyi_sym(500, 8, seed=4)
+    A.sort_indices()
+    rs = rbl.partition_rows(500, 4)
+    for rank in range(4):
+        Al = A[rs[rank]:rs[rank + 1], :]
+        out = rbl.halo_plan(500, 4, rs, rank, Al.indptr, Al.indices)
+        ref = partition_oracle.halo_plan(500, 4, rs, rank, Al.indptr, Al.indices)
+        for a, b_ in zip(out, ref):
+            assert np.array_equal(a, b_)
