@@ -1,0 +1,128 @@
+"""Kernel-level parity on the GPU, through the C ABI, against NumPy/SciPy on the same seeded inputs."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import matrices
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("b", [1, 2, 4, 5, 8, 16, 32])
+def test_spmm_matches_scipy(gpu, b):
+    A = matrices.laplacian_3d(14).tocsr()
+    Q = np.random.default_rng(b).standard_normal((A.shape[0], b))
+    U = gpu.k_spmm(A, Q)
+    ref = A @ Q
+    # summation in CSR order with fma: a few ulp of the row sum of |a||q|
+    bound = 8 * np.finfo(float).eps * (abs(A) @ np.abs(Q))
+    assert np.all(np.abs(U - ref) <= bound + 1e-300)
+
+
+def test_spmm_shift_and_irregular_rows(gpu):
+    A = matrices.erdos_renyi_sym(3000, 24, seed=1)
+    A = A + sp.diags(np.arange(3000.0))          # also rows with many entries and an empty-ish structure
+    A = sp.csr_matrix(A)
+    A[17, :] = 0
+    A[:, 17] = 0
+    A.eliminate_zeros()                           # an empty row
+    Q = np.random.default_rng(2).standard_normal((3000, 16))
+    U = gpu.k_spmm(A, Q, op=1, sigma=3.5)
+    ref = 3.5 * Q - A @ Q
+    assert np.max(np.abs(U - ref)) <= 1e-12 * np.max(np.abs(ref))
+    assert np.array_equal(U[17], 3.5 * Q[17])
+
+
+def test_spmm_dense_operator(gpu):
+    rng = np.random.default_rng(3)
+    M = rng.standard_normal((150, 150)); M = M + M.T
+    Q = rng.standard_normal((150, 4))
+    U = gpu.k_spmm(M, Q)
+    assert np.max(np.abs(U - M @ Q)) < 1e-12 * np.max(np.abs(M @ Q))
+
+
+@pytest.mark.parametrize("n,b", [(1, 4), (127, 3), (4096, 16), (50001, 16), (20000, 32), (9999, 8), (777, 1)])
+def test_gram(gpu, n, b):
+    rng = np.random.default_rng(n + b)
+    X = rng.standard_normal((n, b)); Y = rng.standard_normal((n, b))
+    C = gpu.k_gram(X, Y)
+    ref = X.T @ Y
+    assert np.max(np.abs(C - ref)) <= 1e-13 * n ** 0.5 * max(1.0, np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("n,b", [(5000, 16), (20011, 4), (3000, 5), (8192, 32), (1000, 1)])
+def test_block_qr_well_conditioned(gpu, n, b):
+    rng = np.random.default_rng(n)
+    U = rng.standard_normal((n, b)) * (10.0 ** rng.uniform(-3, 3, b))[None, :]
+    Q, R, d = gpu.k_block_qr(U)
+    assert not d.any()
+    assert np.allclose(np.triu(R), R)
+    assert np.max(np.abs(Q.T @ Q - np.eye(b))) < 1e-13
+    assert np.max(np.abs(Q @ R - U)) < 1e-12 * np.max(np.abs(U))
+    # same factor as Householder QR up to column signs
+    Rh = np.linalg.qr(U, mode="r")
+    assert np.allclose(np.abs(np.diag(R)), np.abs(np.diag(Rh)), rtol=1e-10)
+
+
+def test_block_qr_ill_conditioned_and_deflation(gpu):
+    rng = np.random.default_rng(0)
+    n, b = 6000, 8
+    Qo = np.linalg.qr(rng.standard_normal((n, b)))[0]
+    U = Qo @ np.diag(10.0 ** -np.arange(0, 16, 2.0)) @ np.linalg.qr(rng.standard_normal((b, b)))[0]  # cond 1e14
+    Q, R, d = gpu.k_block_qr(U)
+    keep = ~d.astype(bool)
+    assert keep.sum() >= 6
+    G = Q[:, keep].T @ Q[:, keep]
+    assert np.max(np.abs(G - np.eye(keep.sum()))) < 1e-10
+    assert np.max(np.abs(Q @ R - U)) < 1e-11
+    # exact rank deficiency: duplicated and zero columns are deflated to exact zeros (SURVEY H4 / step_dec fixture)
+    U2 = rng.standard_normal((n, 5))
+    U2[:, 3] = U2[:, 1] * 2.0 - U2[:, 0]
+    U2[:, 4] = 0.0
+    Q2, R2, d2 = gpu.k_block_qr(U2)
+    assert d2.tolist() == [0, 0, 0, 1, 1]
+    assert np.all(Q2[:, 3] == 0) and np.all(Q2[:, 4] == 0)
+    assert np.max(np.abs(Q2 @ R2 - U2)) < 1e-10 * np.max(np.abs(U2))
+    assert np.max(np.abs(Q2[:, :3].T @ Q2[:, :3] - np.eye(3))) < 1e-13
+
+
+def _krylov_like(n, b, m, rng):
+    Qall = np.linalg.qr(rng.standard_normal((n, (m + 2) * b)))[0]
+    blocks = Qall[:, :m * b].reshape(n, m, b).transpose(1, 0, 2).copy()
+    W0 = Qall[:, m * b:(m + 1) * b] + 1e-3 * Qall[:, :b] @ rng.standard_normal((b, b))
+    W1 = Qall[:, (m + 1) * b:] + 1e-3 * Qall[:, b:2 * b] @ rng.standard_normal((b, b))
+    return blocks, W0.copy(), W1.copy()
+
+
+@pytest.mark.parametrize("n,b,m,fp32", [(4000, 16, 5, False), (4000, 16, 5, True), (10007, 16, 70, True),
+                                         (2500, 4, 300, True), (2500, 4, 30, False), (3001, 8, 40, True),
+                                         (3001, 32, 12, True), (1500, 32, 9, False), (900, 5, 7, False), (64, 16, 1, True)])
+def test_reorth_block_cgs(gpu, n, b, m, fp32):
+    rng = np.random.default_rng(n + m)
+    blocks, W0, W1 = _krylov_like(n, b, m, rng)
+    w0, w1, C = gpu.k_reorth(blocks, W0, W1, fp32)
+    dt = np.float32 if fp32 else np.float64
+    Qs = blocks.astype(dt).astype(np.float64)              # what the buffer holds
+    Qm = Qs.transpose(1, 0, 2).reshape(n, m * b)
+    W = np.hstack([W0, W1])
+    Cref = Qm.T @ W
+    tolC = (3e-6 if fp32 else 1e-13) * max(1.0, np.max(np.abs(Cref))) * 10
+    assert np.max(np.abs(C.astype(np.float64) - Cref)) < tolC
+    Wref = W - Qm @ Cref
+    tolW = 2e-6 if fp32 else 1e-13
+    assert np.max(np.abs(np.hstack([w0, w1]) - Wref)) < tolW
+    # orthogonality against the stored blocks after the pass
+    assert np.max(np.abs(Qm.T @ np.hstack([w0, w1]))) < (5e-6 if fp32 else 1e-12)
+
+
+@pytest.mark.parametrize("n,b,m,k,fp32", [(3000, 16, 6, 100, True), (3000, 16, 6, 100, False), (5001, 4, 50, 10, True),
+                                           (2000, 32, 5, 50, False), (1000, 8, 9, 64, True), (700, 5, 4, 7, False)])
+def test_ritz(gpu, n, b, m, k, fp32):
+    rng = np.random.default_rng(k)
+    blocks = rng.standard_normal((m, n, b))
+    S = rng.standard_normal((m * b, k))
+    V = gpu.k_ritz(blocks, S, fp32)
+    dt = np.float32 if fp32 else np.float64
+    ref = blocks.astype(dt).astype(np.float64).transpose(1, 0, 2).reshape(n, m * b) @ S.astype(dt).astype(np.float64)
+    tol = (2e-5 if fp32 else 1e-12) * np.max(np.abs(ref))
+    assert np.max(np.abs(V.astype(np.float64) - ref)) < tol

@@ -1,0 +1,114 @@
+"""End-to-end parity of the device path (through the C ABI / RBL_gpu mirror) against the oracle:
+the reference's own known-answer fixtures, and the north-star bars on reduced BASELINE configs
+(eigenvalues rel 1e-8 vs the oracle, Ritz residual <= 1e-6 ||A||, orthogonality of V)."""
+import numpy as np
+import pytest
+
+from oracle import matrices, rbl_oracle
+
+pytestmark = pytest.mark.gpu
+BAR = 1e-13  # Unit Testing/*_dec.jl:5
+
+
+@pytest.mark.parametrize("gen,n", [(matrices.slow_decay, 100), (matrices.slow_decay, 500), (matrices.slow_decay, 900),
+                                    (matrices.moderate_decay, 300), (matrices.moderate_decay, 700),
+                                    (matrices.step_decay, 100000), (matrices.step_decay, 900000)])
+def test_reference_fixtures_on_device(gpu, gen, n):
+    """test.jl:10-50 with RBL replaced by the device path (k = b = 5, fp64 as shipped)."""
+    A, eig = gen(n, 5)
+    Om = np.random.default_rng(n).standard_normal((n, 5))
+    d, V, st = gpu.RBL(A, 5, 5, Omega=Om, return_stats=True)
+    assert st.converged
+    assert np.linalg.norm((d - eig) / eig) < BAR
+    assert np.max(rbl_oracle.ritz_residuals(A, d, V)) < 1e-6
+
+
+@pytest.mark.parametrize("precision", ["fp64", "mixed"])
+@pytest.mark.parametrize("async_check", [False, True])
+def test_config1_reduced_lowest_pairs(gpu, precision, async_check):
+    """2-D 5-point Laplacian (config 1 at 60x60), 10 lowest pairs as the largest of 8I - A, b = 4."""
+    N, k, b = 60, 10, 4
+    L = matrices.laplacian_2d(N)
+    A = matrices.shifted(L, 8.0)
+    Om = np.random.default_rng(1).standard_normal((N * N, b))
+    D, V, st = gpu.RBL_gpu(L, k, b, Omega=Om, shift=8.0, precision=precision, async_check=async_check,
+                           max_kryl_sz=1400, return_stats=True)
+    Do, Vo, det = rbl_oracle.RBL(A, k, b, Om, return_details=True)
+    exact = 8.0 - matrices.laplacian_eigs(N, 2, k)
+    assert st.converged
+    assert np.max(np.abs(D - Do) / np.abs(Do)) < 1e-8            # north star: rel 1e-8 vs the reference restatement
+    assert np.max(np.abs(D - exact) / exact) < 1e-8
+    assert np.max(rbl_oracle.ritz_residuals(A, D, V, norm_a=8.0)) < 1e-6
+    assert abs(st.iterations - det["stats"].iterations) <= 8      # same stopping check, +- two checks
+    G = V.T.astype(np.float64) @ V.astype(np.float64)
+    assert np.max(np.abs(G - np.eye(k))) < (1e-5 if precision == "mixed" else 1e-9)
+    # subspace agreement with the oracle's Ritz vectors (degenerate pairs: compare projectors)
+    P = Vo.T @ V
+    assert np.min(np.linalg.svd(P, compute_uv=False)) > 1 - 1e-6
+
+
+def test_async_equals_sync(gpu):
+    N, k, b = 40, 8, 4
+    L = matrices.laplacian_2d(N)
+    Om = np.random.default_rng(5).standard_normal((N * N, b))
+    r1 = gpu.RBL_gpu(L, k, b, Omega=Om, shift=8.0, async_check=False, return_stats=True)
+    r2 = gpu.RBL_gpu(L, k, b, Omega=Om, shift=8.0, async_check=True, return_stats=True)
+    assert r1[2].iterations == r2[2].iterations
+    assert np.max(np.abs(r1[0] - r2[0])) < 1e-12
+    assert r2[2].iterations_run >= r2[2].iterations
+
+
+@pytest.mark.parametrize("precision", ["fp64", "mixed"])
+def test_config2_reduced_3d(gpu, precision):
+    """3-D 7-point Laplacian (config 2 at 24^3), 30 lowest pairs via 12I - A, b = 16."""
+    N, k, b = 24, 30, 16
+    L = matrices.laplacian_3d(N)
+    A = matrices.shifted(L, 12.0)
+    Om = np.random.default_rng(2).standard_normal((N ** 3, b))
+    D, V, st = gpu.RBL_gpu(L, k, b, Omega=Om, shift=12.0, precision=precision, max_kryl_sz=3000, return_stats=True)
+    exact = 12.0 - matrices.laplacian_eigs(N, 3, k)
+    assert st.converged
+    assert np.max(np.abs(D - exact) / exact) < 1e-8
+    assert np.max(rbl_oracle.ritz_residuals(A, D, V, norm_a=12.0)) < 1e-6
+    Do, Vo = rbl_oracle.RBL(A, k, b, Om, max_kryl_sz=3000)
+    assert np.max(np.abs(D - Do) / np.abs(Do)) < 1e-8
+
+
+def test_config3_reduced_er_largest_magnitude(gpu):
+    """Symmetric Erdos-Renyi (config 3 reduced): k extreme eigenvalues of both signs, b = 32."""
+    n, k, b = 6000, 12, 32
+    A = matrices.erdos_renyi_sym(n, 32, seed=3)
+    Om = np.random.default_rng(3).standard_normal((n, b))
+    D, V, st = gpu.RBL_gpu(A, k, b, Omega=Om, return_stats=True, max_kryl_sz=4000)
+    Do, Vo = rbl_oracle.RBL(A, k, b, Om, max_kryl_sz=4000)
+    assert st.converged
+    assert (D > 0).any() and (D < 0).any()
+    assert np.max(np.abs(D - Do) / np.abs(Do)) < 1e-8
+    assert np.all(np.abs(D)[:-1] >= np.abs(D)[1:])
+    assert np.max(rbl_oracle.ritz_residuals(A, D, V)) < 1e-6
+
+
+def test_dense_operator_like_images_jl(gpu):
+    """images.jl:14-30 style: eigenpairs of a dense B'B with block size 1."""
+    rng = np.random.default_rng(8)
+    Bm = rng.standard_normal((300, 120)) @ np.diag(0.9 ** np.arange(120))
+    M = Bm.T @ Bm
+    D, V = gpu.RBL_gpu(M, 6, 1, Omega=rng.standard_normal((120, 1)))
+    w = np.linalg.eigvalsh(M)[::-1][:6]
+    assert np.max(np.abs(D - w) / w) < 1e-8
+
+
+def test_not_converged_status_and_cap(gpu):
+    L = matrices.laplacian_2d(40)
+    with pytest.raises(gpu.RblError) as e:
+        gpu.RBL_gpu(L, 10, 4, shift=8.0, max_kryl_sz=64)
+    assert e.value.status == 1
+    D, V, st = gpu.RBL_gpu(L, 10, 4, shift=8.0, max_kryl_sz=64, allow_not_converged=True, return_stats=True)
+    assert not st.converged and st.kryl_sz <= 64
+
+
+def test_device_rng_start_block(gpu):
+    """Omega = nothing: the library draws the start block itself (CUDA.randn, RBL_gpu.jl:213)."""
+    A, eig = matrices.slow_decay(400, 5)
+    d, V = gpu.RBL_gpu(A, 5, 5)
+    assert np.linalg.norm((d - eig) / eig) < 1e-12
