@@ -5,6 +5,6 @@ Host-side mirror (Python, ctypes) of the Julia interface of Iasonaspg/GPU-Random
 ``lib/librbl_b200.so`` (hand-written sm_100a kernels + C++ host driver); there is no CPU fallback.
 """
 from .binding import (RblError, RblOptions, RblStats, Solver, lib, lib_path, load_library,  # noqa: F401
-                      band_eig_topk, band_count_below, halo_plan, partition_rows, microbench,
+                      band_eig_topk, band_count_below, Checker, halo_plan, partition_rows, microbench,
                       k_spmm, k_gram, k_block_qr, k_reorth, k_ritz)
 from .rbl import RBL, RBL_gpu, rbl_solve_sharded  # noqa: F401

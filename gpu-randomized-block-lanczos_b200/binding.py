@@ -76,6 +76,10 @@ SIGNATURES = {
     "rbl_ritz": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, _PD, C.c_void_p]),
     "rbl_band_eig_topk": (C.c_int, [C.c_int64, C.c_int64, _PD, C.c_int64, _PD, C.c_int64, C.c_double, C.c_int, _PD,
                                     _PD, _PD, _P32]),
+    "rbl_checker_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "rbl_checker_check": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _PD, C.c_int64, _PD, C.c_int64, C.c_double, C.c_int,
+                                    _PD, _PD, _PD, _P32, _P32, _P64]),
+    "rbl_checker_destroy": (C.c_int, [C.c_void_p]),
     "rbl_band_count_below": (C.c_int, [C.c_int64, C.c_int64, _PD, C.c_double, _P64]),
     "rbl_partition_rows": (C.c_int, [C.c_int64, C.c_int, _P64]),
     "rbl_halo_plan": (C.c_int, [C.c_int64, C.c_int, _P64, C.c_int, C.c_int64, C.c_int64, _P64, _P64, _P64, _P64, _P64,
@@ -283,6 +287,36 @@ def band_eig_topk(ab, k: int, Bi=None, tol: float = 1e-7, threads: int = 1):
     _check(lib().rbl_band_eig_topk(N, kd, _pd(ab), k, _pd(bi) if bi is not None else None, b, tol, threads, _pd(D),
                                    _pd(S), _pd(res), C.byref(conv)))
     return D, S, res, bool(conv.value)
+
+
+class Checker:
+    """Stateful host eigen-check (the object the solver keeps between convergence checks)."""
+
+    def __init__(self, threads: int = 1):
+        self._c = C.c_void_p()
+        _check(lib().rbl_checker_create(threads, C.byref(self._c)))
+
+    def check(self, ab, k: int, Bi, tol: float = 1e-7, force_full: bool = False):
+        ab = np.asfortranarray(ab, dtype=np.float64)
+        kd, N = ab.shape[0] - 1, ab.shape[1]
+        bi = np.asfortranarray(Bi, dtype=np.float64)
+        D = np.zeros(k); S = np.zeros((N, k), order="F"); res = np.zeros(k)
+        conv = C.c_int32(); have = C.c_int32(); st = np.zeros(2, dtype=np.int64)
+        _check(lib().rbl_checker_check(self._c, N, kd, _pd(ab), k, _pd(bi), bi.shape[0], tol, int(force_full), _pd(D),
+                                       _pd(S), _pd(res), C.byref(conv), C.byref(have), _p64(st)))
+        return dict(converged=bool(conv.value), have_all=bool(have.value), D=D, S=S, resid=res,
+                    factorizations=int(st[0]), full=bool(st[1]))
+
+    def close(self):
+        if self._c:
+            lib().rbl_checker_destroy(self._c)
+            self._c = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def band_count_below(ab, x: float) -> int:

@@ -557,6 +557,13 @@ double resid_bound(const double* bi, int b, const std::vector<double>& s) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ BandTopK
+// Decision procedure (identical outcome to dsbev + sort_eig_abs + check_convergence, common.jl:36-65):
+//   "not converged" needs ONE Ritz pair among the k largest |lambda| whose bound ||B_i s_last|| exceeds tol;
+//   "converged" needs all k of them.
+//   stage 1  follow the witness pairs of the previous check by Rayleigh-quotient iteration (a few factorisations)
+//   stage 2  isolate the pair(s) at rank k (the slowest to converge) from a bracket that starts at the previous
+//            k-th value (the k-th largest |lambda| never decreases when T grows: Cauchy interlacing)
+//   stage 3  all k pairs by spectrum slicing (only when stages 1-2 found nothing unconverged)
 TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k, double tol, bool force_full) {
     TopKResult R;
     R.N = T.N;
@@ -564,79 +571,136 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     const double tn = std::max(T.norm_inf, 1e-300);
     Work wk;
     if (k > N) k = N;
+    const double g = tn * (1.0 + 1e-12) + 1e-300;
 
-    auto count_abs_above = [&](double x) -> int64_t {  // #{ |lambda| > x }, x >= 0
+    // #{ |lambda| > x } for x >= 0, remembering the two one-sided Sturm counts
+    struct Cnt { int64_t below_pos, below_neg, above; };
+    double neg_free_from = -1.0;  // for x >= this value the negative side is known to be empty (within this check)
+    auto count_abs_above = [&](double x) -> Cnt {
+        Cnt c;
         wk.lu.factor(T, x);
         ++wk.nfac;
-        int64_t above = N - wk.lu.nneg;
-        wk.lu.factor(T, -x);
-        ++wk.nfac;
-        return above + wk.lu.nneg;
+        c.below_pos = wk.lu.nneg;
+        if (neg_free_from >= 0.0 && x >= neg_free_from) {
+            c.below_neg = 0;
+        } else {
+            wk.lu.factor(T, -x);
+            ++wk.nfac;
+            c.below_neg = wk.lu.nneg;
+            if (c.below_neg == 0) neg_free_from = x;
+        }
+        c.above = (N - c.below_pos) + c.below_neg;
+        return c;
+    };
+    auto finish = [&](bool conv) {
+        R.converged = conv;
+        R.factorizations = wk.nfac;
+        total_factorizations += wk.nfac;
+        return R;
     };
 
-    // ---- cheap path: follow the witness pair of the previous check -------------------------------
-    if (!force_full && !wit_.empty() && (int64_t)wit_.size() <= N && bi) {
-        std::vector<double> x(N, 0.0);
-        std::copy(wit_.begin(), wit_.end(), x.begin());
-        double nn = nrm2(x.data(), N);
-        if (nn > 0) {
+    // ---- stage 1: witnesses of the previous check -------------------------------------------------------
+    if (!force_full && bi) {
+        for (size_t wi = 0; wi < wit_.size(); ++wi) {
+            if ((int64_t)wit_[wi].size() > N) continue;
+            std::vector<double> x(N, 0.0);
+            std::copy(wit_[wi].begin(), wit_[wi].end(), x.begin());
+            double nn = nrm2(x.data(), N);
+            if (!(nn > 0)) continue;
             scal(x.data(), 1.0 / nn, N);
-            double th = wit_theta_, rs = 0;
-            if (rqi(T, wk, th, x, rs, 0.0, 0.0, 6, 2e-15)) {
-                double rho = resid_bound(bi, b, x);
-                if (rho > tol) {
-                    // is it still one of the k largest |lambda| ?  fewer than k strictly larger ones.
-                    double delta = std::max(1e-12 * std::fabs(th), 1e-14 * tn);
-                    int64_t larger = count_abs_above(std::fabs(th) + delta);
-                    if (larger < k) {
-                        wit_ = x;
-                        wit_theta_ = th;
-                        R.converged = false;
-                        R.factorizations = wk.nfac;
-                        total_factorizations += wk.nfac;
+            double th = wit_theta_[wi], rs = 0;
+            if (!rqi(T, wk, th, x, rs, 0.0, 0.0, 6, 2e-15)) continue;
+            const double rho = resid_bound(bi, b, x);
+            if (rho <= tol) continue;
+            const double delta = std::max(1e-12 * std::fabs(th), 1e-14 * tn);
+            const Cnt c = count_abs_above(std::fabs(th) + delta);
+            if (c.above < k) {  // fewer than k strictly larger: the pair is one of the k wanted and is not converged
+                wit_[0] = x;
+                wit_theta_[0] = th;
+                wit_.resize(1);
+                wit_theta_.resize(1);
+                kth_est_ = std::max(kth_est_, 0.0);
+                if (verbose > 1)
+                    std::fprintf(stderr, "[rbl] check N=%lld witness theta=%.12g rho=%.3e (nfac=%d)\n", (long long)N, th,
+                                 rho, wk.nfac);
+                return finish(false);
+            }
+        }
+    }
+
+    // ---- stage 2: the pair(s) at rank k -----------------------------------------------------------------
+    if (!force_full && bi && kth_est_ > 0.0) {
+        double x_lo = std::max(0.0, kth_est_ - std::max(1e-10 * kth_est_, 1e-13 * tn));
+        Cnt c_lo = count_abs_above(x_lo);
+        if (c_lo.above >= k) {
+            double h = std::max(kth_step_, 1e-7 * tn);
+            double x_hi = std::min(g, x_lo + h);
+            Cnt c_hi = count_abs_above(x_hi);
+            while (c_hi.above >= k && x_hi < g) {
+                x_lo = x_hi;
+                c_lo = c_hi;
+                h *= 4.0;
+                x_hi = std::min(g, x_lo + h);
+                c_hi = count_abs_above(x_hi);
+            }
+            if (c_hi.above < k) {
+                while (c_lo.above - c_hi.above > 6 && (x_hi - x_lo) > 1e-12 * tn) {
+                    const double xm = 0.5 * (x_lo + x_hi);
+                    const Cnt cm = count_abs_above(xm);
+                    if (cm.above >= k) { x_lo = xm; c_lo = cm; } else { x_hi = xm; c_hi = cm; }
+                }
+                std::vector<Interval> roots;
+                roots.push_back(Interval{x_lo, x_hi, c_lo.below_pos, c_hi.below_pos});
+                if (c_lo.below_neg > c_hi.below_neg) roots.push_back(Interval{-x_hi, -x_lo, c_hi.below_neg, c_lo.below_neg});
+                std::vector<Pair> pairs;
+                int64_t nf = 0;
+                slice(T, roots, 1, pairs, nf);
+                wk.nfac += (int)nf;
+                std::stable_sort(pairs.begin(), pairs.end(),
+                                 [](const Pair& a, const Pair& b2) { return std::fabs(a.theta) > std::fabs(b2.theta); });
+                const int64_t in_topk = k - c_hi.above;  // the first in_topk of them are among the k wanted
+                if ((int64_t)pairs.size() == c_lo.above - c_hi.above && in_topk >= 1) {
+                    const double th_k = std::fabs(pairs[in_topk - 1].theta);
+                    kth_step_ = std::max(2.0 * (th_k - kth_est_), 1e-7 * tn);
+                    kth_est_ = th_k;
+                    double worst = -1;
+                    int64_t wj = -1;
+                    for (int64_t j = 0; j < in_topk; ++j) {
+                        const double rho = resid_bound(bi, b, pairs[j].v);
+                        if (rho > worst) { worst = rho; wj = j; }
+                    }
+                    if (worst > tol) {
+                        wit_.assign(1, pairs[wj].v);
+                        wit_theta_.assign(1, pairs[wj].theta);
                         if (verbose > 1)
-                            std::fprintf(stderr, "[rbl] check N=%lld witness theta=%.12g rho=%.3e (nfac=%d)\n",
-                                         (long long)N, th, rho, wk.nfac);
-                        return R;
+                            std::fprintf(stderr, "[rbl] check N=%lld rank-k pair theta=%.12g rho=%.3e (nfac=%d)\n",
+                                         (long long)N, pairs[wj].theta, worst, wk.nfac);
+                        return finish(false);
                     }
                 }
             }
         }
     }
 
-    // ---- full check: all k pairs of largest |lambda| ---------------------------------------------
+    // ---- stage 3: all k pairs of largest |lambda| --------------------------------------------------------
     ++full_checks;
-    const double g = tn * (1.0 + 1e-12) + 1e-300;
     // bracket the k-th largest |lambda|: largest x_lo with #{|lambda| > x_lo} >= k (within a modest surplus)
     double x_lo = 0.0, x_hi = g;
-    int64_t c_lo = N;  // #{|lambda| > 0} upper bound (zeros are not counted exactly; harmless surplus)
+    Cnt c_lo{0, 0, N};
+    bool have_clo = false;
     for (int it = 0; it < 60; ++it) {
-        if (c_lo >= k && c_lo <= k + std::max<int64_t>(2, k / 8)) break;
+        if (c_lo.above >= k && c_lo.above <= k + std::max<int64_t>(2, k / 8)) break;
         if (x_hi - x_lo <= 1e-13 * tn) break;
-        double xm = 0.5 * (x_lo + x_hi);
-        int64_t cm = count_abs_above(xm);
-        if (cm >= k) {
-            x_lo = xm;
-            c_lo = cm;
-        } else {
-            x_hi = xm;
-        }
+        const double xm = 0.5 * (x_lo + x_hi);
+        const Cnt cm = count_abs_above(xm);
+        if (cm.above >= k) { x_lo = xm; c_lo = cm; have_clo = true; } else { x_hi = xm; }
     }
     std::vector<Interval> roots;
-    {
-        // positive side (x_lo, g), negative side (-g, -x_lo)
-        wk.lu.factor(T, x_lo);
-        ++wk.nfac;
-        int64_t below_pos = wk.lu.nneg;
-        roots.push_back(Interval{x_lo, g, below_pos, N});
-        if (x_lo > 0) {
-            wk.lu.factor(T, -x_lo);
-            ++wk.nfac;
-            roots.push_back(Interval{-g, -x_lo, 0, wk.lu.nneg});
-        } else {
-            roots.clear();
-            roots.push_back(Interval{-g, g, 0, N});
-        }
+    if (x_lo > 0 && have_clo) {
+        roots.push_back(Interval{x_lo, g, c_lo.below_pos, N});
+        if (c_lo.below_neg > 0) roots.push_back(Interval{-g, -x_lo, 0, c_lo.below_neg});
+    } else {
+        roots.push_back(Interval{-g, g, 0, N});
     }
     std::vector<Pair> pairs;
     int64_t nf = 0;
@@ -650,32 +714,34 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     R.d.assign(k, 0.0);
     R.resid.assign(k, 0.0);
     R.s.assign((size_t)N * k, 0.0);
-    double worst = -1;
-    int64_t worst_j = -1;
     bool all_ok = (kk == k);
+    std::vector<std::pair<double, int64_t>> order;
     for (int64_t j = 0; j < kk; ++j) {
         R.d[j] = pairs[j].theta;
         std::copy(pairs[j].v.begin(), pairs[j].v.end(), R.s.begin() + (size_t)j * N);
-        double rho = resid_bound(bi, b, pairs[j].v);
+        const double rho = resid_bound(bi, b, pairs[j].v);
         R.resid[j] = rho;
         if (rho > tol) all_ok = false;
-        if (rho > worst) {
-            worst = rho;
-            worst_j = j;
-        }
+        order.emplace_back(rho, j);
     }
     R.have_all = (kk == k);
-    R.converged = all_ok && bi != nullptr;
-    if (worst_j >= 0) {
-        wit_ = pairs[worst_j].v;
-        wit_theta_ = pairs[worst_j].theta;
+    // witnesses for the next check: the worst few pairs
+    std::sort(order.begin(), order.end(), [](const std::pair<double, int64_t>& a, const std::pair<double, int64_t>& b2) { return a.first > b2.first; });
+    wit_.clear();
+    wit_theta_.clear();
+    for (size_t j = 0; j < order.size() && j < 3; ++j) {
+        wit_.push_back(pairs[order[j].second].v);
+        wit_theta_.push_back(pairs[order[j].second].theta);
     }
-    R.factorizations = wk.nfac;
-    total_factorizations += wk.nfac;
+    if (kk == k) {
+        const double th_k = std::fabs(pairs[k - 1].theta);
+        kth_step_ = kth_est_ > 0 ? std::max(2.0 * (th_k - kth_est_), 1e-7 * tn) : 1e-4 * tn;
+        kth_est_ = th_k;
+    }
     if (verbose > 0)
         std::fprintf(stderr, "[rbl] full check N=%lld found=%lld worst rho=%.3e conv=%d (nfac=%d)\n", (long long)N,
-                     (long long)kk, worst, (int)R.converged, wk.nfac);
-    return R;
+                     (long long)kk, order.empty() ? 0.0 : order[0].first, (int)(all_ok && bi != nullptr), wk.nfac);
+    return finish(all_ok && bi != nullptr);
 }
 
 }  // namespace rbl

@@ -359,6 +359,53 @@ int rbl_band_eig_topk(int64_t N, int64_t kd, const double* ab, int64_t k, const 
     });
 }
 
+struct rbl_checker {
+    BandTopK chk;
+};
+
+int rbl_checker_create(int threads, rbl_checker** out) {
+    return guarded([&] {
+        if (!out) throw Error(RBL_INVALID, "rbl_checker_create: null out");
+        *out = new rbl_checker();
+        (*out)->chk.threads = threads > 0 ? threads : 1;
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_checker_check(rbl_checker* c, int64_t N, int64_t kd, const double* ab, int64_t k, const double* bi, int64_t b,
+                      double tol, int force_full, double* d_out, double* s_out, double* resid_out,
+                      int32_t* converged_out, int32_t* have_all_out, int64_t* stats_out) {
+    return guarded([&] {
+        if (!c || N < 1 || kd < 0 || !ab || k < 1 || k > N || !bi) throw Error(RBL_INVALID, "rbl_checker_check: bad arguments");
+        BandSym T;
+        T.from_lapack_lower(N, (int)kd, ab);
+        std::vector<double> bir((size_t)b * b);
+        for (int r = 0; r < b; ++r)
+            for (int cc = 0; cc < b; ++cc) bir[(size_t)r * b + cc] = bi[(size_t)cc * b + r];
+        const int full_before = c->chk.full_checks;
+        TopKResult r = c->chk.check(T, bir.data(), (int)b, k, tol, force_full != 0);
+        if (converged_out) *converged_out = r.converged ? 1 : 0;
+        if (have_all_out) *have_all_out = r.have_all ? 1 : 0;
+        if (stats_out) {
+            stats_out[0] = r.factorizations;
+            stats_out[1] = c->chk.full_checks - full_before;
+        }
+        if (r.have_all) {
+            for (int64_t j = 0; j < k; ++j) {
+                if (d_out) d_out[j] = r.d[j];
+                if (resid_out) resid_out[j] = r.resid[j];
+            }
+            if (s_out) std::memcpy(s_out, r.s.data(), (size_t)N * k * sizeof(double));
+        }
+        return (int)RBL_OK;
+    });
+}
+
+int rbl_checker_destroy(rbl_checker* c) {
+    delete c;
+    return RBL_OK;
+}
+
 int rbl_band_count_below(int64_t N, int64_t kd, const double* ab, double x, int64_t* count_out) {
     return guarded([&] {
         if (N < 1 || kd < 0 || !ab || !count_out) throw Error(RBL_INVALID, "rbl_band_count_below: bad arguments");

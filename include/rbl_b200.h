@@ -193,6 +193,17 @@ int rbl_band_eig_topk(int64_t N, int64_t kd, const double* ab, int64_t k, const 
                       double tol, int threads, double* d_out, double* s_out, double* resid_out,
                       int32_t* converged_out);
 
+/* Stateful variant used by the solver between checks (keeps the witness Ritz pair of the previous check):
+ * returns the decision of check_convergence; when all k pairs were computed (*have_all_out = 1) d_out/s_out/
+ * resid_out are filled as in rbl_band_eig_topk.  stats_out[0] = band factorisations of this call,
+ * stats_out[1] = 1 if the full k-pair path ran. */
+typedef struct rbl_checker rbl_checker;
+int rbl_checker_create(int threads, rbl_checker** out);
+int rbl_checker_check(rbl_checker* c, int64_t N, int64_t kd, const double* ab, int64_t k, const double* bi, int64_t b,
+                      double tol, int force_full, double* d_out, double* s_out, double* resid_out,
+                      int32_t* converged_out, int32_t* have_all_out, int64_t* stats_out);
+int rbl_checker_destroy(rbl_checker* c);
+
 /* Number of eigenvalues of the band matrix strictly below x (Sturm count by row-wise elimination). */
 int rbl_band_count_below(int64_t N, int64_t kd, const double* ab, double x, int64_t* count_out);
 
