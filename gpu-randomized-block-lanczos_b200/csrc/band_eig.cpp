@@ -42,14 +42,19 @@ void BandSym::from_lapack_lower(int64_t n, int kd_, const double* ab) {
 
 void BandSym::update_norm() {
     const int W = 2 * kd + 1;
-    double m = 0.0;
+    double m = 0.0, lo = 1e300, hi = -1e300;
     for (int64_t r = 0; r < N; ++r) {
         double s = 0.0;
         const double* row = &F[(size_t)r * W];
         for (int t = 0; t < W; ++t) s += std::fabs(row[t]);
         m = std::max(m, s);
+        const double off = s - std::fabs(row[kd]);
+        lo = std::min(lo, row[kd] - off);
+        hi = std::max(hi, row[kd] + off);
     }
     norm_inf = m;
+    gersh_lo = N ? lo : 0.0;
+    gersh_hi = N ? hi : 0.0;
 }
 
 void BandSym::matvec(const double* x, double* y) const {
@@ -82,44 +87,55 @@ void BandLU::factor(const BandSym& T, double shift) {
     const double pivmin = std::max(T.norm_inf, 1e-290) * 1e-20;
     int P = 1;
     nneg = 0;
-    double* wp = w.data();
+    double* __restrict__ wp = w.data();
+    double* __restrict__ Ubase = U.data();
+    double* __restrict__ Lbase = L.data();
+    uint8_t* __restrict__ swbase = sw.data();
+    const double* __restrict__ Fbase = T.F.data();
     for (int64_t r = 0; r < N; ++r) {
         const int64_t base = r - kd;
-        const double* row = &T.F[(size_t)r * W];
+        const double* __restrict__ row = Fbase + (size_t)r * W;
         for (int t = 0; t < W; ++t) wp[t] = row[t];
         for (int t = W; t < 3 * kd + 1; ++t) wp[t] = 0.0;
         wp[kd] -= shift;
         const int prev = P;
         const int64_t cstart = base < 0 ? 0 : base;
+        double* __restrict__ Lr = Lbase + (size_t)r * kd;
+        uint8_t* __restrict__ sr = swbase + (size_t)r * kd;
         for (int64_t c = cstart; c < r; ++c) {
             const int wi = (int)(c - base);
-            double* Uc = &U[(size_t)c * W];
-            double wc = wp[wi];
+            double* __restrict__ Uc = Ubase + (size_t)c * W;
+            double* __restrict__ ws = wp + wi;
+            const double wc = ws[0];
+            const double piv = Uc[0];
             if (wc == 0.0) {
-                L[(size_t)r * kd + wi] = 0.0;
-                sw[(size_t)r * kd + wi] = 0;
+                Lr[wi] = 0.0;
+                sr[wi] = 0;
                 continue;
             }
-            uint8_t s = 0;
-            if (std::fabs(wc) > std::fabs(Uc[0])) {
-                const int so = Uc[0] < 0 ? -1 : 1, sn = wc < 0 ? -1 : 1;
-                double* ws = wp + wi;
+            if (std::fabs(wc) > std::fabs(piv)) {
+                // interchange: the working row becomes the pivot row; fused swap + elimination
+                const double m = piv / wc;
+                P = ((piv < 0) != (wc < 0)) ? P : -P;
+#pragma GCC ivdep
                 for (int t = 0; t < W; ++t) {
-                    double tmp = ws[t];
-                    ws[t] = Uc[t];
-                    Uc[t] = tmp;
+                    const double a = ws[t], b = Uc[t];
+                    Uc[t] = a;
+                    ws[t] = b - m * a;
                 }
-                s = 1;
-                P = -P * so * sn;
+                ws[0] = 0.0;
+                Lr[wi] = m;
+                sr[wi] = 1;
+            } else {
+                const double m = wc / piv;
+#pragma GCC ivdep
+                for (int t = 1; t < W; ++t) ws[t] -= m * Uc[t];
+                ws[0] = 0.0;
+                Lr[wi] = m;
+                sr[wi] = 0;
             }
-            const double m = wp[wi] / Uc[0];
-            double* ws = wp + wi;
-            for (int t = 1; t < W; ++t) ws[t] -= m * Uc[t];
-            ws[0] = 0.0;
-            L[(size_t)r * kd + wi] = m;
-            sw[(size_t)r * kd + wi] = s;
         }
-        double* Ur = &U[(size_t)r * W];
+        double* __restrict__ Ur = Ubase + (size_t)r * W;
         for (int t = 0; t < W; ++t) Ur[t] = wp[kd + t];
         if (std::fabs(Ur[0]) < pivmin) Ur[0] = -pivmin;
         const int cur = P * (Ur[0] < 0 ? -1 : 1);
@@ -573,22 +589,28 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     if (k > N) k = N;
     const double g = tn * (1.0 + 1e-12) + 1e-300;
 
-    // #{ |lambda| > x } for x >= 0, remembering the two one-sided Sturm counts
+    // #{ |lambda| > x } for x >= 0, remembering the two one-sided Sturm counts.  A side that lies outside the
+    // Gershgorin interval of T is empty and costs no factorisation.
     struct Cnt { int64_t below_pos, below_neg, above; };
-    double neg_free_from = -1.0;  // for x >= this value the negative side is known to be empty (within this check)
+    double neg_free_from = (T.gersh_lo >= 0.0) ? 0.0 : -1.0;  // for x >= this the negative side is empty
+    auto neg_side = [&](double x) -> int64_t {  // #{ lambda < -x }
+        if (-x < T.gersh_lo) return 0;
+        if (neg_free_from >= 0.0 && x >= neg_free_from) return 0;
+        wk.lu.factor(T, -x);
+        ++wk.nfac;
+        if (wk.lu.nneg == 0) neg_free_from = x;
+        return wk.lu.nneg;
+    };
     auto count_abs_above = [&](double x) -> Cnt {
         Cnt c;
-        wk.lu.factor(T, x);
-        ++wk.nfac;
-        c.below_pos = wk.lu.nneg;
-        if (neg_free_from >= 0.0 && x >= neg_free_from) {
-            c.below_neg = 0;
+        if (x > T.gersh_hi) {
+            c.below_pos = N;
         } else {
-            wk.lu.factor(T, -x);
+            wk.lu.factor(T, x);
             ++wk.nfac;
-            c.below_neg = wk.lu.nneg;
-            if (c.below_neg == 0) neg_free_from = x;
+            c.below_pos = wk.lu.nneg;
         }
+        c.below_neg = neg_side(x);
         c.above = (N - c.below_pos) + c.below_neg;
         return c;
     };
@@ -600,6 +622,9 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     };
 
     // ---- stage 1: witnesses of the previous check -------------------------------------------------------
+    // Inverse iteration from the zero-padded old Ritz vector: one factorisation at the old Ritz value, a few
+    // solves, then (if needed) a second factorisation just beside the improved Rayleigh quotient.  The Sturm
+    // count of that factorisation also bounds the rank of the pair, so no separate counting is needed.
     if (!force_full && bi) {
         for (size_t wi = 0; wi < wit_.size(); ++wi) {
             if ((int64_t)wit_[wi].size() > N) continue;
@@ -608,18 +633,57 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
             double nn = nrm2(x.data(), N);
             if (!(nn > 0)) continue;
             scal(x.data(), 1.0 / nn, N);
-            double th = wit_theta_[wi], rs = 0;
-            if (!rqi(T, wk, th, x, rs, 0.0, 0.0, 6, 2e-15)) continue;
+            double th, rs;
+            rayleigh(T, x, wk.t, th, rs);
+            const double sgn = th < 0 ? -1.0 : 1.0;
+            double sigma = th;              // shift of the factorisation in hand
+            int64_t cnt_sigma = -1;         // eigenvalues below sigma
+            bool ok = false;
+            for (int round = 0; round < 3 && !ok; ++round) {
+                // keep the shift on the inner side of the Ritz value so that its Sturm count bounds the rank
+                sigma = (round == 0) ? th : th - sgn * 2.0 * rs;
+                wk.lu.factor(T, sigma);
+                ++wk.nfac;
+                cnt_sigma = wk.lu.nneg;
+                for (int it = 0; it < 3; ++it) {
+                    wk.y = x;
+                    wk.lu.solve(wk.y.data());
+                    const double n2 = nrm2(wk.y.data(), N);
+                    if (!(n2 > 0) || !std::isfinite(n2)) break;
+                    scal(wk.y.data(), 1.0 / n2, N);
+                    x.swap(wk.y);
+                    const double prev = rs;
+                    rayleigh(T, x, wk.t, th, rs);
+                    if (rs <= 2e-13 * tn) { ok = true; break; }
+                    if (rs > 0.25 * prev) break;  // slow: better shift needed
+                }
+                if (!ok && rs <= 1e-11 * tn && round >= 1) ok = true;
+            }
+            if (!ok) continue;
             const double rho = resid_bound(bi, b, x);
             if (rho <= tol) continue;
-            const double delta = std::max(1e-12 * std::fabs(th), 1e-14 * tn);
-            const Cnt c = count_abs_above(std::fabs(th) + delta);
-            if (c.above < k) {  // fewer than k strictly larger: the pair is one of the k wanted and is not converged
+            // rank: the pair is wanted iff fewer than k eigenvalues have larger magnitude
+            int64_t larger;
+            const double margin = 1e-13 * tn;
+            if (sgn > 0 && sigma < th - margin) {
+                larger = (N - cnt_sigma - 1) + neg_side(std::fabs(th));
+            } else if (sgn < 0 && sigma > th + margin) {
+                int64_t pos = 0;
+                if (std::fabs(th) <= T.gersh_hi) {
+                    wk.lu.factor(T, std::fabs(th));
+                    ++wk.nfac;
+                    pos = N - wk.lu.nneg;
+                }
+                larger = (cnt_sigma - 1) + pos;
+            } else {
+                const double delta = std::max(1e-12 * std::fabs(th), 1e-14 * tn);
+                larger = count_abs_above(std::fabs(th) + delta).above;
+            }
+            if (larger < k) {  // one of the k wanted pairs is not converged
                 wit_[0] = x;
                 wit_theta_[0] = th;
                 wit_.resize(1);
                 wit_theta_.resize(1);
-                kth_est_ = std::max(kth_est_, 0.0);
                 if (verbose > 1)
                     std::fprintf(stderr, "[rbl] check N=%lld witness theta=%.12g rho=%.3e (nfac=%d)\n", (long long)N, th,
                                  rho, wk.nfac);

@@ -18,6 +18,7 @@ struct BandSym {
     int kd = 0;
     std::vector<double> F;
     double norm_inf = 0.0;
+    double gersh_lo = 0.0, gersh_hi = 0.0;  // Gershgorin interval containing the spectrum
 
     void reset(int64_t n, int kd_);
     inline double& at(int64_t r, int64_t c) { return F[(size_t)r * (2 * kd + 1) + (size_t)(c - r + kd)]; }

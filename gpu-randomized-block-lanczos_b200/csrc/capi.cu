@@ -251,10 +251,11 @@ int rbl_block_qr(int64_t n, int64_t b, double* u, double* r_out, int32_t* deflat
 int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qbuf, double* w0, double* w1,
                void* c_out, int impl) {
     return guarded([&] {
-        (void)impl;
         need_device();
         if (!qbuf || !w0 || !w1 || b < 1 || b > 32 || n < 1 || m < 1) throw Error(RBL_INVALID, "rbl_reorth: bad arguments");
         const int B = padded_block((int)b);
+        const bool tc = impl != 1 && reorth_tc_supported(B, storage_fp32);
+        if (impl == 2 && !tc) throw Error(RBL_INVALID, "rbl_reorth: tensor-core path needs fp32 storage and padded block size 16");
         const size_t ssz = storage_fp32 ? 4 : 8;
         // pad the stored blocks
         std::vector<unsigned char> hb((size_t)m * n * B * ssz, 0);
@@ -274,8 +275,16 @@ int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qb
         ReorthPlan p = reorth_plan(B, storage_fp32, n, m);
         dC.alloc((size_t)m * B * 2 * B * ssz);
         dpart.alloc(p.partial_elems * ssz);
-        launch_reorth_gram(p, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, 0);
-        launch_reorth_update(p, dbuf.p, n * B, dC.p, W0.dev.p, W1.dev.p, nullptr, 0);
+        if (tc) {
+            DevBuf<float> scratch;
+            scratch.alloc(reorth_tc_scratch_floats(B, n, m));
+            launch_reorth_gram_tc(p, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, scratch.p, m, 0);
+            launch_reorth_update_tc(p, dbuf.p, n * B, W0.dev.p, W1.dev.p, nullptr, scratch.p, m, 0);
+            RBL_CUDA(cudaDeviceSynchronize());
+        } else {
+            launch_reorth_gram(p, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, 0);
+            launch_reorth_update(p, dbuf.p, n * B, dC.p, W0.dev.p, W1.dev.p, nullptr, 0);
+        }
         RBL_CUDA(cudaDeviceSynchronize());
         W0.download(n, (int)b, B, w0);
         W1.download(n, (int)b, B, w1);

@@ -81,6 +81,17 @@ void launch_reorth_gram_reduce(const ReorthPlan& p, const void* partials, void* 
 void launch_reorth_update(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, const void* C, double* w0,
                           double* w1, void* store_w1, cudaStream_t st);
 
+// tensor-core (3xTF32 mma.sync + cp.async pipelines) variants of K5, fp32 buffer, B = 16 (reorth_tc.cu).
+// `scratch` holds the tf32 hi/lo parts of the targets and of the coefficients (reorth_tc_scratch_floats).
+bool reorth_tc_supported(int B, int fp32);
+size_t reorth_tc_scratch_floats(int B, int64_t n, int64_t m_cap);
+void launch_reorth_gram_tc(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, const double* w0,
+                           const double* w1, void* partials, void* C, float* scratch, int64_t m_cap, cudaStream_t st);
+// after an all-reduce of C: recompute the coefficient hi/lo parts from C (ranges must be 1, partials = C)
+void launch_reorth_gram_tc_resplit(const ReorthPlan& p, void* C, float* scratch, int64_t m_cap, cudaStream_t st);
+void launch_reorth_update_tc(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, double* w0, double* w1,
+                             void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st);
+
 // ---- K6 Ritz vectors -----------------------------------------------------------------------------
 // V[:, t] = sum_j buf_j * S[(j*B .. j*B+B), t];  S device, row-major (m*B) x kpad in the buffer's type;
 // V column-major n x k (ldv), float or double as the buffer.                  RBL_gpu.jl:106-132

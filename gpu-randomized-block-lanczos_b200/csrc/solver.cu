@@ -216,6 +216,8 @@ struct Ctx {
     DevBuf<double> part, small;  // rowop partials; small: G, Ai, Bp, Gloc (4 * B*B)
     DevBuf<QrState> qr;
     DevBuf<unsigned char> Cmat, rpart;
+    DevBuf<float> tc_scratch;
+    bool use_tc = false;
     DevBuf<double> sendbuf;
     PinnedBuf<double> hA, hB;
     PinnedBuf<QrState> hqr;
@@ -343,9 +345,9 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     size_t free_b = 0, total_b = 0;
     RBL_CUDA(cudaMemGetInfo(&free_b, &total_b));
     c.rgrid = rowop_grid(B, c.nloc);
-    const size_t fixed = 3 * (size_t)c.next * B * 8 + (size_t)c.rgrid * B * B * 8 + (size_t)c.nloc * (size_t)(b + k) * 8 +
+    const size_t fixed = 3 * (size_t)c.next * B * 8 + (size_t)c.nloc * 4 * B * 4 + (size_t)c.rgrid * B * B * 8 + (size_t)c.nloc * (size_t)(b + k) * 8 +
                          ((size_t)64 << 20);
-    const size_t per_block = (size_t)c.bstride * c.ssz + (size_t)B * 2 * B * c.ssz;
+    const size_t per_block = (size_t)c.bstride * c.ssz + (size_t)B * 2 * B * (c.ssz + 8);
     if ((double)fixed + 2.0 * per_block > 0.92 * (double)free_b) throw Error(RBL_OOM, "rbl_solve: problem does not fit device memory");
     {
         size_t rp_elems = reorth_max_partial_elems(B, c.fp32, c.nloc, m_cap);
@@ -364,6 +366,10 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     c.qr.alloc(1);
     c.Cmat.alloc((size_t)m_cap * B * 2 * B * c.ssz);
     c.rpart.alloc(std::max<size_t>(1, reorth_max_partial_elems(B, c.fp32, c.nloc, m_cap)) * c.ssz);
+    c.use_tc = reorth_tc_supported(B, c.fp32) && opt.reorth_impl != 1;
+    if (opt.reorth_impl == 2 && !c.use_tc)
+        throw Error(RBL_INVALID, "rbl_solve: tensor-core reorth needs precision=mixed and padded block size 16");
+    if (c.use_tc) c.tc_scratch.alloc(reorth_tc_scratch_floats(B, c.nloc, m_cap));
     if (h->comm.active()) c.sendbuf.alloc(std::max<int64_t>(1, h->send_ptr[h->world]) * (size_t)B);
     c.hA.alloc((size_t)m_cap * B * B);
     c.hB.alloc((size_t)m_cap * B * B);
@@ -507,17 +513,35 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             const int64_t m = i - 2;
             ReorthPlan p = reorth_plan(B, c.fp32, c.nloc, m);
             c.tm.mark(PH_RGRAM);
-            launch_reorth_gram(p, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.st);
-            c.launches += 2;
-            if (h->comm.active()) {
-                std::string err;
-                const size_t cnt = (size_t)m * B * 2 * B;
-                c.nccl(c.fp32 ? h->comm.allreduce_f32((float*)c.Cmat.p, cnt, c.st, err)
-                              : h->comm.allreduce_f64((double*)c.Cmat.p, cnt, c.st, err), err);
+            if (c.use_tc) {
+                launch_reorth_gram_tc(p, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.tc_scratch.p, m_cap, c.st);
+                c.launches += 3;
+                if (h->comm.active()) {
+                    // the hi/lo parts are not additive across ranks: reduce C, then re-split on every rank
+                    std::string err;
+                    const size_t cnt = (size_t)m * B * 2 * B;
+                    c.nccl(h->comm.allreduce_f32((float*)c.Cmat.p, cnt, c.st, err), err);
+                    ReorthPlan one = p;
+                    one.ranges = 1;
+                    launch_reorth_gram_tc_resplit(one, c.Cmat.p, c.tc_scratch.p, m_cap, c.st);
+                    ++c.launches;
+                }
+                c.tm.mark(PH_RUPD);
+                launch_reorth_update_tc(p, c.buf.p, c.bstride, cur, prev, c.slot(i - 2), c.tc_scratch.p, m_cap, c.st);
+                ++c.launches;
+            } else {
+                launch_reorth_gram(p, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.st);
+                c.launches += 2;
+                if (h->comm.active()) {
+                    std::string err;
+                    const size_t cnt = (size_t)m * B * 2 * B;
+                    c.nccl(c.fp32 ? h->comm.allreduce_f32((float*)c.Cmat.p, cnt, c.st, err)
+                                  : h->comm.allreduce_f64((double*)c.Cmat.p, cnt, c.st, err), err);
+                }
+                c.tm.mark(PH_RUPD);
+                launch_reorth_update(p, c.buf.p, c.bstride, c.Cmat.p, cur, prev, c.slot(i - 2), c.st);
+                ++c.launches;
             }
-            c.tm.mark(PH_RUPD);
-            launch_reorth_update(p, c.buf.p, c.bstride, c.Cmat.p, cur, prev, c.slot(i - 2), c.st);
-            ++c.launches;
             ++c.n_rgram; ++c.n_rupd;
             c.bytes_rgram += (double)c.ssz * (double)c.nloc * (double)m * B + 8.0 * (double)c.nloc * 2 * B;
             c.bytes_rupd += (double)c.ssz * (double)c.nloc * (double)m * B + 2 * 8.0 * (double)c.nloc * 2 * B +

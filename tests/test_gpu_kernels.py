@@ -98,9 +98,21 @@ def _krylov_like(n, b, m, rng):
                                          (2500, 4, 300, True), (2500, 4, 30, False), (3001, 8, 40, True),
                                          (3001, 32, 12, True), (1500, 32, 9, False), (900, 5, 7, False), (64, 16, 1, True)])
 def test_reorth_block_cgs(gpu, n, b, m, fp32):
+    _reorth_case(gpu, n, b, m, fp32, impl=0)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("n,b,m", [(4000, 16, 5), (10007, 16, 70), (700, 16, 33), (70000, 16, 3), (5000, 13, 9), (64, 16, 1),
+                                   (20000, 16, 130)])
+def test_reorth_simt_and_tensor_core_paths(gpu, impl, n, b, m):
+    """Both implementations of K5 (SIMT fp32 FMA / 3xTF32 tensor-core MMA) meet the same fp32-grade bars."""
+    _reorth_case(gpu, n, b, m, True, impl=impl)
+
+
+def _reorth_case(gpu, n, b, m, fp32, impl):
     rng = np.random.default_rng(n + m)
     blocks, W0, W1 = _krylov_like(n, b, m, rng)
-    w0, w1, C = gpu.k_reorth(blocks, W0, W1, fp32)
+    w0, w1, C = gpu.k_reorth(blocks, W0, W1, fp32, impl=impl)
     dt = np.float32 if fp32 else np.float64
     Qs = blocks.astype(dt).astype(np.float64)              # what the buffer holds
     Qm = Qs.transpose(1, 0, 2).reshape(n, m * b)
