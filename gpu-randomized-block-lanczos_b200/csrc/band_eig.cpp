@@ -621,128 +621,150 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         return R;
     };
 
-    // ---- stage 1: witnesses of the previous check -------------------------------------------------------
-    // Inverse iteration from the zero-padded old Ritz vector: one factorisation at the old Ritz value, a few
-    // solves, then (if needed) a second factorisation just beside the improved Rayleigh quotient.  The Sturm
-    // count of that factorisation also bounds the rank of the pair, so no separate counting is needed.
+    // Refine an approximate eigenvector x (unit norm) by inverse iteration: the shift is kept on the inner
+    // side of the Ritz value, so the Sturm count of the last factorisation bounds the rank of the pair from
+    // above without any further factorisation.  Returns false if the iteration does not settle.
+    struct Refined { double theta, res; int64_t larger; };
+    auto refine = [&](std::vector<double>& x, bool have_factor, double sigma0, int64_t cnt0, Refined& out) -> bool {
+        double th, rs;
+        rayleigh(T, x, wk.t, th, rs);
+        double sigma = sigma0;
+        int64_t cnt_sigma = cnt0;
+        bool ok = false;
+        for (int round = 0; round < 7 && !ok; ++round) {
+            if (round > 0 || !have_factor) {
+                // Rayleigh-quotient shifts while far from convergence (cubic); once close, step to the inner
+                // side of the Ritz value by twice the residual (the eigenvalue is within one residual of it)
+                const double sg = th < 0 ? -1.0 : 1.0;
+                const double off = (rs <= 1e-6 * tn) ? 2.0 * rs : 0.0;
+                sigma = th - sg * off;
+                wk.lu.factor(T, sigma);
+                ++wk.nfac;
+                cnt_sigma = wk.lu.nneg;
+            }
+            for (int it = 0; it < 4; ++it) {
+                wk.y = x;
+                wk.lu.solve(wk.y.data());
+                const double n2 = nrm2(wk.y.data(), N);
+                if (!(n2 > 0) || !std::isfinite(n2)) break;
+                scal(wk.y.data(), 1.0 / n2, N);
+                x.swap(wk.y);
+                const double prev = rs;
+                rayleigh(T, x, wk.t, th, rs);
+                if (rs <= 2e-13 * tn) { ok = true; break; }
+                if (rs > 0.25 * prev) break;  // slow: a closer shift is needed
+            }
+            if (!ok && rs <= 1e-11 * tn && round >= 1) ok = true;
+        }
+        if (!ok) return false;
+        out.theta = th;
+        out.res = rs;
+        const double margin = 1e-13 * tn;
+        if (th >= 0 && sigma < th - margin) {
+            out.larger = (N - cnt_sigma - 1) + neg_side(std::fabs(th));
+        } else if (th < 0 && sigma > th + margin) {
+            int64_t pos = 0;
+            if (std::fabs(th) <= T.gersh_hi) {
+                wk.lu.factor(T, std::fabs(th));
+                ++wk.nfac;
+                pos = N - wk.lu.nneg;
+            }
+            out.larger = (cnt_sigma - 1) + pos;
+        } else {
+            const double delta = std::max(1e-12 * std::fabs(th), 1e-14 * tn);
+            out.larger = count_abs_above(std::fabs(th) + delta).above;
+        }
+        return true;
+    };
+    auto reject_with = [&](std::vector<double>& x, double th, double rho, const char* how) {
+        wit_.assign(1, x);
+        wit_theta_.assign(1, th);
+        if (verbose > 1)
+            std::fprintf(stderr, "[rbl] check N=%lld %s theta=%.12g rho=%.3e (nfac=%d)\n", (long long)N, how, th, rho, wk.nfac);
+        return finish(false);
+    };
+
+    // ---- stage 1: witnesses of the previous check (zero-padded old Ritz vectors) -------------------------
     if (!force_full && bi) {
         for (size_t wi = 0; wi < wit_.size(); ++wi) {
             if ((int64_t)wit_[wi].size() > N) continue;
             std::vector<double> x(N, 0.0);
             std::copy(wit_[wi].begin(), wit_[wi].end(), x.begin());
-            double nn = nrm2(x.data(), N);
+            const double nn = nrm2(x.data(), N);
             if (!(nn > 0)) continue;
             scal(x.data(), 1.0 / nn, N);
-            double th, rs;
-            rayleigh(T, x, wk.t, th, rs);
-            const double sgn = th < 0 ? -1.0 : 1.0;
-            double sigma = th;              // shift of the factorisation in hand
-            int64_t cnt_sigma = -1;         // eigenvalues below sigma
-            bool ok = false;
-            for (int round = 0; round < 3 && !ok; ++round) {
-                // keep the shift on the inner side of the Ritz value so that its Sturm count bounds the rank
-                sigma = (round == 0) ? th : th - sgn * 2.0 * rs;
-                wk.lu.factor(T, sigma);
-                ++wk.nfac;
-                cnt_sigma = wk.lu.nneg;
-                for (int it = 0; it < 3; ++it) {
-                    wk.y = x;
-                    wk.lu.solve(wk.y.data());
-                    const double n2 = nrm2(wk.y.data(), N);
-                    if (!(n2 > 0) || !std::isfinite(n2)) break;
-                    scal(wk.y.data(), 1.0 / n2, N);
-                    x.swap(wk.y);
-                    const double prev = rs;
-                    rayleigh(T, x, wk.t, th, rs);
-                    if (rs <= 2e-13 * tn) { ok = true; break; }
-                    if (rs > 0.25 * prev) break;  // slow: better shift needed
-                }
-                if (!ok && rs <= 1e-11 * tn && round >= 1) ok = true;
-            }
-            if (!ok) continue;
+            Refined rf;
+            const bool rok = refine(x, false, 0.0, 0, rf);
+            if (verbose > 2) std::fprintf(stderr, "[rbl]   stage1 w%zu ok=%d theta=%.10g res=%.2e larger=%lld rho=%.3e\n", wi, (int)rok, rf.theta, rf.res, (long long)rf.larger, rok ? resid_bound(bi, b, x) : -1.0);
+            if (!rok) continue;
             const double rho = resid_bound(bi, b, x);
-            if (rho <= tol) continue;
-            // rank: the pair is wanted iff fewer than k eigenvalues have larger magnitude
-            int64_t larger;
-            const double margin = 1e-13 * tn;
-            if (sgn > 0 && sigma < th - margin) {
-                larger = (N - cnt_sigma - 1) + neg_side(std::fabs(th));
-            } else if (sgn < 0 && sigma > th + margin) {
-                int64_t pos = 0;
-                if (std::fabs(th) <= T.gersh_hi) {
-                    wk.lu.factor(T, std::fabs(th));
-                    ++wk.nfac;
-                    pos = N - wk.lu.nneg;
-                }
-                larger = (cnt_sigma - 1) + pos;
-            } else {
-                const double delta = std::max(1e-12 * std::fabs(th), 1e-14 * tn);
-                larger = count_abs_above(std::fabs(th) + delta).above;
-            }
-            if (larger < k) {  // one of the k wanted pairs is not converged
-                wit_[0] = x;
-                wit_theta_[0] = th;
-                wit_.resize(1);
-                wit_theta_.resize(1);
-                if (verbose > 1)
-                    std::fprintf(stderr, "[rbl] check N=%lld witness theta=%.12g rho=%.3e (nfac=%d)\n", (long long)N, th,
-                                 rho, wk.nfac);
-                return finish(false);
-            }
+            if (rho > tol && rf.larger < k) return reject_with(x, rf.theta, rho, "witness");
         }
     }
 
-    // ---- stage 2: the pair(s) at rank k -----------------------------------------------------------------
-    if (!force_full && bi && kth_est_ > 0.0) {
-        double x_lo = std::max(0.0, kth_est_ - std::max(1e-10 * kth_est_, 1e-13 * tn));
-        Cnt c_lo = count_abs_above(x_lo);
-        if (c_lo.above >= k) {
-            double h = std::max(kth_step_, 1e-7 * tn);
-            double x_hi = std::min(g, x_lo + h);
-            Cnt c_hi = count_abs_above(x_hi);
-            while (c_hi.above >= k && x_hi < g) {
-                x_lo = x_hi;
-                c_lo = c_hi;
-                h *= 4.0;
-                x_hi = std::min(g, x_lo + h);
-                c_hi = count_abs_above(x_hi);
-            }
-            if (c_hi.above < k) {
-                while (c_lo.above - c_hi.above > 6 && (x_hi - x_lo) > 1e-12 * tn) {
-                    const double xm = 0.5 * (x_lo + x_hi);
-                    const Cnt cm = count_abs_above(xm);
-                    if (cm.above >= k) { x_lo = xm; c_lo = cm; } else { x_hi = xm; c_hi = cm; }
-                }
-                std::vector<Interval> roots;
-                roots.push_back(Interval{x_lo, x_hi, c_lo.below_pos, c_hi.below_pos});
-                if (c_lo.below_neg > c_hi.below_neg) roots.push_back(Interval{-x_hi, -x_lo, c_hi.below_neg, c_lo.below_neg});
-                std::vector<Pair> pairs;
-                int64_t nf = 0;
-                slice(T, roots, 1, pairs, nf);
-                wk.nfac += (int)nf;
-                std::stable_sort(pairs.begin(), pairs.end(),
-                                 [](const Pair& a, const Pair& b2) { return std::fabs(a.theta) > std::fabs(b2.theta); });
-                const int64_t in_topk = k - c_hi.above;  // the first in_topk of them are among the k wanted
-                if ((int64_t)pairs.size() == c_lo.above - c_hi.above && in_topk >= 1) {
-                    const double th_k = std::fabs(pairs[in_topk - 1].theta);
-                    kth_step_ = std::max(2.0 * (th_k - kth_est_), 1e-7 * tn);
-                    kth_est_ = th_k;
-                    double worst = -1;
-                    int64_t wj = -1;
-                    for (int64_t j = 0; j < in_topk; ++j) {
-                        const double rho = resid_bound(bi, b, pairs[j].v);
-                        if (rho > worst) { worst = rho; wj = j; }
+    // ---- stage 2: a pair found from a shift x with a <= #{|lambda| > x} <= hi (hi <= k-1) ----------------
+    // The eigenvalue nearest to such an x has rank <= hi+1 <= k on either side of x, so whatever inverse
+    // iteration at x converges to is one of the k wanted pairs.  First a target a little inside the wanted
+    // set (robust while Ritz values still enter it), then the boundary itself.
+    if (!force_full && bi && k >= 1) {
+        const int64_t margin = std::max<int64_t>(1, std::min<int64_t>(k / 6, k - 1));
+        struct Target { int64_t lo, hi; double* x; double* step; };
+        Target targets[2] = {{std::max<int64_t>(0, k - 1 - 2 * margin), k - 1 - margin, &xA_, &stepA_},
+                             {std::max<int64_t>(0, k - margin), k - 1, &xB_, &stepB_}};
+        for (int ti = 0; ti < 2; ++ti) {
+            const Target& tg = targets[ti];
+            if (tg.hi < tg.lo || tg.hi < 0) continue;
+            // locate x with lo <= above(x) <= hi; above(.) never decreases from one check to the next, so the
+            // previous x is a lower bound
+            double xl = 0.0, xh = g, x = -1.0;
+            double xs = (*tg.x > 0.0) ? *tg.x : -1.0;
+            double step = std::max(*tg.step, 1e-6 * tn);
+            bool found = false;
+            if (xs >= 0.0) {
+                Cnt c = count_abs_above(xs);
+                if (c.above >= tg.lo && c.above <= tg.hi) { x = xs; found = true; }
+                else if (c.above > tg.hi) {
+                    xl = xs;
+                    for (int it = 0; it < 40 && !found; ++it) {
+                        const double xn = std::min(g, xl + step);
+                        c = count_abs_above(xn);
+                        if (c.above >= tg.lo && c.above <= tg.hi) { x = xn; found = true; }
+                        else if (c.above > tg.hi) { xl = xn; step *= 3.0; if (xn >= g) break; }
+                        else { xh = xn; break; }
                     }
-                    if (worst > tol) {
-                        wit_.assign(1, pairs[wj].v);
-                        wit_theta_.assign(1, pairs[wj].theta);
-                        if (verbose > 1)
-                            std::fprintf(stderr, "[rbl] check N=%lld rank-k pair theta=%.12g rho=%.3e (nfac=%d)\n",
-                                         (long long)N, pairs[wj].theta, worst, wk.nfac);
-                        return finish(false);
-                    }
+                } else {
+                    xh = xs;
                 }
             }
+            for (int it = 0; it < 60 && !found; ++it) {
+                if (xh - xl <= 1e-13 * tn) break;
+                const double xm = 0.5 * (xl + xh);
+                const Cnt c = count_abs_above(xm);
+                if (c.above >= tg.lo && c.above <= tg.hi) { x = xm; found = true; }
+                else if (c.above > tg.hi) xl = xm;
+                else xh = xm;
+            }
+            if (verbose > 2) std::fprintf(stderr, "[rbl]   stage2 target %d [%lld,%lld] found=%d x=%.10g (nfac=%d)\n", ti, (long long)tg.lo, (long long)tg.hi, (int)found, x, wk.nfac);
+            if (!found) continue;
+            *tg.step = std::max(2.0 * (x - std::max(*tg.x, 0.0)), 1e-6 * tn);
+            *tg.x = x;
+            // inverse iteration at +x (or -x if the spectrum there is the nearer one): start random
+            wk.lu.factor(T, x);
+            ++wk.nfac;
+            std::vector<double> v;
+            wk.random_unit(v, N);
+            for (int it = 0; it < 5; ++it) {
+                wk.lu.solve(v.data());
+                const double n2 = nrm2(v.data(), N);
+                if (!(n2 > 0) || !std::isfinite(n2)) { wk.random_unit(v, N); continue; }
+                scal(v.data(), 1.0 / n2, N);
+            }
+            Refined rf;
+            const bool rok = refine(v, true, x, wk.lu.nneg, rf);
+            if (verbose > 2) std::fprintf(stderr, "[rbl]   stage2 refine ok=%d theta=%.10g res=%.2e larger=%lld rho=%.3e\n", (int)rok, rf.theta, rf.res, (long long)rf.larger, rok ? resid_bound(bi, b, v) : -1.0);
+            if (!rok) continue;
+            const double rho = resid_bound(bi, b, v);
+            if (rho > tol && rf.larger < k) return reject_with(v, rf.theta, rho, ti == 0 ? "inner pair" : "boundary pair");
         }
     }
 
@@ -797,10 +819,13 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         wit_.push_back(pairs[order[j].second].v);
         wit_theta_.push_back(pairs[order[j].second].theta);
     }
-    if (kk == k) {
-        const double th_k = std::fabs(pairs[k - 1].theta);
-        kth_step_ = kth_est_ > 0 ? std::max(2.0 * (th_k - kth_est_), 1e-7 * tn) : 1e-4 * tn;
-        kth_est_ = th_k;
+    if (kk == k) {  // seeds for the stage-2 brackets of the next check
+        const int64_t margin = std::max<int64_t>(1, std::min<int64_t>(k / 6, k - 1));
+        const int64_t ia = std::max<int64_t>(0, k - 1 - margin - margin / 2);
+        xB_ = std::fabs(pairs[k - 1].theta) * (1.0 - 1e-12);
+        xA_ = std::fabs(pairs[ia].theta) * (1.0 - 1e-12);
+        if (stepA_ <= 0) stepA_ = 1e-5 * tn;
+        if (stepB_ <= 0) stepB_ = 1e-5 * tn;
     }
     if (verbose > 0)
         std::fprintf(stderr, "[rbl] full check N=%lld found=%lld worst rho=%.3e conv=%d (nfac=%d)\n", (long long)N,

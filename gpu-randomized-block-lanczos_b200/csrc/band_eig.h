@@ -64,13 +64,13 @@ public:
     // T: current N x N band matrix; bi: b x b upper-triangular B_i row-major (bi[r*b+c]); k wanted.
     // force_full: compute all k pairs even when a witness already proves non-convergence.
     TopKResult check(const BandSym& T, const double* bi, int b, int64_t k, double tol, bool force_full);
-    void reset() { wit_.clear(); wit_theta_.clear(); kth_est_ = 0; kth_step_ = 0; }
+    void reset() { wit_.clear(); wit_theta_.clear(); xA_ = xB_ = stepA_ = stepB_ = 0; }
 
 private:
     std::vector<std::vector<double>> wit_;  // Ritz vectors of T that failed the bound at the last check
     std::vector<double> wit_theta_;
-    double kth_est_ = 0;                    // k-th largest |lambda| at the last check (lower bound for the next)
-    double kth_step_ = 0;                   // how far it moved (initial bracket width)
+    double xA_ = 0, xB_ = 0;                // stage-2 bracket points of the last check (lower bounds for the next)
+    double stepA_ = 0, stepB_ = 0;          // how far they moved
 };
 
 int64_t band_count_below(const BandSym& T, double x);

@@ -1,4 +1,5 @@
 // extern "C" entry points declared in include/rbl_b200.h.
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -377,6 +378,7 @@ int rbl_checker_create(int threads, rbl_checker** out) {
         if (!out) throw Error(RBL_INVALID, "rbl_checker_create: null out");
         *out = new rbl_checker();
         (*out)->chk.threads = threads > 0 ? threads : 1;
+        if (const char* v = getenv("RBL_CHECK_VERBOSE")) (*out)->chk.verbose = atoi(v);
         return (int)RBL_OK;
     });
 }
