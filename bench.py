@@ -217,21 +217,22 @@ def main():
     if world > 1:
         rs = rbl_b200.partition_rows(n, world)
         r0, r1 = int(rs[rank]), int(rs[rank + 1])
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            import ctypes
-            buf = ctypes.create_string_buffer(128)
-            assert rbl_b200.lib().rbl_nccl_unique_id(buf) == 0, rbl_b200.lib().rbl_last_error()
-            uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        uid_bytes = bytes(uid.cpu().numpy().tobytes())
+        def fresh_uid():
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                import ctypes
+                buf = ctypes.create_string_buffer(128)
+                assert rbl_b200.lib().rbl_nccl_unique_id(buf) == 0, rbl_b200.lib().rbl_last_error()
+                uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            return bytes(uid.cpu().numpy().tobytes())
         Lloc = L[r0:r1, :]
         Lloc.sort_indices()
 
         def make_solver():
             return B.Solver(options=B.default_options(**opt_kw),
                             shard=dict(n=n, row0=r0, rowptr=Lloc.indptr.astype(np.int64), colidx=Lloc.indices.astype(np.int64),
-                                       vals=Lloc.data, rank=rank, world=world, uid=uid_bytes))
+                                       vals=Lloc.data, rank=rank, world=world, uid=fresh_uid()))
         Om_loc = np.asfortranarray(Om[r0:r1])
         nloc = r1 - r0
     else:

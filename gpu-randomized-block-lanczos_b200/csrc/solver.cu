@@ -374,6 +374,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     c.hA.alloc((size_t)m_cap * B * B);
     c.hB.alloc((size_t)m_cap * B * B);
     c.hqr.alloc(1);
+    const double t_alloc_done = now_s();
     RBL_CUDA(cudaMemsetAsync(c.qr.p, 0, sizeof(QrState), c.st));
     RBL_CUDA(cudaMemsetAsync(c.small.p, 0, 4 * (size_t)B * B * 8, c.st));
     for (int i = 0; i < 3; ++i) RBL_CUDA(cudaMemsetAsync(c.X[i].p, 0, (size_t)c.next * B * 8, c.st));
@@ -490,17 +491,63 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     int64_t last_check_i = 0;
     int checks = 0;
     double t_wait = 0.0;
+    // Row-sharded runs: only rank 0 evaluates the host check; the decision (and, on acceptance, D and S)
+    // is summed over ranks with every other rank contributing zeros, so all ranks follow the same control
+    // flow and use the same Ritz basis.
+    const bool is_root = (h->rank == 0);
+    const bool multi = h->comm.active();
+    DevBuf<double> d_ctrl;
+    PinnedBuf<double> h_ctrl;
+    if (multi) {
+        d_ctrl.alloc(2);
+        h_ctrl.alloc(2);
+    }
+    auto agree_flag = [&](bool local) -> bool {
+        if (!multi) return local;
+        h_ctrl.p[0] = (is_root && local) ? 1.0 : 0.0;
+        RBL_CUDA(cudaMemcpyAsync(d_ctrl.p, h_ctrl.p, 8, cudaMemcpyHostToDevice, c.st));
+        c.allreduce(d_ctrl.p, 1);
+        RBL_CUDA(cudaMemcpyAsync(h_ctrl.p + 1, d_ctrl.p, 8, cudaMemcpyDeviceToHost, c.st));
+        RBL_CUDA(cudaStreamSynchronize(c.st));
+        return h_ctrl.p[1] > 0.5;
+    };
+    auto share_result = [&](TopKResult& r, int64_t Nrows) {
+        if (!multi) return;
+        const size_t cnt = (size_t)k + (size_t)Nrows * k;
+        std::vector<double> hbuf(cnt, 0.0);
+        if (is_root) {
+            std::copy(r.d.begin(), r.d.begin() + k, hbuf.begin());
+            std::copy(r.s.begin(), r.s.begin() + (size_t)Nrows * k, hbuf.begin() + k);
+        }
+        DevBuf<double> dbuf;
+        dbuf.alloc(cnt);
+        RBL_CUDA(cudaMemcpyAsync(dbuf.p, hbuf.data(), cnt * 8, cudaMemcpyHostToDevice, c.st));
+        c.allreduce(dbuf.p, cnt);
+        RBL_CUDA(cudaMemcpyAsync(hbuf.data(), dbuf.p, cnt * 8, cudaMemcpyDeviceToHost, c.st));
+        RBL_CUDA(cudaStreamSynchronize(c.st));
+        r.N = Nrows;
+        r.d.assign(hbuf.begin(), hbuf.begin() + k);
+        r.s.assign(hbuf.begin() + k, hbuf.end());
+    };
+    bool check_in_flight = false;
     auto harvest = [&]() -> bool {  // wait for the in-flight check; true when it accepted
-        if (!pending.valid()) return false;
-        const double t0 = now_s();
-        TopKResult r = pending.get();
-        t_wait += now_s() - t0;
+        if (!check_in_flight) return false;
+        check_in_flight = false;
+        TopKResult r;
+        bool local = false;
+        if (is_root) {
+            const double t0 = now_s();
+            r = pending.get();
+            t_wait += now_s() - t0;
+            local = r.converged;
+        }
         ++checks;
         last_check_i = pending_i;
-        if (r.converged) {
+        if (agree_flag(local)) {
             converged = true;
             final_i = pending_i;
             final_res = std::move(r);
+            share_result(final_res, final_i * b);
             return true;
         }
         return false;
@@ -583,18 +630,22 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             RBL_CUDA(cudaEventCreateWithFlags(&step_event[i], cudaEventDisableTiming));
             RBL_CUDA(cudaEventRecord(step_event[i], c.st));
             pending_i = i;
+            check_in_flight = true;
             const int64_t it = i;
-            if (async_ok) {
-                pending = std::async(std::launch::async, [&, it]() { return run_check(it, false); });
-            } else {
-                std::promise<TopKResult> pr;
-                pr.set_value(run_check(it, false));
-                pending = pr.get_future();
-                if (harvest()) break;
+            if (is_root) {
+                if (async_ok) {
+                    pending = std::async(std::launch::async, [&, it]() { return run_check(it, false); });
+                } else {
+                    std::promise<TopKResult> pr;
+                    pr.set_value(run_check(it, false));
+                    pending = pr.get_future();
+                }
             }
+            if (!async_ok && harvest()) break;
         }
     }
     if (!converged) harvest();
+    const double t_loop_done = now_s();
     const int64_t iterations_run = i;
     RBL_CUDA(cudaStreamSynchronize(c.st));
     int status = RBL_OK;
@@ -611,13 +662,15 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             T.reset(0, b);
             t_blocks = 0;
         }
-        final_res = run_check(it, true);
+        if (is_root) final_res = run_check(it, true);
+        share_result(final_res, it * b);
         ++checks;
         final_i = it;
     }
     for (auto e : step_event)
         if (e) cudaEventDestroy(e);
 
+    const double t_final_done = now_s();
     // ---- Ritz vectors V = Qbuf * S                                              RBL_gpu.jl:106-132,219 ----
     const int64_t mfin = final_i;
     const int kpad = (int)((k + 15) / 16 * 16);
@@ -672,6 +725,10 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     stats.t_total = now_s() - t_begin;
     if (c.hqr.p->bad) status = RBL_BREAKDOWN;
     if (stats_out) *stats_out = stats;
+    if (opt.verbose)
+        std::fprintf(stderr, "[rbl] timeline: alloc %.3f  start+loop %.3f  final-check %.3f  ritz+d2h %.3f (d2h %.3f, h2d %.3f)\n",
+                     t_alloc_done - t_begin, t_loop_done - t_alloc_done, t_final_done - t_loop_done,
+                     now_s() - t_final_done, stats.t_d2h, stats.t_h2d);
     if (opt.verbose)
         std::fprintf(stderr, "[rbl] Iterations: %lld and kryl_sz: %lld (ran %lld), checks %d (full %d), t=%.3fs eig=%.3fs wait=%.3fs\n",
                      (long long)final_i, (long long)(final_i * b), (long long)iterations_run, checks,
