@@ -479,16 +479,39 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
         for (auto& t : th) t.join();
     }
 
-    // clusters sequentially, each orthogonal to already accepted vectors within a few ctol
+    // tight clusters (degenerate Ritz values), in parallel: each orthogonal to the already accepted single
+    // vectors within a few ctol; clusters that a bisection point split in two are repaired by the final pass
     std::sort(clusters.begin(), clusters.end(), [](const Interval& a, const Interval& b) { return a.lo < b.lo; });
-    Work wk;
-    for (auto& c : clusters) {
-        std::vector<const std::vector<double>*> against;
-        for (auto& p : out)
-            if (p.theta > c.lo - 8 * ctol && p.theta < c.hi + 8 * ctol) against.push_back(&p.v);
-        extract_cluster(T, wk, 0.5 * (c.lo + c.hi), (int)(c.chi - c.clo), against, out);
+    {
+        const size_t nsingle = out.size();
+        std::vector<std::vector<Pair>> found(clusters.size());
+        std::atomic<size_t> next{0};
+        auto cworker = [&](int seed) {
+            Work wk;
+            wk.rng.seed(424242ull + 31ull * seed);
+            for (;;) {
+                const size_t ci = next.fetch_add(1);
+                if (ci >= clusters.size()) break;
+                const Interval& c = clusters[ci];
+                std::vector<const std::vector<double>*> against;
+                for (size_t j = 0; j < nsingle; ++j)
+                    if (out[j].theta > c.lo - 8 * ctol && out[j].theta < c.hi + 8 * ctol) against.push_back(&out[j].v);
+                wk.rng.seed(1000003ull * (ci + 1));  // deterministic per cluster, whatever thread runs it
+                extract_cluster(T, wk, 0.5 * (c.lo + c.hi), (int)(c.chi - c.clo), against, found[ci]);
+            }
+            fac += wk.nfac;
+        };
+        const int ct = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, clusters.size()));
+        if (ct <= 1) {
+            cworker(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < ct; ++t) th.emplace_back(cworker, t);
+            for (auto& t : th) t.join();
+        }
+        for (auto& f : found)
+            for (auto& p : f) out.push_back(std::move(p));
     }
-    fac += wk.nfac;
 
     // final pass: neighbouring eigenvalues closer than a few ctol must have orthogonal vectors
     std::sort(out.begin(), out.end(), [](const Pair& a, const Pair& b) { return a.theta < b.theta; });

@@ -256,7 +256,7 @@ int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qb
         if (!qbuf || !w0 || !w1 || b < 1 || b > 32 || n < 1 || m < 1) throw Error(RBL_INVALID, "rbl_reorth: bad arguments");
         const int B = padded_block((int)b);
         const bool tc = impl != 1 && reorth_tc_supported(B, storage_fp32);
-        if (impl == 2 && !tc) throw Error(RBL_INVALID, "rbl_reorth: tensor-core path needs fp32 storage and padded block size 16");
+        if (impl >= 2 && !tc) throw Error(RBL_INVALID, "rbl_reorth: tensor-core path needs fp32 storage and padded block size 16");
         const size_t ssz = storage_fp32 ? 4 : 8;
         // pad the stored blocks
         std::vector<unsigned char> hb((size_t)m * n * B * ssz, 0);
@@ -276,7 +276,14 @@ int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qb
         ReorthPlan p = reorth_plan(B, storage_fp32, n, m);
         dC.alloc((size_t)m * B * 2 * B * ssz);
         dpart.alloc(p.partial_elems * ssz);
-        if (tc) {
+        if (tc && impl != 2) {
+            DevBuf<float> scratch;
+            scratch.alloc(reorth_h_scratch_words(B, n, m));
+            launch_reorth_gram_h(p, n, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, scratch.p, m, 0);
+            launch_reorth_coeff_h(p, dC.p, scratch.p, m, 0, 0);
+            launch_reorth_update_h(p, n, dbuf.p, n * B, W0.dev.p, W1.dev.p, nullptr, scratch.p, m, 0);
+            RBL_CUDA(cudaDeviceSynchronize());
+        } else if (tc) {
             DevBuf<float> scratch;
             scratch.alloc(reorth_tc_scratch_floats(B, n, m));
             launch_reorth_gram_tc(p, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, scratch.p, m, 0);

@@ -279,25 +279,23 @@ void launch_rowop(int B, const RowOpArgs& a, int grid, cudaStream_t st) {
     });
 }
 
+// one warp per output element: lanes stride over the partials, fixed-order shuffle tree (deterministic)
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int nparts, int count,
                                        double* __restrict__ out) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= count) return;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int p = 0;
-    for (; p + 4 <= nparts; p += 4) {
-        s0 += partials[(size_t)p * count + e];
-        s1 += partials[(size_t)(p + 1) * count + e];
-        s2 += partials[(size_t)(p + 2) * count + e];
-        s3 += partials[(size_t)(p + 3) * count + e];
-    }
-    for (; p < nparts; ++p) s0 += partials[(size_t)p * count + e];
-    out[e] = (s0 + s1) + (s2 + s3);
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= count) return;
+    double s = 0.0;
+    for (int p = lane; p < nparts; p += 32) s += partials[(size_t)p * count + warp];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if (lane == 0) out[warp] = s;
 }
 
 void launch_reduce_partials(const double* partials, int nparts, int count, double* out, cudaStream_t st) {
-    int threads = 128;
-    reduce_partials_kernel<<<(count + threads - 1) / threads, threads, 0, st>>>(partials, nparts, count, out);
+    const int threads = 256;
+    const int blocks = (count * 32 + threads - 1) / threads;
+    reduce_partials_kernel<<<blocks, threads, 0, st>>>(partials, nparts, count, out);
 }
 
 // =================================================================================================

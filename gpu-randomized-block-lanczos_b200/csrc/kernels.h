@@ -92,6 +92,17 @@ void launch_reorth_gram_tc_resplit(const ReorthPlan& p, void* C, float* scratch,
 void launch_reorth_update_tc(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, double* w0, double* w1,
                              void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st);
 
+// scaled two-term FP16 split on mma.sync m16n8k16 (reorth_tc16.cu): same interface, half the tensor-pipe time.
+// `n_global` fixes the power-of-two operand scale (orthonormal columns of global length n_global).
+size_t reorth_h_scratch_words(int B, int64_t n, int64_t m_cap);
+void launch_reorth_gram_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t block_stride_elems,
+                          const double* w0, const double* w1, void* partials, void* C, float* scratch, int64_t m_cap,
+                          cudaStream_t st);
+void launch_reorth_coeff_h(const ReorthPlan& p, const void* C, float* scratch, int64_t m_cap, int recompute_max,
+                           cudaStream_t st);
+void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t block_stride_elems,
+                            double* w0, double* w1, void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st);
+
 // ---- K6 Ritz vectors -----------------------------------------------------------------------------
 // V[:, t] = sum_j buf_j * S[(j*B .. j*B+B), t];  S device, row-major (m*B) x kpad in the buffer's type;
 // V column-major n x k (ldv), float or double as the buffer.                  RBL_gpu.jl:106-132

@@ -2,6 +2,7 @@
 //   which 0: streaming copy GB/s (read+write)      1: streaming read GB/s
 //         2: FP32 FFMA TFLOP/s                      3: FP64 DFMA TFLOP/s
 //         4: mma.sync m16n8k8 tf32 TFLOP/s          5: mma.sync m8n8k4 f64 TFLOP/s
+//         6: mma.sync m16n8k16 f16 TFLOP/s          7: mma.sync m16n8k16 bf16 TFLOP/s
 #include "kernels.h"
 
 #include <cstdio>
@@ -88,6 +89,37 @@ __global__ void mb_mma_f64_kernel(double* out, int iters) {
     if (s == -1.0) out[0] = s;
 }
 
+template <int KIND>  // 0: f16, 1: bf16
+__global__ void mb_mma_h_kernel(float* out, int iters) {
+    float c[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+    unsigned a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = a0 + 4, b1 = a0 + 5;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (KIND == 0)
+                asm volatile(
+                    "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                    : "+f"(c[u][0]), "+f"(c[u][1]), "+f"(c[u][2]), "+f"(c[u][3])
+                    : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+            else
+                asm volatile(
+                    "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                    : "+f"(c[u][0]), "+f"(c[u][1]), "+f"(c[u][2]), "+f"(c[u][3])
+                    : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += c[i][j];
+    if (s == -1.f) out[0] = s;
+}
+
 double microbench(int which, int64_t size, int iters) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -135,6 +167,8 @@ double microbench(int which, int64_t size, int iters) {
             if (which == 2) { mb_fma_kernel<float><<<grid, block>>>((float*)out, inner); flops = 2.0 * 64 * (double)inner * grid * block; }
             if (which == 3) { mb_fma_kernel<double><<<grid, block>>>((double*)out, inner); flops = 2.0 * 64 * (double)inner * grid * block; }
             if (which == 4) { mb_mma_tf32_kernel<<<grid, block>>>((float*)out, inner); flops = 2.0 * 16 * 8 * 8 * 4 * (double)inner * grid * (block / 32); }
+            if (which == 6) { mb_mma_h_kernel<0><<<grid, block>>>((float*)out, inner); flops = 2.0 * 16 * 8 * 16 * 4 * (double)inner * grid * (block / 32); }
+            if (which == 7) { mb_mma_h_kernel<1><<<grid, block>>>((float*)out, inner); flops = 2.0 * 16 * 8 * 16 * 4 * (double)inner * grid * (block / 32); }
             if (which == 5) { mb_mma_f64_kernel<<<grid, block>>>((double*)out, inner); flops = 2.0 * 8 * 8 * 4 * 4 * (double)inner * grid * (block / 32); }
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);

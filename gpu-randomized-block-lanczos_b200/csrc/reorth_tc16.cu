@@ -1,0 +1,528 @@
+// K5, second tensor-core version: scaled two-term FP16 split on mma.sync m16n8k16 (fp32 accumulate).
+//
+//   x * S = h + l,  h = fp16(x S),  l = fp16(x S - h)        (S a power of two, |x| <= 1 for orthonormal columns)
+//   x y S_x S_y ~= h_x h_y + h_x l_y + l_x h_y               (22 significant bits, like 3xTF32)
+//
+// Three k16 MMAs cover 16 reduction steps where the TF32 kernel needs six k8 MMAs, and ncu shows the
+// TF32 kernel bound by the tensor pipe (profiles/r01_ncu_full_prof_gram.txt: tensor active 69%, DRAM 46%);
+// f16 mma.sync runs at 2x the TF32 rate on B200 (553 vs 277 TFLOP/s measured, rbl_microbench 6 / 4).
+//
+// Operands that are reused by every CTA (the 2B target columns for the Gram pass, the coefficient
+// blocks for the update pass) are converted once per re-orthogonalisation into packed f16x2 words
+// whose two halves are the two reduction-dimension neighbours an MMA fragment register needs.
+//
+// Replaces hybrid_part_reorth! / part_reorth_gpu_async!  (Julia/RBL_gpu.jl:59-81, 29-47).
+#include <cuda_fp16.h>
+
+#include <cstdio>
+
+#include "kernels.h"
+
+namespace rbl {
+
+namespace {
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// two scaled fp32 values -> packed (hi, hi) and (lo, lo) f16x2 words; element 0 in the low half
+__device__ __forceinline__ void split_h2(float x0, float x1, float scale, unsigned& hi, unsigned& lo) {
+    const float s0 = x0 * scale, s1 = x1 * scale;
+    const __half2 h = __floats2half2_rn(s0, s1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+    hi = *reinterpret_cast<const unsigned*>(&h);
+    lo = *reinterpret_cast<const unsigned*>(&l);
+}
+
+// D(16x8) += A(16x16, row) * B(16x8, col), f16 inputs, fp32 accumulate
+__device__ __forceinline__ void mma_f16(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+}  // namespace
+
+// ---- targets: row-pair interleaved f16x2 words  Wp[(r/2) * 2B + t] = (W[r][t], W[r+1][t]) ----------------
+template <int B>
+__global__ void split_targets_h_kernel(int64_t n, const double* __restrict__ w0, const double* __restrict__ w1,
+                                       float scale, unsigned* __restrict__ wh, unsigned* __restrict__ wl) {
+    const int64_t npairs = (n + 1) / 2;
+    const int64_t total = npairs * 2 * B;
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; e < total; e += stride) {
+        const int64_t rp = e / (2 * B);
+        const int t = (int)(e % (2 * B));
+        const int64_t ra = 2 * rp, rb = 2 * rp + 1;
+        const double* src = (t < B) ? w0 : w1;
+        const int tc = (t < B) ? t : t - B;
+        const float x0 = (float)src[ra * B + tc];
+        const float x1 = (rb < n) ? (float)src[rb * B + tc] : 0.f;
+        unsigned hi, lo;
+        split_h2(x0, x1, scale, hi, lo);
+        wh[e] = hi;
+        wl[e] = lo;
+    }
+}
+
+// =================================================================================================
+// Gram.  MMA roles: M = 16 Krylov columns of a stored block, N = 8 targets, K = 16 rows.
+// =================================================================================================
+template <int B>
+struct GramH {
+    static constexpr int NW = 16;                // warps per CTA (ncu: with 8 the schedulers had 0.6 eligible warps/cycle)
+    static constexpr int WB = 2;                 // stored blocks per warp
+    static constexpr int JT = NW * WB;           // stored blocks per CTA (= reorth_plan's chunk size)
+    static constexpr int NT = (2 * B) / 8;
+    static constexpr int PA = B;                 // unpadded 64-byte rows, permuted + swizzled (see gram_slot)
+    static constexpr int PW = 2 * B + 8;         // words per staged target row-pair
+    static constexpr int NST = 5;
+    static constexpr int RS = 16;                // rows per stage
+    static constexpr int RW = 64;                // rows per shared target chunk (32 row pairs)
+    static constexpr int STAGE = WB * RS * PA;   // floats
+    static constexpr int WBUF = (RW / 2) * PW;   // words per target buffer (hi or lo)
+    static constexpr int NCP = (WB * RS * (B / 4)) / 32;  // cp.async per lane per stage
+    static constexpr size_t smem_bytes = (size_t)(NW * NST * STAGE + 4 * WBUF) * sizeof(float);
+};
+
+// Shared-memory slot of element (row r of a 16-row stage, column c) of a stored block, in floats.
+// Rows keep their 64 contiguous bytes (a multiple of 32 B: both 16-byte halves of a global 32-byte sector land
+// in one shared-memory sector, so cp.async fetches every sector once - a padded 80-byte pitch was measured to
+// fetch 1.47x the sectors from L2).  Bank conflicts of the fragment loads (rows 2t / 2t+1 / 2t+8 / 2t+9,
+// columns g / g+8) are removed by storing row r at position p = (r&1)*8 + (r>>1) and swapping the two 32-byte
+// halves of the row when p&2.
+__device__ __forceinline__ int gram_slot(int r, int c) {
+    const int p = ((r & 1) << 3) + (r >> 1);
+    return p * 16 + ((((c >> 2) ^ (p & 2))) << 2) + (c & 3);
+}
+
+template <int B>
+__global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
+    reorth_gram_h_kernel(int64_t n, int64_t m, const float* __restrict__ buf, int64_t bstride,
+                         const unsigned* __restrict__ wh, const unsigned* __restrict__ wl, float scale,
+                         float inv_scale2, float* __restrict__ partials, int64_t rows_per_range) {
+    using C = GramH<B>;
+    constexpr int NW = C::NW, WB = C::WB, JT = C::JT, NT = C::NT, PA = C::PA, PW = C::PW, NST = C::NST, RS = C::RS,
+                  RW = C::RW, STAGE = C::STAGE, WBUF = C::WBUF, NCP = C::NCP, NTHR = NW * 32;
+    static_assert(B == 16, "instantiated for B = 16");
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    float* sA = smem + (size_t)warp * NST * STAGE;
+    unsigned* sW = reinterpret_cast<unsigned*>(smem + (size_t)NW * NST * STAGE);  // [2][hi,lo][RW/2][PW]
+    const int64_t jbase = (int64_t)blockIdx.x * JT + (int64_t)warp * WB;
+    const int64_t rbeg = (int64_t)blockIdx.y * rows_per_range;  // multiple of RW
+    const int64_t rend = min(n, rbeg + rows_per_range);
+    const int64_t nrows = rend - rbeg;
+
+    float acc[WB][NT][4];
+#pragma unroll
+    for (int b = 0; b < WB; ++b)
+#pragma unroll
+        for (int x = 0; x < NT; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[b][x][y] = 0.f;
+
+    if (nrows > 0) {
+        const int nks = (int)((nrows + RS - 1) / RS);
+        constexpr int KPC = RW / RS;  // k-steps per target chunk
+        // per-lane constants of the NCP copies of a stage: source pointer at stage 0, row inside the stage,
+        // destination slot; a stage advances every source by RS*B floats
+        const float* src0[NCP];
+        int dst0[NCP], row0[NCP];
+        bool blk_ok[NCP];
+#pragma unroll
+        for (int u = 0; u < NCP; ++u) {
+            const int q = lane + 32 * u;
+            const int blk = q / (RS * (B / 4));
+            const int rem = q % (RS * (B / 4));
+            const int row = rem / (B / 4), c4 = rem % (B / 4);
+            blk_ok[u] = (jbase + blk) < m;
+            row0[u] = row;
+            dst0[u] = blk * RS * PA + gram_slot(row, c4 * 4);
+            src0[u] = buf + (size_t)(blk_ok[u] ? jbase + blk : 0) * bstride + (size_t)(rbeg + row) * B + c4 * 4;
+        }
+        auto issue_a = [&](int ks) {
+            float* st = sA + (size_t)(ks % NST) * STAGE;
+            const int64_t rem_rows = nrows - (int64_t)ks * RS;  // rows of this range not yet consumed
+            const size_t adv = (size_t)ks * RS * B;
+#pragma unroll
+            for (int u = 0; u < NCP; ++u) {
+                const bool ok = blk_ok[u] && (row0[u] < rem_rows);
+                cp_async16(st + dst0[u], ok ? src0[u] + adv : buf, ok ? 16 : 0);
+            }
+        };
+        auto issue_w = [&](int chunk) {  // whole CTA: RW/2 row pairs x 2B words; threads < 256 copy hi, the rest lo
+            const int half = tid / 256, q = tid % 256;
+            unsigned* dst = sW + (size_t)((chunk & 1) * 2 + half) * WBUF;
+            const unsigned* srcb = half ? wl : wh;
+            const int64_t rp0 = (rbeg + (int64_t)chunk * RW) / 2;
+            const int64_t rp_end = (rend + 1) / 2;
+            const int rp = q / (2 * B / 4), c4 = q % (2 * B / 4);
+            const bool ok = (rp0 + rp < rp_end);
+            cp_async16(dst + rp * PW + c4 * 4, ok ? srcb + (size_t)(rp0 + rp) * 2 * B + c4 * 4 : srcb, ok ? 16 : 0);
+        };
+        static_assert(((RW / 2) * 2 * B / 4) == 256 && NTHR == 512, "target chunk copy assumes 512 threads");
+        issue_w(0);
+        issue_a(0);
+        cp_async_commit();
+#pragma unroll
+        for (int s = 1; s < NST - 1; ++s) {
+            issue_a(s);
+            cp_async_commit();
+        }
+        for (int ks = 0; ks < nks; ++ks) {
+            cp_async_wait<NST - 2>();
+            if ((ks % KPC) == 0) __syncthreads();
+            else __syncwarp();
+            if ((ks % KPC) == 0 && (int64_t)(ks / KPC + 1) * RW < nrows) issue_w(ks / KPC + 1);
+            issue_a(ks + NST - 1);
+            cp_async_commit();
+
+            const float* st = sA + (size_t)(ks % NST) * STAGE;
+            const int chunk = ks / KPC;
+            const unsigned* ph = sW + (size_t)((chunk & 1) * 2 + 0) * WBUF + (size_t)(ks % KPC) * 8 * PW;
+            const unsigned* pl = sW + (size_t)((chunk & 1) * 2 + 1) * WBUF + (size_t)(ks % KPC) * 8 * PW;
+            unsigned bh[NT][2], bl[NT][2];
+#pragma unroll
+            for (int x = 0; x < NT; ++x) {
+                bh[x][0] = ph[t * PW + x * 8 + g];
+                bh[x][1] = ph[(t + 4) * PW + x * 8 + g];
+                bl[x][0] = pl[t * PW + x * 8 + g];
+                bl[x][1] = pl[(t + 4) * PW + x * 8 + g];
+            }
+#pragma unroll
+            for (int b = 0; b < WB; ++b) {
+                const float* a = st + b * RS * PA;
+                unsigned ah[4], al[4];
+                // A[m = column][k = row]: register halves are rows 2t, 2t+1 (and +8) of columns g / g+8
+                split_h2(a[gram_slot(2 * t, g)], a[gram_slot(2 * t + 1, g)], scale, ah[0], al[0]);
+                split_h2(a[gram_slot(2 * t, g + 8)], a[gram_slot(2 * t + 1, g + 8)], scale, ah[1], al[1]);
+                split_h2(a[gram_slot(2 * t + 8, g)], a[gram_slot(2 * t + 9, g)], scale, ah[2], al[2]);
+                split_h2(a[gram_slot(2 * t + 8, g + 8)], a[gram_slot(2 * t + 9, g + 8)], scale, ah[3], al[3]);
+#pragma unroll
+                for (int x = 0; x < NT; ++x) mma_f16(acc[b][x], al, bh[x]);
+#pragma unroll
+                for (int x = 0; x < NT; ++x) mma_f16(acc[b][x], ah, bl[x]);
+#pragma unroll
+                for (int x = 0; x < NT; ++x) mma_f16(acc[b][x], ah, bh[x]);
+            }
+        }
+        cp_async_wait<0>();
+    }
+#pragma unroll
+    for (int b = 0; b < WB; ++b) {
+        const int64_t j = jbase + b;
+        if (j >= m) continue;
+        float* out = partials + ((size_t)blockIdx.y * m * B + (size_t)j * B) * (2 * B);
+#pragma unroll
+        for (int x = 0; x < NT; ++x) {
+            *reinterpret_cast<float2*>(out + (size_t)g * 2 * B + x * 8 + 2 * t) =
+                make_float2(acc[b][x][0] * inv_scale2, acc[b][x][1] * inv_scale2);
+            *reinterpret_cast<float2*>(out + (size_t)(g + 8) * 2 * B + x * 8 + 2 * t) =
+                make_float2(acc[b][x][2] * inv_scale2, acc[b][x][3] * inv_scale2);
+        }
+    }
+}
+
+// sum over row ranges (double); also the running max |C| (bit pattern of a non-negative float orders like uint)
+__global__ void reorth_reduce_max_kernel(const float* __restrict__ partials, int ranges, size_t count,
+                                         float* __restrict__ Cout, unsigned* __restrict__ cmax_bits) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float c = 0.f;
+    if (e < count) {
+        double s = 0.0;
+        for (int p = 0; p < ranges; ++p) s += (double)partials[(size_t)p * count + e];
+        c = (float)s;
+        Cout[e] = c;
+    }
+    float mx = fabsf(c);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(cmax_bits, __float_as_uint(mx));
+}
+
+// coefficients: column-pair interleaved f16x2 words  Cp[(j*B/2 + c/2) * 2B + t] = (C_j[c][t], C_j[c+1][t]),
+// scaled by the power of two that brings max|C| into [1024, 2048)
+__global__ void split_coeff_h_kernel(size_t nwords, int B, const float* __restrict__ Cin,
+                                     const unsigned* __restrict__ cmax_bits, unsigned* __restrict__ ch,
+                                     unsigned* __restrict__ cl, float* __restrict__ scale_out) {
+    const float cmax = __uint_as_float(*cmax_bits);
+    float scale = 1.f;
+    if (cmax > 0.f && isfinite(cmax)) {
+        int ex;
+        frexpf(cmax, &ex);           // cmax = f * 2^ex, f in [0.5, 1)
+        scale = ldexpf(1.f, 11 - ex);  // cmax * scale in [1024, 2048)
+    }
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) *scale_out = scale;
+    if (e >= nwords) return;
+    const size_t cp = e / (2 * B);
+    const int t = (int)(e % (2 * B));
+    const float x0 = Cin[(cp * 2) * (2 * B) + t];
+    const float x1 = Cin[(cp * 2 + 1) * (2 * B) + t];
+    unsigned hi, lo;
+    split_h2(x0, x1, scale, hi, lo);
+    ch[e] = hi;
+    cl[e] = lo;
+}
+
+// =================================================================================================
+// Update.  MMA roles: M = 16 rows, N = 8 targets, K = 16 Krylov columns (one k-step per stored block).
+// =================================================================================================
+template <int B>
+struct UpdH {
+    static constexpr int MT = 2;
+    static constexpr int NT = (2 * B) / 8;
+    static constexpr int PA = B + 8;             // floats per staged row: conflict-free float2 A fragments
+    static constexpr int PC = 2 * B + 8;         // words per staged coefficient row pair
+    static constexpr int JC = 8;
+    static constexpr int NST = 4;
+    static constexpr int STAGE = 32 * PA;
+    static constexpr int CBUF = JC * (B / 2) * PC;
+    static constexpr int ROWS_CTA = 8 * 32;
+    static constexpr size_t smem_bytes = (size_t)(8 * NST * STAGE + 4 * CBUF) * sizeof(float);
+};
+
+template <int B>
+__global__ void __launch_bounds__(256, 1)
+    reorth_update_h_kernel(int64_t n, int64_t m, const float* __restrict__ buf, int64_t bstride,
+                           const unsigned* __restrict__ Ch, const unsigned* __restrict__ Cl, float scale_a,
+                           const float* __restrict__ scale_c_ptr, double* __restrict__ w0, double* __restrict__ w1,
+                           float* __restrict__ store_w1) {
+    using C = UpdH<B>;
+    constexpr int MT = C::MT, NT = C::NT, PA = C::PA, PC = C::PC, JC = C::JC, NST = C::NST, STAGE = C::STAGE,
+                  CBUF = C::CBUF;
+    static_assert(B == 16, "instantiated for B = 16");
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    float* sA = smem + (size_t)warp * NST * STAGE;
+    unsigned* sC = reinterpret_cast<unsigned*>(smem + (size_t)8 * NST * STAGE);  // [2][hi,lo][JC][B/2][PC]
+    const int64_t r0 = (int64_t)blockIdx.x * C::ROWS_CTA + (int64_t)warp * 32;
+    const int mi = (int)m;
+
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int x = 0; x < NT; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[a][x][y] = 0.f;
+
+    auto issue_a = [&](int j) {
+        float* st = sA + (size_t)(j % NST) * STAGE;
+#pragma unroll
+        for (int u = 0; u < (32 * (B / 4)) / 32; ++u) {
+            const int q = lane + 32 * u;
+            const int row = q / (B / 4), c4 = q % (B / 4);
+            const bool ok = (j < mi) && (r0 + row < n);
+            const float* src = ok ? buf + (size_t)j * bstride + (size_t)(r0 + row) * B + c4 * 4 : buf;
+            cp_async16(st + row * PA + c4 * 4, src, ok ? 16 : 0);
+        }
+    };
+    auto issue_c = [&](int chunk) {
+        unsigned* dsth = sC + (size_t)((chunk & 1) * 2 + 0) * CBUF;
+        unsigned* dstl = sC + (size_t)((chunk & 1) * 2 + 1) * CBUF;
+        const int j0 = chunk * JC;
+#pragma unroll
+        for (int u = 0; u < (JC * (B / 2) * (2 * B / 4)) / 256; ++u) {
+            const int q = tid + 256 * u;
+            const int rowc = q / (2 * B / 4), c4 = q % (2 * B / 4);  // rowc = jb*(B/2) + c/2
+            const bool ok = (j0 * (B / 2) + rowc) < mi * (B / 2);
+            const size_t off = ((size_t)j0 * (B / 2) + rowc) * (2 * B) + c4 * 4;
+            cp_async16(dsth + rowc * PC + c4 * 4, ok ? Ch + off : Ch, ok ? 16 : 0);
+            cp_async16(dstl + rowc * PC + c4 * 4, ok ? Cl + off : Cl, ok ? 16 : 0);
+        }
+    };
+    issue_c(0);
+    issue_a(0);
+    cp_async_commit();
+#pragma unroll
+    for (int s = 1; s < NST - 1; ++s) {
+        issue_a(s);
+        cp_async_commit();
+    }
+    for (int j = 0; j < mi; ++j) {
+        cp_async_wait<NST - 2>();
+        if ((j % JC) == 0) __syncthreads();
+        else __syncwarp();
+        if ((j % JC) == 0 && (j / JC + 1) * JC < mi) issue_c(j / JC + 1);
+        issue_a(j + NST - 1);
+        cp_async_commit();
+
+        const float* st = sA + (size_t)(j % NST) * STAGE;
+        const int chunk = j / JC;
+        const unsigned* ph = sC + (size_t)((chunk & 1) * 2 + 0) * CBUF + (size_t)(j % JC) * (B / 2) * PC;
+        const unsigned* pl = sC + (size_t)((chunk & 1) * 2 + 1) * CBUF + (size_t)(j % JC) * (B / 2) * PC;
+        unsigned bh[NT][2], bl[NT][2];
+#pragma unroll
+        for (int x = 0; x < NT; ++x) {
+            bh[x][0] = ph[t * PC + x * 8 + g];
+            bh[x][1] = ph[(t + 4) * PC + x * 8 + g];
+            bl[x][0] = pl[t * PC + x * 8 + g];
+            bl[x][1] = pl[(t + 4) * PC + x * 8 + g];
+        }
+#pragma unroll
+        for (int a = 0; a < MT; ++a) {
+            const float* ap = st + (a * 16) * PA;
+            // A[m = row][k = column]: register halves are columns 2t, 2t+1 (and +8) of rows g / g+8
+            const float2 v0 = *reinterpret_cast<const float2*>(ap + g * PA + 2 * t);
+            const float2 v1 = *reinterpret_cast<const float2*>(ap + (g + 8) * PA + 2 * t);
+            const float2 v2 = *reinterpret_cast<const float2*>(ap + g * PA + 2 * t + 8);
+            const float2 v3 = *reinterpret_cast<const float2*>(ap + (g + 8) * PA + 2 * t + 8);
+            unsigned ah[4], al[4];
+            split_h2(v0.x, v0.y, scale_a, ah[0], al[0]);
+            split_h2(v1.x, v1.y, scale_a, ah[1], al[1]);
+            split_h2(v2.x, v2.y, scale_a, ah[2], al[2]);
+            split_h2(v3.x, v3.y, scale_a, ah[3], al[3]);
+#pragma unroll
+            for (int x = 0; x < NT; ++x) mma_f16(acc[a][x], al, bh[x]);
+#pragma unroll
+            for (int x = 0; x < NT; ++x) mma_f16(acc[a][x], ah, bl[x]);
+#pragma unroll
+            for (int x = 0; x < NT; ++x) mma_f16(acc[a][x], ah, bh[x]);
+        }
+    }
+    cp_async_wait<0>();
+    const float inv = 1.0f / (scale_a * __ldg(scale_c_ptr));
+#pragma unroll
+    for (int a = 0; a < MT; ++a) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t row = r0 + a * 16 + g + 8 * h;
+            if (row >= n) continue;
+#pragma unroll
+            for (int x = 0; x < NT; ++x) {
+                const int tgt = x * 8 + 2 * t;
+                const float d0 = acc[a][x][2 * h] * inv, d1 = acc[a][x][2 * h + 1] * inv;
+                if (tgt < B) {
+                    double2* p = reinterpret_cast<double2*>(w0 + (size_t)row * B + tgt);
+                    double2 v = *p;
+                    v.x -= (double)d0;
+                    v.y -= (double)d1;
+                    *p = v;
+                } else {
+                    double2* p = reinterpret_cast<double2*>(w1 + (size_t)row * B + (tgt - B));
+                    double2 v = *p;
+                    v.x -= (double)d0;
+                    v.y -= (double)d1;
+                    *p = v;
+                    if (store_w1 != nullptr)
+                        *reinterpret_cast<float2*>(store_w1 + (size_t)row * B + (tgt - B)) = make_float2((float)v.x, (float)v.y);
+                }
+            }
+        }
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------------
+// scratch layout (32-bit words): Wh, Wl: ((n+1)/2) * 2B each | Ch, Cl: m_cap*(B/2) * 2B each | cmax bits | scale_c
+static float pick_scale(int64_t n_global) {
+    // orthonormal columns: |x| <= 1, rms 1/sqrt(n); bring the rms to ~8 but never above 2^15 (fp16 max 65504)
+    double s = 8.0 * std::sqrt((double)std::max<int64_t>(n_global, 1));
+    int e = (int)std::floor(std::log2(s));
+    if (e > 15) e = 15;
+    if (e < 0) e = 0;
+    return std::ldexp(1.0f, e);
+}
+
+size_t reorth_h_scratch_words(int B, int64_t n, int64_t m_cap) {
+    return 2 * (size_t)((n + 1) / 2) * 2 * B + 2 * (size_t)m_cap * (B / 2) * 2 * B + 64;
+}
+
+struct HScratch {
+    unsigned *wh, *wl, *ch, *cl, *cmax;
+    float* scale_c;
+};
+static HScratch h_layout(float* scratch, int B, int64_t n, int64_t m_cap) {
+    HScratch s;
+    unsigned* p = reinterpret_cast<unsigned*>(scratch);
+    const size_t wn = (size_t)((n + 1) / 2) * 2 * B, cn = (size_t)m_cap * (B / 2) * 2 * B;
+    s.wh = p;
+    s.wl = s.wh + wn;
+    s.ch = s.wl + wn;
+    s.cl = s.ch + cn;
+    s.cmax = s.cl + cn;
+    s.scale_c = reinterpret_cast<float*>(s.cmax + 16);
+    return s;
+}
+
+void launch_reorth_gram_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, const double* w0,
+                          const double* w1, void* partials, void* Cmat, float* scratch, int64_t m_cap, cudaStream_t st) {
+    constexpr int B = 16;
+    using G = GramH<B>;
+    HScratch s = h_layout(scratch, B, p.n, m_cap);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(reorth_gram_h_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
+        configured = true;
+    }
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const float scale = pick_scale(n_global);
+    const int64_t total = ((p.n + 1) / 2) * 2 * B;
+    const int sgrid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sms * 16);
+    split_targets_h_kernel<B><<<sgrid, 256, 0, st>>>(p.n, w0, w1, scale, s.wh, s.wl);
+    cudaMemsetAsync(s.cmax, 0, 4, st);
+    int64_t rpr = (p.n + p.ranges - 1) / p.ranges;
+    rpr = (rpr + G::RW - 1) / G::RW * G::RW;
+    dim3 grid(p.chunks, p.ranges);
+    reorth_gram_h_kernel<B><<<grid, G::NW * 32, G::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.wh, s.wl, scale,
+                                                               1.0f / (scale * scale), (float*)partials, rpr);
+    const size_t count = (size_t)p.m * B * 2 * B;
+    reorth_reduce_max_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>((const float*)partials, p.ranges, count,
+                                                                               (float*)Cmat, s.cmax);
+}
+
+// (re)build the packed coefficient words from C - after the all-reduce of C in a row-sharded run the local
+// maxima differ, so `recompute_max` rescans C first
+__global__ void coeff_max_kernel(size_t count, const float* __restrict__ Cin, unsigned* __restrict__ cmax_bits) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float mx = (e < count) ? fabsf(Cin[e]) : 0.f;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(cmax_bits, __float_as_uint(mx));
+}
+
+void launch_reorth_coeff_h(const ReorthPlan& p, const void* Cmat, float* scratch, int64_t m_cap, int recompute_max,
+                           cudaStream_t st) {
+    constexpr int B = 16;
+    HScratch s = h_layout(scratch, B, p.n, m_cap);
+    const size_t count = (size_t)p.m * B * 2 * B;
+    if (recompute_max) {
+        cudaMemsetAsync(s.cmax, 0, 4, st);
+        coeff_max_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(count, (const float*)Cmat, s.cmax);
+    }
+    const size_t nwords = count / 2;
+    split_coeff_h_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(nwords, B, (const float*)Cmat, s.cmax, s.ch, s.cl,
+                                                                            s.scale_c);
+}
+
+void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, double* w0,
+                            double* w1, void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st) {
+    constexpr int B = 16;
+    using U = UpdH<B>;
+    HScratch s = h_layout(scratch, B, p.n, m_cap);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(reorth_update_h_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::smem_bytes);
+        configured = true;
+    }
+    const unsigned grid = (unsigned)((p.n + U::ROWS_CTA - 1) / U::ROWS_CTA);
+    reorth_update_h_kernel<B><<<grid, 256, U::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.ch, s.cl,
+                                                                 pick_scale(n_global), s.scale_c, w0, w1, (float*)store_w1);
+}
+
+}  // namespace rbl

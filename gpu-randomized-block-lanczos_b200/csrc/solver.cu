@@ -218,6 +218,7 @@ struct Ctx {
     DevBuf<unsigned char> Cmat, rpart;
     DevBuf<float> tc_scratch;
     bool use_tc = false;
+    bool use_h = false;   // FP16-split tensor-core kernels (default when supported); else TF32x3
     DevBuf<double> sendbuf;
     PinnedBuf<double> hA, hB;
     PinnedBuf<QrState> hqr;
@@ -369,7 +370,10 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     c.use_tc = reorth_tc_supported(B, c.fp32) && opt.reorth_impl != 1;
     if (opt.reorth_impl == 2 && !c.use_tc)
         throw Error(RBL_INVALID, "rbl_solve: tensor-core reorth needs precision=mixed and padded block size 16");
-    if (c.use_tc) c.tc_scratch.alloc(reorth_tc_scratch_floats(B, c.nloc, m_cap));
+    if (opt.reorth_impl == 3 && !c.use_tc)
+        throw Error(RBL_INVALID, "rbl_solve: tensor-core reorth needs precision=mixed and padded block size 16");
+    c.use_h = c.use_tc && opt.reorth_impl != 2;
+    if (c.use_tc) c.tc_scratch.alloc(std::max(reorth_tc_scratch_floats(B, c.nloc, m_cap), reorth_h_scratch_words(B, c.nloc, m_cap)));
     if (h->comm.active()) c.sendbuf.alloc(std::max<int64_t>(1, h->send_ptr[h->world]) * (size_t)B);
     c.hA.alloc((size_t)m_cap * B * B);
     c.hB.alloc((size_t)m_cap * B * B);
@@ -451,6 +455,9 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             for (int cc = 0; cc < b; ++cc) Bi[(size_t)r * b + cc] = Bm[r * B + cc];
         TopKResult r = checker.check(T, Bi.data(), b, k, opt.tol, force_full);
         t_eig += now_s() - t0;
+        if (opt.verbose > 1)
+            std::fprintf(stderr, "[rbl] check it=%lld N=%lld nfac=%d took %.2f ms conv=%d\n", (long long)it, (long long)T.N,
+                         r.factorizations, (now_s() - t0) * 1e3, (int)r.converged);
         return r;
     };
 
@@ -539,6 +546,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             const double t0 = now_s();
             r = pending.get();
             t_wait += now_s() - t0;
+            if (opt.verbose > 1) std::fprintf(stderr, "[rbl] harvest it=%lld waited %.2f ms\n", (long long)pending_i, (now_s() - t0) * 1e3);
             local = r.converged;
         }
         ++checks;
@@ -560,7 +568,20 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             const int64_t m = i - 2;
             ReorthPlan p = reorth_plan(B, c.fp32, c.nloc, m);
             c.tm.mark(PH_RGRAM);
-            if (c.use_tc) {
+            if (c.use_h) {
+                launch_reorth_gram_h(p, h->n, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.tc_scratch.p, m_cap, c.st);
+                c.launches += 4;
+                if (h->comm.active()) {
+                    std::string err;
+                    const size_t cnt = (size_t)m * B * 2 * B;
+                    c.nccl(h->comm.allreduce_f32((float*)c.Cmat.p, cnt, c.st, err), err);
+                }
+                launch_reorth_coeff_h(p, c.Cmat.p, c.tc_scratch.p, m_cap, h->comm.active() ? 1 : 0, c.st);
+                ++c.launches;
+                c.tm.mark(PH_RUPD);
+                launch_reorth_update_h(p, h->n, c.buf.p, c.bstride, cur, prev, c.slot(i - 2), c.tc_scratch.p, m_cap, c.st);
+                ++c.launches;
+            } else if (c.use_tc) {
                 launch_reorth_gram_tc(p, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.tc_scratch.p, m_cap, c.st);
                 c.launches += 3;
                 if (h->comm.active()) {

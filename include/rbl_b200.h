@@ -59,7 +59,7 @@ typedef struct {
     int32_t host_threads;  /* worker threads for the final host eigensolve (0: hardware)          */
     int32_t v_fp32;        /* 1: V_out is float (reference's FLOAT=Float32 build), else double    */
     int32_t verbose;
-    int32_t reorth_impl;   /* 0: auto; 1: SIMT kernels; 2: tensor-core (tf32x3) kernels           */
+    int32_t reorth_impl;   /* 0: auto; 1: SIMT; 2: tensor-core TF32x3; 3: tensor-core scaled FP16 split */
     int32_t reserved[7];
 } rbl_options;
 
@@ -172,7 +172,7 @@ int rbl_block_qr(int64_t n, int64_t b, double* u_inout, double* r_out, int32_t* 
  *   qbuf   m blocks, each n x b row-major, contiguous (fp32 when storage_fp32, else fp64)
  *   w      n x (2b) given as two n x b row-major fp64 blocks w0,w1 (Q_i and Q_{i-1})
  *   c_out  optional m*b x 2b row-major coefficients (float or double as storage), may be NULL
- *   impl   0 auto, 1 SIMT, 2 tensor-core */
+ *   impl   0 auto, 1 SIMT, 2 tensor-core TF32x3, 3 tensor-core scaled FP16 split (needs |entries| <= 1) */
 int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qbuf, double* w0, double* w1,
                void* c_out, int impl);
 
