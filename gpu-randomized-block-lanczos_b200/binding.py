@@ -65,6 +65,7 @@ SIGNATURES = {
     "rbl_create_sharded": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P64, _P64, _PD, C.c_int, C.c_int,
                                      C.c_int, C.c_void_p, C.POINTER(RblOptions), C.POINTER(C.c_void_p)]),
     "rbl_destroy": (C.c_int, [C.c_void_p]),
+    "rbl_release_cached_memory": (C.c_int, []),
     "rbl_solve": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _PD, _PD, C.c_void_p, C.POINTER(RblStats)]),
     "rbl_solve_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, _PD, C.c_void_p, C.POINTER(RblStats)]),
     "rbl_buffer_blocks": (C.c_int, [C.c_void_p, C.c_int64, _P64]),

@@ -17,14 +17,57 @@
 #include <cstring>
 #include <future>
 #include <memory>
+#include <mutex>
 #include <thread>
 
 #include "partition.h"
 
 using namespace rbl;
 
+namespace rbl {
+namespace {
+std::mutex g_slab_mu;
+std::vector<std::pair<int, std::pair<unsigned char*, size_t>>> g_slabs;  // (device, (ptr, bytes))
+}  // namespace
+void slab_cache_take(int device, DevBuf<unsigned char>& into) {
+    std::lock_guard<std::mutex> lk(g_slab_mu);
+    for (size_t i = 0; i < g_slabs.size(); ++i)
+        if (g_slabs[i].first == device) {
+            into.p = g_slabs[i].second.first;
+            into.count = g_slabs[i].second.second;
+            g_slabs.erase(g_slabs.begin() + i);
+            return;
+        }
+}
+void slab_cache_park(int device, DevBuf<unsigned char>& from) {
+    if (!from.p) return;
+    std::lock_guard<std::mutex> lk(g_slab_mu);
+    for (auto& e : g_slabs)
+        if (e.first == device) {  // keep the larger one
+            if (e.second.second >= from.count) return;  // `from` is freed by its destructor
+            cudaFree(e.second.first);
+            e.second = {from.p, from.count};
+            from.p = nullptr;
+            from.count = 0;
+            return;
+        }
+    g_slabs.push_back({device, {from.p, from.count}});
+    from.p = nullptr;
+    from.count = 0;
+}
+void slab_cache_release_all() {
+    std::lock_guard<std::mutex> lk(g_slab_mu);
+    for (auto& e : g_slabs) {
+        cudaSetDevice(e.first);
+        cudaFree(e.second.first);
+    }
+    g_slabs.clear();
+}
+}  // namespace rbl
+
 rbl_handle::~rbl_handle() {
     cudaSetDevice(device);
+    rbl::slab_cache_park(device, ws.buf);
     for (auto e : event_pool) cudaEventDestroy(e);
     comm.destroy();
     if (stream) cudaStreamDestroy(stream);
@@ -211,17 +254,21 @@ struct Ctx {
     bool fp32 = false;
     size_t ssz = 8;
     int64_t nloc = 0, next = 0, m_cap = 0, bstride = 0;
-    DevBuf<double> X[3];
-    DevBuf<unsigned char> buf;
-    DevBuf<double> part, small;  // rowop partials; small: G, Ai, Bp, Gloc (4 * B*B)
-    DevBuf<QrState> qr;
-    DevBuf<unsigned char> Cmat, rpart;
-    DevBuf<float> tc_scratch;
+    Workspace& w;
+    DevBuf<double> (&X)[3];
+    DevBuf<unsigned char>& buf;
+    DevBuf<double>&part, &small;  // rowop partials; small: G, Ai, Bp, Gloc (4 * B*B)
+    DevBuf<QrState>& qr;
+    DevBuf<unsigned char>&Cmat, &rpart;
+    DevBuf<float>& tc_scratch;
+    DevBuf<double>& sendbuf;
+    PinnedBuf<double>&hA, &hB;
+    PinnedBuf<QrState>& hqr;
+    explicit Ctx(Workspace& ws)
+        : w(ws), X(ws.X), buf(ws.buf), part(ws.part), small(ws.small), qr(ws.qr), Cmat(ws.Cmat), rpart(ws.rpart),
+          tc_scratch(ws.tc_scratch), sendbuf(ws.sendbuf), hA(ws.hA), hB(ws.hB), hqr(ws.hqr) {}
     bool use_tc = false;
     bool use_h = false;   // FP16-split tensor-core kernels (default when supported); else TF32x3
-    DevBuf<double> sendbuf;
-    PinnedBuf<double> hA, hB;
-    PinnedBuf<QrState> hqr;
     int rgrid = 1;
     int64_t launches = 0;
     PhaseTimer tm;
@@ -329,7 +376,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     if (k > h->n) throw Error(RBL_INVALID, "rbl_solve: k > n");
     if (!d_out || !v_out) throw Error(RBL_INVALID, "rbl_solve: null output");
     RBL_CUDA(cudaSetDevice(h->device));
-    Ctx c;
+    Ctx c(h->ws);
     c.h = h; c.st = h->stream; c.b = (int)b_in; c.B = padded_block(c.b); c.k = k;
     c.fp32 = opt.precision == RBL_PRECISION_MIXED;
     c.ssz = c.fp32 ? 4 : 8;
@@ -344,7 +391,13 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
 
     // ---- memory plan (gpu_buffer_size, RBL_gpu.jl:95-104: how many Krylov blocks fit) ---------------
     size_t free_b = 0, total_b = 0;
+    if (!c.buf.p) slab_cache_take(h->device, c.buf);
     RBL_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    {   // memory already held by this handle's workspace is available to this solve
+        const Workspace& w = h->ws;
+        free_b += w.buf.count + (w.X[0].count + w.X[1].count + w.X[2].count + w.part.count + w.small.count + w.sendbuf.count) * 8 +
+                  w.Cmat.count + w.rpart.count + w.tc_scratch.count * 4;
+    }
     c.rgrid = rowop_grid(B, c.nloc);
     const size_t fixed = 3 * (size_t)c.next * B * 8 + (size_t)c.nloc * 4 * B * 4 + (size_t)c.rgrid * B * B * 8 + (size_t)c.nloc * (size_t)(b + k) * 8 +
                          ((size_t)64 << 20);
@@ -360,24 +413,24 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         }
     }
     c.m_cap = m_cap;
-    for (int i = 0; i < 3; ++i) c.X[i].alloc((size_t)c.next * B);
-    c.buf.alloc((size_t)m_cap * c.bstride * c.ssz);
-    c.part.alloc((size_t)c.rgrid * B * B);
-    c.small.alloc(4 * (size_t)B * B);
-    c.qr.alloc(1);
-    c.Cmat.alloc((size_t)m_cap * B * 2 * B * c.ssz);
-    c.rpart.alloc(std::max<size_t>(1, reorth_max_partial_elems(B, c.fp32, c.nloc, m_cap)) * c.ssz);
+    for (int i = 0; i < 3; ++i) c.X[i].ensure((size_t)c.next * B);
+    c.buf.ensure((size_t)m_cap * c.bstride * c.ssz);
+    c.part.ensure((size_t)c.rgrid * B * B);
+    c.small.ensure(4 * (size_t)B * B);
+    c.qr.ensure(1);
+    c.Cmat.ensure((size_t)m_cap * B * 2 * B * c.ssz);
+    c.rpart.ensure(std::max<size_t>(1, reorth_max_partial_elems(B, c.fp32, c.nloc, m_cap)) * c.ssz);
     c.use_tc = reorth_tc_supported(B, c.fp32) && opt.reorth_impl != 1;
     if (opt.reorth_impl == 2 && !c.use_tc)
         throw Error(RBL_INVALID, "rbl_solve: tensor-core reorth needs precision=mixed and padded block size 16");
     if (opt.reorth_impl == 3 && !c.use_tc)
         throw Error(RBL_INVALID, "rbl_solve: tensor-core reorth needs precision=mixed and padded block size 16");
     c.use_h = c.use_tc && opt.reorth_impl != 2;
-    if (c.use_tc) c.tc_scratch.alloc(std::max(reorth_tc_scratch_floats(B, c.nloc, m_cap), reorth_h_scratch_words(B, c.nloc, m_cap)));
-    if (h->comm.active()) c.sendbuf.alloc(std::max<int64_t>(1, h->send_ptr[h->world]) * (size_t)B);
-    c.hA.alloc((size_t)m_cap * B * B);
-    c.hB.alloc((size_t)m_cap * B * B);
-    c.hqr.alloc(1);
+    if (c.use_tc) c.tc_scratch.ensure(std::max(reorth_tc_scratch_floats(B, c.nloc, m_cap), reorth_h_scratch_words(B, c.nloc, m_cap)));
+    if (h->comm.active()) c.sendbuf.ensure(std::max<int64_t>(1, h->send_ptr[h->world]) * (size_t)B);
+    c.hA.ensure((size_t)m_cap * B * B);
+    c.hB.ensure((size_t)m_cap * B * B);
+    c.hqr.ensure(1);
     const double t_alloc_done = now_s();
     RBL_CUDA(cudaMemsetAsync(c.qr.p, 0, sizeof(QrState), c.st));
     RBL_CUDA(cudaMemsetAsync(c.small.p, 0, 4 * (size_t)B * B * 8, c.st));

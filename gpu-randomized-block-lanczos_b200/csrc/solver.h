@@ -42,6 +42,10 @@ struct DevBuf {
         count = n;
         if (n) RBL_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
     }
+    // grow-only: keeps the allocation when it is already large enough (workspace reuse across solves)
+    void ensure(size_t n) {
+        if (n > count || (n && !p)) alloc(n);
+    }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
@@ -62,6 +66,9 @@ struct PinnedBuf {
         count = n;
         if (n) RBL_CUDA(cudaMallocHost((void**)&p, n * sizeof(T)));
     }
+    void ensure(size_t n) {
+        if (n > count || (n && !p)) alloc(n);
+    }
     void release() {
         if (p) cudaFreeHost(p);
         p = nullptr;
@@ -71,8 +78,30 @@ struct PinnedBuf {
 
 }  // namespace rbl
 
+namespace rbl {
+// Per-handle device workspace, kept between solves (cudaMalloc/cudaFree of the tens-of-GB Krylov slab costs
+// hundreds of ms; CUDA.jl's pool allocator gives the reference the same reuse).  The slab itself is parked in
+// a process-wide cache when a handle is destroyed and picked up by the next handle on the same device;
+// rbl_release_cached_memory() returns it to the driver (the analogue of CUDA.reclaim(), RBL_gpu.jl:201).
+struct Workspace {
+    DevBuf<double> X[3];
+    DevBuf<unsigned char> buf;
+    DevBuf<double> part, small;
+    DevBuf<QrState> qr;
+    DevBuf<unsigned char> Cmat, rpart;
+    DevBuf<float> tc_scratch;
+    DevBuf<double> sendbuf;
+    PinnedBuf<double> hA, hB;
+    PinnedBuf<QrState> hqr;
+};
+void slab_cache_take(int device, DevBuf<unsigned char>& into);
+void slab_cache_park(int device, DevBuf<unsigned char>& from);
+void slab_cache_release_all();
+}  // namespace rbl
+
 struct rbl_handle {
     rbl_options opt{};
+    rbl::Workspace ws;
     int device = 0;
     int64_t n = 0;      // global order
     int64_t row0 = 0;   // first owned row

@@ -128,6 +128,9 @@ int rbl_create_sharded(int64_t n, int64_t row0, int64_t nloc, int64_t nnz_loc, c
                        const void* nccl_uid, const rbl_options* opts, rbl_handle** out);
 
 int rbl_destroy(rbl_handle* h);
+/* The Krylov slab of a destroyed handle is kept for the next handle on the same device (allocation of tens
+ * of GB costs hundreds of ms); this returns it to the driver - the analogue of CUDA.reclaim() (RBL_gpu.jl:201). */
+int rbl_release_cached_memory(void);
 
 /* Replaces the body of RBL_gpu (RBL_gpu.jl:211-220): random start (213-214), lanczos_iteration
  * (134-203) and recover_eigvec (106-132).
