@@ -97,6 +97,7 @@ int rbl_create_sharded(int64_t n, int64_t row0, int64_t nloc, int64_t nnz_loc, c
 
 int rbl_release_cached_memory(void) {
     slab_cache_release_all();
+    Comm::release_cached();
     return RBL_OK;
 }
 

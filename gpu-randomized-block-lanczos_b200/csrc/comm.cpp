@@ -4,6 +4,7 @@
 
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace rbl {
 namespace {
@@ -82,19 +83,49 @@ bool Comm::unique_id(void* uid128, std::string& err) {
     return true;
 }
 
+namespace {
+// Communicators are expensive to create (ncclCommInitRank is a collective of ~1 s); a destroyed handle parks
+// its communicator here and the next handle with the same (device, rank, world) reuses it.  Every rank of a
+// job takes the same decision because every rank created and parked the same communicators in the same order.
+struct Parked { int device, rank, world; void* comm; };
+std::mutex g_comm_mu;
+std::vector<Parked> g_parked;
+}  // namespace
+
 bool Comm::init(const void* uid128, int rank_, int world_, std::string& err) {
     rank = rank_;
     world = world_;
     if (world <= 1) return true;
     if (!ready(err)) return false;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    device_ = dev;
+    {
+        std::lock_guard<std::mutex> lk(g_comm_mu);
+        for (size_t i = 0; i < g_parked.size(); ++i)
+            if (g_parked[i].device == dev && g_parked[i].rank == rank && g_parked[i].world == world) {
+                comm_ = g_parked[i].comm;
+                g_parked.erase(g_parked.begin() + i);
+                return true;
+            }
+    }
     nccl_uid_t id;
     std::memcpy(&id, uid128, sizeof(id));
     return ok(api().CommInitRank(&comm_, world, id, rank), "CommInitRank", err);
 }
 
 void Comm::destroy() {
-    if (comm_) api().CommDestroy(comm_);
+    if (comm_) {
+        std::lock_guard<std::mutex> lk(g_comm_mu);
+        g_parked.push_back(Parked{device_, rank, world, comm_});
+    }
     comm_ = nullptr;
+}
+
+void Comm::release_cached() {
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    for (auto& p : g_parked) api().CommDestroy(p.comm);
+    g_parked.clear();
 }
 
 bool Comm::allreduce_f64(double* buf, size_t count, cudaStream_t st, std::string& err) {

@@ -15,7 +15,8 @@ public:
     bool active() const { return world > 1 && comm_ != nullptr; }
     static bool unique_id(void* uid128, std::string& err);
     bool init(const void* uid128, int rank, int world, std::string& err);
-    void destroy();
+    void destroy();                 // parks the communicator for reuse by the next handle
+    static void release_cached();   // really destroys parked communicators
     // in-place sum all-reduce of `count` doubles / floats on `st`
     bool allreduce_f64(double* buf, size_t count, cudaStream_t st, std::string& err);
     bool allreduce_f32(float* buf, size_t count, cudaStream_t st, std::string& err);
@@ -27,6 +28,7 @@ public:
 
 private:
     void* comm_ = nullptr;
+    int device_ = 0;
 };
 
 }  // namespace rbl

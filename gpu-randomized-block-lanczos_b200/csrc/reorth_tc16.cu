@@ -282,33 +282,34 @@ __global__ void split_coeff_h_kernel(size_t nwords, int B, const float* __restri
 // =================================================================================================
 template <int B>
 struct UpdH {
+    static constexpr int NW = 16;                // warps per CTA
     static constexpr int MT = 2;
     static constexpr int NT = (2 * B) / 8;
-    static constexpr int PA = B + 8;             // floats per staged row: conflict-free float2 A fragments
+    static constexpr int PA = B + 8;             // floats per staged row: conflict-free float2 A fragments, 32-byte multiple
     static constexpr int PC = 2 * B + 8;         // words per staged coefficient row pair
     static constexpr int JC = 8;
-    static constexpr int NST = 4;
+    static constexpr int NST = 3;
     static constexpr int STAGE = 32 * PA;
     static constexpr int CBUF = JC * (B / 2) * PC;
-    static constexpr int ROWS_CTA = 8 * 32;
-    static constexpr size_t smem_bytes = (size_t)(8 * NST * STAGE + 4 * CBUF) * sizeof(float);
+    static constexpr int ROWS_CTA = NW * 32;
+    static constexpr size_t smem_bytes = (size_t)(NW * NST * STAGE + 4 * CBUF) * sizeof(float);
 };
 
 template <int B>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(UpdH<B>::NW * 32, 1)
     reorth_update_h_kernel(int64_t n, int64_t m, const float* __restrict__ buf, int64_t bstride,
                            const unsigned* __restrict__ Ch, const unsigned* __restrict__ Cl, float scale_a,
                            const float* __restrict__ scale_c_ptr, double* __restrict__ w0, double* __restrict__ w1,
                            float* __restrict__ store_w1) {
     using C = UpdH<B>;
-    constexpr int MT = C::MT, NT = C::NT, PA = C::PA, PC = C::PC, JC = C::JC, NST = C::NST, STAGE = C::STAGE,
-                  CBUF = C::CBUF;
+    constexpr int NW = C::NW, MT = C::MT, NT = C::NT, PA = C::PA, PC = C::PC, JC = C::JC, NST = C::NST, STAGE = C::STAGE,
+                  CBUF = C::CBUF, NTHR = NW * 32;
     static_assert(B == 16, "instantiated for B = 16");
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     float* sA = smem + (size_t)warp * NST * STAGE;
-    unsigned* sC = reinterpret_cast<unsigned*>(smem + (size_t)8 * NST * STAGE);  // [2][hi,lo][JC][B/2][PC]
+    unsigned* sC = reinterpret_cast<unsigned*>(smem + (size_t)NW * NST * STAGE);  // [2][hi,lo][JC][B/2][PC]
     const int64_t r0 = (int64_t)blockIdx.x * C::ROWS_CTA + (int64_t)warp * 32;
     const int mi = (int)m;
 
@@ -320,31 +321,43 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
             for (int y = 0; y < 4; ++y) acc[a][x][y] = 0.f;
 
+    // per-lane constants of the 4 copies of a stage (32 rows x B floats of one stored block)
+    constexpr int NCP = (32 * (B / 4)) / 32;
+    const float* src0[NCP];
+    int dst0[NCP];
+    bool row_ok[NCP];
+#pragma unroll
+    for (int u = 0; u < NCP; ++u) {
+        const int q = lane + 32 * u;
+        const int row = q / (B / 4), c4 = q % (B / 4);
+        row_ok[u] = (r0 + row) < n;
+        dst0[u] = row * PA + c4 * 4;
+        src0[u] = buf + (size_t)(row_ok[u] ? r0 + row : 0) * B + c4 * 4;
+    }
     auto issue_a = [&](int j) {
         float* st = sA + (size_t)(j % NST) * STAGE;
+        const size_t adv = (size_t)j * bstride;
 #pragma unroll
-        for (int u = 0; u < (32 * (B / 4)) / 32; ++u) {
-            const int q = lane + 32 * u;
-            const int row = q / (B / 4), c4 = q % (B / 4);
-            const bool ok = (j < mi) && (r0 + row < n);
-            const float* src = ok ? buf + (size_t)j * bstride + (size_t)(r0 + row) * B + c4 * 4 : buf;
-            cp_async16(st + row * PA + c4 * 4, src, ok ? 16 : 0);
+        for (int u = 0; u < NCP; ++u) {
+            const bool ok = row_ok[u] && (j < mi);
+            cp_async16(st + dst0[u], ok ? src0[u] + adv : buf, ok ? 16 : 0);
         }
     };
-    auto issue_c = [&](int chunk) {
-        unsigned* dsth = sC + (size_t)((chunk & 1) * 2 + 0) * CBUF;
-        unsigned* dstl = sC + (size_t)((chunk & 1) * 2 + 1) * CBUF;
+    auto issue_c = [&](int chunk) {  // JC blocks x B/2 column pairs x 2B words; threads < 256 copy hi, the rest lo
+        const int half = tid / 256, q0 = tid % 256;
+        unsigned* dst = sC + (size_t)((chunk & 1) * 2 + half) * CBUF;
+        const unsigned* srcb = half ? Cl : Ch;
         const int j0 = chunk * JC;
 #pragma unroll
         for (int u = 0; u < (JC * (B / 2) * (2 * B / 4)) / 256; ++u) {
-            const int q = tid + 256 * u;
+            const int q = q0 + 256 * u;
             const int rowc = q / (2 * B / 4), c4 = q % (2 * B / 4);  // rowc = jb*(B/2) + c/2
             const bool ok = (j0 * (B / 2) + rowc) < mi * (B / 2);
             const size_t off = ((size_t)j0 * (B / 2) + rowc) * (2 * B) + c4 * 4;
-            cp_async16(dsth + rowc * PC + c4 * 4, ok ? Ch + off : Ch, ok ? 16 : 0);
-            cp_async16(dstl + rowc * PC + c4 * 4, ok ? Cl + off : Cl, ok ? 16 : 0);
+            cp_async16(dst + rowc * PC + c4 * 4, ok ? srcb + off : srcb, ok ? 16 : 0);
         }
     };
+    static_assert(NTHR == 512, "coefficient chunk copy assumes 512 threads");
     issue_c(0);
     issue_a(0);
     cp_async_commit();
@@ -521,7 +534,7 @@ void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* b
         configured = true;
     }
     const unsigned grid = (unsigned)((p.n + U::ROWS_CTA - 1) / U::ROWS_CTA);
-    reorth_update_h_kernel<B><<<grid, 256, U::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.ch, s.cl,
+    reorth_update_h_kernel<B><<<grid, U::NW * 32, U::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.ch, s.cl,
                                                                  pick_scale(n_global), s.scale_c, w0, w1, (float*)store_w1);
 }
 
