@@ -186,12 +186,6 @@ inline void axpy(double* y, double a, const double* x, int64_t n) {
     for (int64_t i = 0; i < n; ++i) y[i] += a * x[i];
 }
 
-struct Pair {
-    double theta = 0;
-    double res = 0;  // ||T v - theta v||
-    std::vector<double> v;
-};
-
 struct Work {
     BandLU lu;
     std::vector<double> y, t;
@@ -376,6 +370,80 @@ void extract_cluster(const BandSym& T, Work& wk, double mu, int m, const std::ve
     }
 }
 
+// Orthonormal eigenvector bases for (nearly) degenerate eigenvalues: vectors of eigenvalues closer than a few
+// ctol are orthonormalised and rotated to Ritz vectors (a duplicate is regenerated inside the cluster), and
+// independently converged vectors of eigenvalues closer than 1e-5 ||T|| get their eps/gap cross-components
+// removed (like LAPACK dstein's ortol).  *dup is set when a vector of the loose pass vanishes (two inputs were
+// the same eigenvector).
+void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, bool* dup) {
+    const double tn = std::max(T.norm_inf, 1e-300);
+    const double ctol = 2e-11 * tn;
+    // final pass: neighbouring eigenvalues closer than a few ctol must have orthogonal vectors
+    std::sort(out.begin(), out.end(), [](const Pair& a, const Pair& b) { return a.theta < b.theta; });
+    size_t g0 = 0;
+    Work wk2;
+    while (g0 < out.size()) {
+        size_t g1 = g0 + 1;
+        while (g1 < out.size() && out[g1].theta - out[g1 - 1].theta <= 4 * ctol) ++g1;
+        if (g1 - g0 >= 2) {
+            std::vector<std::vector<double>> X;
+            for (size_t j = g0; j < g1; ++j) X.push_back(out[j].v);
+            std::vector<const std::vector<double>*> none;
+            // duplicate detection: a vector that (nearly) vanishes under MGS is regenerated
+            for (size_t j = 0; j < X.size(); ++j) {
+                std::vector<std::vector<double>> head(X.begin(), X.begin() + j + 1);
+                double keep = mgs(head, j, none, T.N);
+                if (keep < 0.5) {
+                    double mu_c = 0.5 * (out[g0].theta + out[g1 - 1].theta);
+                    wk2.lu.factor(T, mu_c + 5e-15 * tn);
+                    ++wk2.nfac;
+                    std::vector<const std::vector<double>*> ag;
+                    for (size_t i = 0; i < j; ++i) ag.push_back(&X[i]);
+                    std::vector<std::vector<double>> one(1);
+                    wk2.random_unit(one[0], T.N);
+                    for (int it = 0; it < 4; ++it) {
+                        mgs(one, 0, ag, T.N);
+                        wk2.lu.solve(one[0].data());
+                        scal(one[0].data(), 1.0 / nrm2(one[0].data(), T.N), T.N);
+                    }
+                    mgs(one, 0, ag, T.N);
+                    X[j] = one[0];
+                } else {
+                    X[j] = head[j];
+                }
+            }
+            std::vector<double> theta, res;
+            rayleigh_ritz(T, X, theta, res);
+            std::vector<size_t> ord(X.size());
+            for (size_t j = 0; j < ord.size(); ++j) ord[j] = j;
+            std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return theta[a] < theta[b]; });
+            for (size_t j = 0; j < ord.size(); ++j) {
+                out[g0 + j].theta = theta[ord[j]];
+                out[g0 + j].res = res[ord[j]];
+                out[g0 + j].v = X[ord[j]];
+            }
+        }
+        g0 = g1;
+    }
+    // loose pass (like LAPACK dstein's ortol): independently converged vectors of eigenvalues closer than
+    // 1e-5 ||T|| carry an eps/gap component of each other; remove it by Gram-Schmidt in eigenvalue order
+    const double otol = 1e-5 * tn;
+    for (size_t j = 1; j < out.size(); ++j) {
+        bool touched = false;
+        for (size_t i = j; i-- > 0;) {
+            if (out[j].theta - out[i].theta > otol) break;
+            axpy(out[j].v.data(), -dot(out[i].v.data(), out[j].v.data(), T.N), out[i].v.data(), T.N);
+            touched = true;
+        }
+        if (touched) {
+            double nn = nrm2(out[j].v.data(), T.N);
+            if (nn < 0.5 && dup) *dup = true;
+            if (nn > 0) scal(out[j].v.data(), 1.0 / nn, T.N);
+        }
+    }
+    nfac += wk2.nfac;
+}
+
 struct Interval {
     double lo, hi;
     int64_t clo, chi;  // eigenvalues below lo / below hi
@@ -513,69 +581,11 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
             for (auto& p : f) out.push_back(std::move(p));
     }
 
-    // final pass: neighbouring eigenvalues closer than a few ctol must have orthogonal vectors
-    std::sort(out.begin(), out.end(), [](const Pair& a, const Pair& b) { return a.theta < b.theta; });
-    size_t g0 = 0;
-    Work wk2;
-    while (g0 < out.size()) {
-        size_t g1 = g0 + 1;
-        while (g1 < out.size() && out[g1].theta - out[g1 - 1].theta <= 4 * ctol) ++g1;
-        if (g1 - g0 >= 2) {
-            std::vector<std::vector<double>> X;
-            for (size_t j = g0; j < g1; ++j) X.push_back(out[j].v);
-            std::vector<const std::vector<double>*> none;
-            // duplicate detection: a vector that (nearly) vanishes under MGS is regenerated
-            for (size_t j = 0; j < X.size(); ++j) {
-                std::vector<std::vector<double>> head(X.begin(), X.begin() + j + 1);
-                double keep = mgs(head, j, none, T.N);
-                if (keep < 0.5) {
-                    double mu_c = 0.5 * (out[g0].theta + out[g1 - 1].theta);
-                    wk2.lu.factor(T, mu_c + 5e-15 * tn);
-                    ++wk2.nfac;
-                    std::vector<const std::vector<double>*> ag;
-                    for (size_t i = 0; i < j; ++i) ag.push_back(&X[i]);
-                    std::vector<std::vector<double>> one(1);
-                    wk2.random_unit(one[0], T.N);
-                    for (int it = 0; it < 4; ++it) {
-                        mgs(one, 0, ag, T.N);
-                        wk2.lu.solve(one[0].data());
-                        scal(one[0].data(), 1.0 / nrm2(one[0].data(), T.N), T.N);
-                    }
-                    mgs(one, 0, ag, T.N);
-                    X[j] = one[0];
-                } else {
-                    X[j] = head[j];
-                }
-            }
-            std::vector<double> theta, res;
-            rayleigh_ritz(T, X, theta, res);
-            std::vector<size_t> ord(X.size());
-            for (size_t j = 0; j < ord.size(); ++j) ord[j] = j;
-            std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return theta[a] < theta[b]; });
-            for (size_t j = 0; j < ord.size(); ++j) {
-                out[g0 + j].theta = theta[ord[j]];
-                out[g0 + j].res = res[ord[j]];
-                out[g0 + j].v = X[ord[j]];
-            }
-        }
-        g0 = g1;
+    {
+        int64_t nf2 = 0;
+        finalize_pairs(T, out, nf2, nullptr);
+        fac += nf2;
     }
-    // loose pass (like LAPACK dstein's ortol): independently converged vectors of eigenvalues closer than
-    // 1e-5 ||T|| carry an eps/gap component of each other; remove it by Gram-Schmidt in eigenvalue order
-    const double otol = 1e-5 * tn;
-    for (size_t j = 1; j < out.size(); ++j) {
-        bool touched = false;
-        for (size_t i = j; i-- > 0;) {
-            if (out[j].theta - out[i].theta > otol) break;
-            axpy(out[j].v.data(), -dot(out[i].v.data(), out[j].v.data(), T.N), out[i].v.data(), T.N);
-            touched = true;
-        }
-        if (touched) {
-            double nn = nrm2(out[j].v.data(), T.N);
-            if (nn > 0) scal(out[j].v.data(), 1.0 / nn, T.N);
-        }
-    }
-    fac += wk2.nfac;
     nfac += fac.load();
 }
 
@@ -596,6 +606,80 @@ double resid_bound(const double* bi, int b, const std::vector<double>& s) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ BandTopK
+void BandTopK::set_seeds(const std::vector<double>& d, const std::vector<double>& svec, int64_t Ns, int64_t k) {
+    if ((int64_t)d.size() < k || (int64_t)svec.size() < Ns * k) return;
+    seeds_.clear();
+    seeds_.resize(k);
+    for (int64_t j = 0; j < k; ++j) {
+        seeds_[j].theta = d[j];
+        seeds_[j].v.assign(svec.begin() + (size_t)j * Ns, svec.begin() + (size_t)(j + 1) * Ns);
+    }
+}
+
+// All k seed pairs refined for the current T by inverse iteration (zero-padded start vectors), in parallel.
+bool BandTopK::refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pairs, int64_t& nfac) {
+    const int64_t N = T.N;
+    const double tn = std::max(T.norm_inf, 1e-300);
+    pairs.assign(k, Pair());
+    std::atomic<int64_t> next{0};
+    std::atomic<int64_t> fac{0};
+    std::atomic<bool> failed{false};
+    auto worker = [&]() {
+        Work wk;
+        for (;;) {
+            const int64_t j = next.fetch_add(1);
+            if (j >= k || failed.load()) break;
+            std::vector<double> x(N, 0.0);
+            std::copy(seeds_[j].v.begin(), seeds_[j].v.end(), x.begin());
+            const double nn = nrm2(x.data(), N);
+            if (!(nn > 0)) { failed = true; break; }
+            scal(x.data(), 1.0 / nn, N);
+            double th, rs;
+            rayleigh(T, x, wk.t, th, rs);
+            bool ok = rs <= 2e-13 * tn;
+            for (int round = 0; round < 6 && !ok; ++round) {
+                const double sg = th < 0 ? -1.0 : 1.0;
+                const double off = (rs <= 1e-6 * tn) ? 2.0 * rs : 0.0;
+                wk.lu.factor(T, th - sg * off);
+                ++wk.nfac;
+                for (int it = 0; it < 4; ++it) {
+                    wk.y = x;
+                    wk.lu.solve(wk.y.data());
+                    const double n2 = nrm2(wk.y.data(), N);
+                    if (!(n2 > 0) || !std::isfinite(n2)) break;
+                    scal(wk.y.data(), 1.0 / n2, N);
+                    x.swap(wk.y);
+                    const double prev = rs;
+                    rayleigh(T, x, wk.t, th, rs);
+                    if (rs <= 2e-13 * tn) { ok = true; break; }
+                    if (rs > 0.25 * prev) break;
+                }
+                if (!ok && rs <= 1e-11 * tn && round >= 1) ok = true;
+            }
+            if (!ok) { failed = true; break; }
+            pairs[j].theta = th;
+            pairs[j].res = rs;
+            pairs[j].v.swap(x);
+        }
+        fac += wk.nfac;
+    };
+    const int nt = (int)std::min<int64_t>(std::max(1, threads), k);
+    if (nt <= 1) {
+        worker();
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(worker);
+        for (auto& t : th) t.join();
+    }
+    nfac += fac.load();
+    if (failed.load()) return false;
+    bool dup = false;
+    int64_t nf2 = 0;
+    finalize_pairs(T, pairs, nf2, &dup);
+    nfac += nf2;
+    return !dup;
+}
+
 // Decision procedure (identical outcome to dsbev + sort_eig_abs + check_convergence, common.jl:36-65):
 //   "not converged" needs ONE Ritz pair among the k largest |lambda| whose bound ||B_i s_last|| exceeds tol;
 //   "converged" needs all k of them.
@@ -702,6 +786,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     auto reject_with = [&](std::vector<double>& x, double th, double rho, const char* how) {
         wit_.assign(1, x);
         wit_theta_.assign(1, th);
+        R.witness_rho = rho;
         if (verbose > 1)
             std::fprintf(stderr, "[rbl] check N=%lld %s theta=%.12g rho=%.3e (nfac=%d)\n", (long long)N, how, th, rho, wk.nfac);
         return finish(false);
@@ -793,11 +878,28 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
 
     // ---- stage 3: all k pairs of largest |lambda| --------------------------------------------------------
     ++full_checks;
+    std::vector<Pair> pairs;
+    bool from_seeds = false;
+    if ((int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N) {
+        // fast path: the k pairs of an earlier full solve (any earlier T) refined in parallel, then validated:
+        // exactly k eigenvalues may have magnitude >= the smallest one found
+        int64_t nf = 0;
+        if (refine_seeds(T, k, pairs, nf)) {
+            std::stable_sort(pairs.begin(), pairs.end(),
+                             [](const Pair& a, const Pair& b2) { return std::fabs(a.theta) > std::fabs(b2.theta); });
+            const double tk = std::fabs(pairs[k - 1].theta);
+            const double delta = std::max(1e-11 * tk, 1e-13 * tn);
+            from_seeds = (count_abs_above(std::max(0.0, tk - delta)).above == k);
+        }
+        wk.nfac += (int)nf;
+        if (!from_seeds) pairs.clear();
+        if (verbose > 0) std::fprintf(stderr, "[rbl] full check N=%lld from seeds: %s\n", (long long)N, from_seeds ? "ok" : "rejected");
+    }
     // bracket the k-th largest |lambda|: largest x_lo with #{|lambda| > x_lo} >= k (within a modest surplus)
     double x_lo = 0.0, x_hi = g;
     Cnt c_lo{0, 0, N};
     bool have_clo = false;
-    for (int it = 0; it < 60; ++it) {
+    for (int it = 0; it < 60 && !from_seeds; ++it) {
         if (c_lo.above >= k && c_lo.above <= k + std::max<int64_t>(2, k / 8)) break;
         if (x_hi - x_lo <= 1e-13 * tn) break;
         const double xm = 0.5 * (x_lo + x_hi);
@@ -811,10 +913,11 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     } else {
         roots.push_back(Interval{-g, g, 0, N});
     }
-    std::vector<Pair> pairs;
-    int64_t nf = 0;
-    slice(T, roots, threads, pairs, nf);
-    wk.nfac += (int)nf;
+    if (!from_seeds) {
+        int64_t nf = 0;
+        slice(T, roots, threads, pairs, nf);
+        wk.nfac += (int)nf;
+    }
     // sort_eig_abs: k largest |lambda|, returned by descending |lambda|
     std::stable_sort(pairs.begin(), pairs.end(),
                      [](const Pair& a, const Pair& b2) { return std::fabs(a.theta) > std::fabs(b2.theta); });
@@ -842,6 +945,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         wit_.push_back(pairs[order[j].second].v);
         wit_theta_.push_back(pairs[order[j].second].theta);
     }
+    if (kk == k) seeds_ = pairs;  // the next full check starts from these
     if (kk == k) {  // seeds for the stage-2 brackets of the next check
         const int64_t margin = std::max<int64_t>(1, std::min<int64_t>(k / 6, k - 1));
         const int64_t ia = std::max<int64_t>(0, k - 1 - margin - margin / 2);

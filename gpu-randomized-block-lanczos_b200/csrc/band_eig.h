@@ -42,6 +42,12 @@ struct BandLU {
     void solve(double* v) const;
 };
 
+struct Pair {
+    double theta = 0;
+    double res = 0;  // ||T v - theta v||
+    std::vector<double> v;
+};
+
 struct TopKResult {
     bool converged = false;
     int64_t N = 0;
@@ -49,6 +55,7 @@ struct TopKResult {
     std::vector<double> s;      // N x k column-major eigenvectors (same order)
     std::vector<double> resid;  // k residual bounds ||B_i s_last||
     bool have_all = false;      // d/s/resid hold all k pairs (full check ran)
+    double witness_rho = -1.0;  // residual bound of the pair that proved non-convergence (stages 1-2), else -1
     int factorizations = 0;
 };
 
@@ -64,9 +71,14 @@ public:
     // T: current N x N band matrix; bi: b x b upper-triangular B_i row-major (bi[r*b+c]); k wanted.
     // force_full: compute all k pairs even when a witness already proves non-convergence.
     TopKResult check(const BandSym& T, const double* bi, int b, int64_t k, double tol, bool force_full);
-    void reset() { wit_.clear(); wit_theta_.clear(); xA_ = xB_ = stepA_ = stepB_ = 0; }
+    void reset() { wit_.clear(); wit_theta_.clear(); xA_ = xB_ = stepA_ = stepB_ = 0; seeds_.clear(); }
+    // k Ritz pairs of an EARLIER T (d: k values, svec: Ns x k column-major): starting points of the next full check
+    void set_seeds(const std::vector<double>& d, const std::vector<double>& svec, int64_t Ns, int64_t k);
+    bool has_seeds() const { return !seeds_.empty(); }
 
 private:
+    bool refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pairs, int64_t& nfac);
+    std::vector<Pair> seeds_;
     std::vector<std::vector<double>> wit_;  // Ritz vectors of T that failed the bound at the last check
     std::vector<double> wit_theta_;
     double xA_ = 0, xB_ = 0;                // stage-2 bracket points of the last check (lower bounds for the next)

@@ -497,16 +497,34 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         T.update_norm();
     };
     double t_eig = 0.0;
+    // Once the witness pair is within two decades of the tolerance, a background full eigensolve of the current
+    // T provides seed pairs; the accepting check then only refines them (see BandTopK::refine_seeds).
+    std::future<TopKResult> seed_job;
+    bool seed_started = false;
     auto run_check = [&](int64_t it, bool force_full) -> TopKResult {
         cudaSetDevice(h->device);
         cudaEventSynchronize(step_event[it]);
         const double t0 = now_s();
         grow_T(it);
+        if (seed_job.valid() && seed_job.wait_for(std::chrono::seconds(0)) == std::future_status::ready) {
+            TopKResult sr = seed_job.get();
+            if (sr.have_all) checker.set_seeds(sr.d, sr.s, sr.N, k);
+        }
         std::vector<double> Bi((size_t)b * b);
         const double* Bm = c.hB.p + (size_t)(it - 1) * B * B;
         for (int r = 0; r < b; ++r)
             for (int cc = 0; cc < b; ++cc) Bi[(size_t)r * b + cc] = Bm[r * B + cc];
         TopKResult r = checker.check(T, Bi.data(), b, k, opt.tol, force_full);
+        if (!r.converged && !seed_started && !checker.has_seeds() && r.witness_rho >= 0.0 && r.witness_rho < 100.0 * opt.tol &&
+            T.N >= 512) {
+            seed_started = true;
+            const int nthreads = std::max(1, checker.threads - 1);
+            seed_job = std::async(std::launch::async, [Tc = T, k, b, nthreads]() {
+                BandTopK tmp;
+                tmp.threads = nthreads;
+                return tmp.check(Tc, nullptr, b, k, 0.0, true);
+            });
+        }
         t_eig += now_s() - t0;
         if (opt.verbose > 1)
             std::fprintf(stderr, "[rbl] check it=%lld N=%lld nfac=%d took %.2f ms conv=%d\n", (long long)it, (long long)T.N,

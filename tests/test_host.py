@@ -182,3 +182,29 @@ def test_halo_plan_random_sparsity(rbl):
         ref = partition_oracle.halo_plan(500, 4, rs, rank, Al.indptr, Al.indices)
         for a, b_ in zip(out, ref):
             assert np.array_equal(a, b_)
+
+
+def test_seeded_full_check_matches_dsbev(rbl):
+    """The accepting check refines the pairs of an earlier full solve (seeds) instead of slicing from scratch:
+    same eigenvalues as dsbev, orthonormal Ritz vectors, same residual bounds (a 3-D Laplacian has many
+    degenerate Ritz values, the hard case for the seeded path)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from tools.replay_checks import capture
+    N, k, b = 12, 24, 8
+    A = matrices.shifted(matrices.laplacian_3d(N), 12.0)
+    Om = np.random.default_rng(2).standard_normal((N ** 3, b))
+    Ts, Bs, oks = capture(A, k, b, Om)
+    assert oks[-1] and len(Ts) >= 3
+    ck = rbl.Checker(threads=2)
+    for T, Bi in zip(Ts[-3:], Bs[-3:]):
+        r = ck.check(T, k, Bi, force_full=True)       # 1st: slicing; 2nd and 3rd: from the seeds of the previous one
+        assert r["have_all"]
+        w, z = rbl_oracle.dsbev(T)
+        Dr, Vr = rbl_oracle.sort_eig_abs(w, z, k)
+        assert np.max(np.abs(r["D"] - Dr[::-1])) < 1e-11 * 12
+        S = r["S"]
+        assert np.max(np.abs(S.T @ S - np.eye(k))) < 1e-8
+        M = rbl_oracle.dense_band_from_T(T)
+        assert np.max(np.linalg.norm(M @ S - S * r["D"][None, :], axis=0)) < 1e-10 * 12
+    assert r["converged"] == oks[-1]
