@@ -262,7 +262,10 @@ def main():
     e0.record()
     agg = {}
     for _ in range(args.steps):
+        tw = time.perf_counter()
         D, stats = solver.solve_device(K_WANTED, BLOCK, om_dev.data_ptr(), v_dev.data_ptr())
+        if args.verbose:
+            print(f"[bench] solve wall {time.perf_counter() - tw:.3f} s, library t_total {stats.t_total:.3f} s", file=sys.stderr)
         for f, v in stats.as_dict().items():
             agg[f] = agg.get(f, 0) + v
     e1.record()

@@ -880,16 +880,24 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     ++full_checks;
     std::vector<Pair> pairs;
     bool from_seeds = false;
-    if ((int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N) {
+    if ((int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N &&
+        (int64_t)seeds_[0].v.size() * 5 >= N * 4) {  // seeds of a T at least 80% as large: close to the current pairs
         // fast path: the k pairs of an earlier full solve (any earlier T) refined in parallel, then validated:
         // exactly k eigenvalues may have magnitude >= the smallest one found
         int64_t nf = 0;
         if (refine_seeds(T, k, pairs, nf)) {
             std::stable_sort(pairs.begin(), pairs.end(),
                              [](const Pair& a, const Pair& b2) { return std::fabs(a.theta) > std::fabs(b2.theta); });
+            // validation: with t_k the smallest magnitude found, every eigenvalue strictly above the (possibly
+            // degenerate) cluster at t_k must have been found, and the cluster must reach rank k
             const double tk = std::fabs(pairs[k - 1].theta);
-            const double delta = std::max(1e-11 * tk, 1e-13 * tn);
-            from_seeds = (count_abs_above(std::max(0.0, tk - delta)).above == k);
+            const double delta = std::max(1e-10 * tk, 1e-12 * tn);
+            int64_t found_above = 0;
+            for (int64_t j = 0; j < k; ++j)
+                if (std::fabs(pairs[j].theta) > tk + delta) ++found_above;
+            const int64_t c_hi = count_abs_above(tk + delta).above;
+            const int64_t c_lo = count_abs_above(std::max(0.0, tk - delta)).above;
+            from_seeds = (c_hi == found_above) && (c_lo >= k);
         }
         wk.nfac += (int)nf;
         if (!from_seeds) pairs.clear();

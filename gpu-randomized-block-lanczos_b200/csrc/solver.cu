@@ -395,7 +395,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     RBL_CUDA(cudaMemGetInfo(&free_b, &total_b));
     {   // memory already held by this handle's workspace is available to this solve
         const Workspace& w = h->ws;
-        free_b += w.buf.count + (w.X[0].count + w.X[1].count + w.X[2].count + w.part.count + w.small.count + w.sendbuf.count) * 8 +
+        free_b += w.buf.count + w.ritzS.count + w.ritzV.count + w.omega.count * 8 + (w.X[0].count + w.X[1].count + w.X[2].count + w.part.count + w.small.count + w.sendbuf.count) * 8 +
                   w.Cmat.count + w.rpart.count + w.tc_scratch.count * 4;
     }
     c.rgrid = rowop_grid(B, c.nloc);
@@ -437,14 +437,14 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     for (int i = 0; i < 3; ++i) RBL_CUDA(cudaMemsetAsync(c.X[i].p, 0, (size_t)c.next * B * 8, c.st));
 
     // ---- start block: Q1 = thin-Q of qr(A * Omega)                              RBL_gpu.jl:213-214 ----
-    DevBuf<double> d_omega;
+    DevBuf<double>& d_omega = h->ws.omega;
     const double* om_dev = nullptr;
     {
         const double t0 = now_s();
         if (omega && omega_on_device) {
             om_dev = omega;
         } else {
-            d_omega.alloc((size_t)c.nloc * b);
+            d_omega.ensure((size_t)c.nloc * b);
             if (omega) {
                 RBL_CUDA(cudaMemcpyAsync(d_omega.p, omega, (size_t)c.nloc * b * 8, cudaMemcpyHostToDevice, c.st));
             } else {
@@ -515,7 +515,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         for (int r = 0; r < b; ++r)
             for (int cc = 0; cc < b; ++cc) Bi[(size_t)r * b + cc] = Bm[r * B + cc];
         TopKResult r = checker.check(T, Bi.data(), b, k, opt.tol, force_full);
-        if (!r.converged && !seed_started && !checker.has_seeds() && r.witness_rho >= 0.0 && r.witness_rho < 100.0 * opt.tol &&
+        if (!r.converged && !seed_started && r.witness_rho >= 0.0 && r.witness_rho < 100.0 * opt.tol &&
             T.N >= 512) {
             seed_started = true;
             const int nthreads = std::max(1, checker.threads - 1);
@@ -776,15 +776,17 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
                     if (c.fp32) reinterpret_cast<float*>(Sh.data())[idx] = (float)v;   // cu() narrows S, RBL_gpu.jl:119
                     else reinterpret_cast<double*>(Sh.data())[idx] = v;
                 }
-        DevBuf<unsigned char> dS, dV;
-        dS.alloc(Sh.size());
+        const double tr0 = now_s();
+        DevBuf<unsigned char>&dS = h->ws.ritzS, &dV = h->ws.ritzV;
+        dS.ensure(Sh.size());
         RBL_CUDA(cudaMemcpyAsync(dS.p, Sh.data(), Sh.size(), cudaMemcpyHostToDevice, c.st));
         const size_t vsz = opt.v_fp32 ? 4 : 8;
         void* Vdev = v_out;
         if (!v_on_device) {
-            dV.alloc((size_t)c.nloc * k * vsz);
+            dV.ensure((size_t)c.nloc * k * vsz);
             Vdev = dV.p;
         }
+        const double tr1 = now_s();
         c.tm.mark(PH_RITZ);
         launch_ritz(B, c.fp32, c.nloc, mfin, (int)k, kpad, c.buf.p, c.bstride, dS.p, Vdev, c.nloc, opt.v_fp32, c.st);
         ++c.launches;
@@ -797,12 +799,15 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             RBL_CUDA(cudaMemcpy(v_out, dV.p, (size_t)c.nloc * k * vsz, cudaMemcpyDeviceToHost));
             stats.t_d2h = now_s() - t0;
         }
+        if (opt.verbose) std::fprintf(stderr, "[rbl] ritz section: setup %.3f kernel+sync %.3f\n", tr1 - tr0, now_s() - tr1 - stats.t_d2h);
     }
     for (int64_t t = 0; t < k; ++t) d_out[t] = final_res.d[t];
     RBL_CUDA(cudaMemcpy(c.hqr.p, c.qr.p, sizeof(QrState), cudaMemcpyDeviceToHost));
 
     double sec[PH_COUNT];
+    const double tc0 = now_s();
     c.tm.collect(sec);
+    if (opt.verbose) std::fprintf(stderr, "[rbl] event collect %.3f s (%zu events)\n", now_s() - tc0, c.tm.used);
     fill_stats(&stats, c, sec);
     stats.iterations = final_i;
     stats.kryl_sz = final_i * b;
@@ -817,6 +822,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     stats.t_total = now_s() - t_begin;
     if (c.hqr.p->bad) status = RBL_BREAKDOWN;
     if (stats_out) *stats_out = stats;
+    if (opt.verbose) std::fprintf(stderr, "[rbl] seed job: started=%d pending=%d\n", (int)seed_started, (int)seed_job.valid());
     if (opt.verbose)
         std::fprintf(stderr, "[rbl] timeline: alloc %.3f  start+loop %.3f  final-check %.3f  ritz+d2h %.3f (d2h %.3f, h2d %.3f)\n",
                      t_alloc_done - t_begin, t_loop_done - t_alloc_done, t_final_done - t_loop_done,

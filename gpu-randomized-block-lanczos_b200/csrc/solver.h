@@ -91,6 +91,8 @@ struct Workspace {
     DevBuf<unsigned char> Cmat, rpart;
     DevBuf<float> tc_scratch;
     DevBuf<double> sendbuf;
+    DevBuf<unsigned char> ritzS, ritzV;   // Ritz coefficient matrix and (host-output solves) the device copy of V
+    DevBuf<double> omega;
     PinnedBuf<double> hA, hB;
     PinnedBuf<QrState> hqr;
 };
