@@ -79,20 +79,51 @@ void BandSym::matvec(const double* x, double* y) const {
 void BandLU::factor(const BandSym& T, double shift) {
     N = T.N;
     kd = T.kd;
+    shift_ = shift;
+    P_ = 1;
+    nneg = 0;
+    ck_row = -1;
+    run(T, 0);
+}
+
+// T grew at its end only (Lanczos appends block rows; rows < N_old - kd are unchanged) and the shift is the
+// same: restore the state saved just before row N_old - kd and eliminate only the new / changed rows.
+bool BandLU::resume(const BandSym& T) {
+    if (ck_row < 0 || T.kd != kd || T.N < N || ck_row > T.N) return false;
+    const int W = 2 * kd + 1;
+    const int64_t r0 = ck_row;
+    const int64_t c0 = std::max<int64_t>(0, r0 - kd);
+    std::copy(ck_U.begin(), ck_U.begin() + (size_t)(r0 - c0) * W, U.begin() + (size_t)c0 * W);
+    P_ = ck_P;
+    nneg = ck_nneg;
+    N = T.N;
+    run(T, r0);
+    return true;
+}
+
+void BandLU::run(const BandSym& T, int64_t r_start) {
     const int W = 2 * kd + 1;
     U.resize((size_t)N * W);
     L.resize((size_t)N * std::max(kd, 1));
     sw.resize((size_t)N * std::max(kd, 1));
     w.assign((size_t)3 * kd + 2, 0.0);
+    const double shift = shift_;
     const double pivmin = std::max(T.norm_inf, 1e-290) * 1e-20;
-    int P = 1;
-    nneg = 0;
+    int P = P_;
     double* __restrict__ wp = w.data();
     double* __restrict__ Ubase = U.data();
     double* __restrict__ Lbase = L.data();
     uint8_t* __restrict__ swbase = sw.data();
     const double* __restrict__ Fbase = T.F.data();
-    for (int64_t r = 0; r < N; ++r) {
+    const int64_t ck_at = N - kd;  // rows >= this change when T grows
+    for (int64_t r = r_start; r < N; ++r) {
+        if (r == ck_at && ck_at >= 0) {
+            const int64_t c0 = std::max<int64_t>(0, r - kd);
+            ck_U.assign(Ubase + (size_t)c0 * W, Ubase + (size_t)r * W);
+            ck_P = P;
+            ck_nneg = nneg;
+            ck_row = r;
+        }
         const int64_t base = r - kd;
         const double* __restrict__ row = Fbase + (size_t)r * W;
         for (int t = 0; t < W; ++t) wp[t] = row[t];
@@ -142,6 +173,7 @@ void BandLU::factor(const BandSym& T, double shift) {
         if (cur != prev) ++nneg;
         P = cur;
     }
+    P_ = P;
 }
 
 void BandLU::solve(double* v) const {
@@ -732,12 +764,22 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     // side of the Ritz value, so the Sturm count of the last factorisation bounds the rank of the pair from
     // above without any further factorisation.  Returns false if the iteration does not settle.
     struct Refined { double theta, res; int64_t larger; };
-    auto refine = [&](std::vector<double>& x, bool have_factor, double sigma0, int64_t cnt0, Refined& out) -> bool {
+    // `lu` is the factorisation object to use; with try_resume it may still hold the factorisation of the
+    // previous (smaller) T at a shift next to this Ritz value, which is then extended instead of recomputed
+    auto refine = [&](BandLU& lu, bool try_resume, std::vector<double>& x, bool have_factor, double sigma0, int64_t cnt0,
+                      Refined& out) -> bool {
         double th, rs;
         rayleigh(T, x, wk.t, th, rs);
         double sigma = sigma0;
         int64_t cnt_sigma = cnt0;
         bool ok = false;
+        if (try_resume && !have_factor && lu.ck_row >= 0 && std::fabs(lu.shift_ - th) <= 1e-9 * tn &&
+            ((th >= 0) ? (lu.shift_ < th) : (lu.shift_ > th)) && lu.resume(T)) {
+            have_factor = true;
+            sigma = lu.shift_;
+            cnt_sigma = lu.nneg;
+            ++resumed_factorizations;
+        }
         for (int round = 0; round < 7 && !ok; ++round) {
             if (round > 0 || !have_factor) {
                 // Rayleigh-quotient shifts while far from convergence (cubic); once close, step to the inner
@@ -745,13 +787,13 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
                 const double sg = th < 0 ? -1.0 : 1.0;
                 const double off = (rs <= 1e-6 * tn) ? 2.0 * rs : 0.0;
                 sigma = th - sg * off;
-                wk.lu.factor(T, sigma);
+                lu.factor(T, sigma);
                 ++wk.nfac;
-                cnt_sigma = wk.lu.nneg;
+                cnt_sigma = lu.nneg;
             }
             for (int it = 0; it < 4; ++it) {
                 wk.y = x;
-                wk.lu.solve(wk.y.data());
+                lu.solve(wk.y.data());
                 const double n2 = nrm2(wk.y.data(), N);
                 if (!(n2 > 0) || !std::isfinite(n2)) break;
                 scal(wk.y.data(), 1.0 / n2, N);
@@ -784,6 +826,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         return true;
     };
     auto reject_with = [&](std::vector<double>& x, double th, double rho, const char* how) {
+        if (std::strcmp(how, "witness") != 0) wlu_.ck_row = -1;
         wit_.assign(1, x);
         wit_theta_.assign(1, th);
         R.witness_rho = rho;
@@ -802,7 +845,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
             if (!(nn > 0)) continue;
             scal(x.data(), 1.0 / nn, N);
             Refined rf;
-            const bool rok = refine(x, false, 0.0, 0, rf);
+            const bool rok = refine(wi == 0 ? wlu_ : wk.lu, wi == 0, x, false, 0.0, 0, rf);
             if (verbose > 2) std::fprintf(stderr, "[rbl]   stage1 w%zu ok=%d theta=%.10g res=%.2e larger=%lld rho=%.3e\n", wi, (int)rok, rf.theta, rf.res, (long long)rf.larger, rok ? resid_bound(bi, b, x) : -1.0);
             if (!rok) continue;
             const double rho = resid_bound(bi, b, x);
@@ -868,7 +911,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
                 scal(v.data(), 1.0 / n2, N);
             }
             Refined rf;
-            const bool rok = refine(v, true, x, wk.lu.nneg, rf);
+            const bool rok = refine(wk.lu, false, v, true, x, wk.lu.nneg, rf);
             if (verbose > 2) std::fprintf(stderr, "[rbl]   stage2 refine ok=%d theta=%.10g res=%.2e larger=%lld rho=%.3e\n", (int)rok, rf.theta, rf.res, (long long)rf.larger, rok ? resid_bound(bi, b, v) : -1.0);
             if (!rok) continue;
             const double rho = resid_bound(bi, b, v);

@@ -38,8 +38,21 @@ struct BandLU {
     std::vector<uint8_t> sw;  // N x kd swap flags
     std::vector<double> w;
     int64_t nneg = 0;         // number of eigenvalues of T below the shift
+    double shift_ = 0.0;
     void factor(const BandSym& T, double shift);
+    bool resume(const BandSym& T);  // same shift, T extended at its end: re-eliminates only the last rows
     void solve(double* v) const;
+    // state saved just before row N - kd (the first row that changes when T grows)
+    int64_t ck_row = -1;
+    std::vector<double> ck_U;
+    int ck_P = 1;
+    int64_t ck_nneg = 0;
+
+private:
+    void run(const BandSym& T, int64_t r_start);
+    int P_ = 1;
+
+public:
 };
 
 struct Pair {
@@ -66,6 +79,7 @@ public:
     int threads = 1;
     int verbose = 0;
     int64_t total_factorizations = 0;
+    int64_t resumed_factorizations = 0;  // witness factorisations extended from the previous check instead of recomputed
     int full_checks = 0;
 
     // T: current N x N band matrix; bi: b x b upper-triangular B_i row-major (bi[r*b+c]); k wanted.
@@ -79,6 +93,7 @@ public:
 private:
     bool refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pairs, int64_t& nfac);
     std::vector<Pair> seeds_;
+    BandLU wlu_;                            // factorisation kept for the first witness between checks
     std::vector<std::vector<double>> wit_;  // Ritz vectors of T that failed the bound at the last check
     std::vector<double> wit_theta_;
     double xA_ = 0, xB_ = 0;                // stage-2 bracket points of the last check (lower bounds for the next)
