@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--precision", default="mixed")
     ap.add_argument("--verbose", type=int, default=0)
     args = ap.parse_args()
+    # keep stdout to the one JSON line: NCCL prints its version banner to stdout at INFO/VERSION level
+    os.environ["NCCL_DEBUG"] = os.environ.get("RBL_NCCL_DEBUG", "WARN")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -7,7 +7,11 @@
 #include "band_eig.h"
 
 #include <algorithm>
+#if defined(__AVX2__)
+#include <immintrin.h>
+#endif
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -102,6 +106,18 @@ bool BandLU::resume(const BandSym& T) {
 }
 
 void BandLU::run(const BandSym& T, int64_t r_start) {
+    switch (kd) {  // compile-time band widths for the common block sizes: fixed-length vector loops
+        case 4: run_t<4>(T, r_start); break;
+        case 8: run_t<8>(T, r_start); break;
+        case 16: run_t<16>(T, r_start); break;
+        case 32: run_t<32>(T, r_start); break;
+        default: run_t<0>(T, r_start); break;
+    }
+}
+
+template <int KD>
+void BandLU::run_t(const BandSym& T, int64_t r_start) {
+    const int kd = KD > 0 ? KD : this->kd;
     const int W = 2 * kd + 1;
     U.resize((size_t)N * W);
     L.resize((size_t)N * std::max(kd, 1));
@@ -181,11 +197,18 @@ void BandLU::solve(double* v) const {
     for (int64_t r = 0; r < N; ++r) {
         const int64_t base = r - kd;
         const int64_t cstart = base < 0 ? 0 : base;
+        const double* __restrict__ Lr = &L[(size_t)r * kd];
+        const uint8_t* __restrict__ sr = &sw[(size_t)r * kd];
+        double vr = v[r];
         for (int64_t c = cstart; c < r; ++c) {
             const int wi = (int)(c - base);
-            if (sw[(size_t)r * kd + wi]) std::swap(v[c], v[r]);
-            v[r] -= L[(size_t)r * kd + wi] * v[c];
+            const double vc = v[c];
+            const bool s = sr[wi] != 0;
+            const double pc = s ? vr : vc, qr = s ? vc : vr;
+            v[c] = pc;
+            vr = qr - Lr[wi] * pc;
         }
+        v[r] = vr;
     }
     for (int64_t r = N - 1; r >= 0; --r) {
         const double* Ur = &U[(size_t)r * W];
@@ -753,7 +776,11 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         c.above = (N - c.below_pos) + c.below_neg;
         return c;
     };
+    const auto t_start = std::chrono::steady_clock::now();
+    int stage_now = 0;
     auto finish = [&](bool conv) {
+        stage_hits[stage_now]++;
+        stage_sec[stage_now] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
         R.converged = conv;
         R.factorizations = wk.nfac;
         total_factorizations += wk.nfac;
@@ -773,7 +800,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         double sigma = sigma0;
         int64_t cnt_sigma = cnt0;
         bool ok = false;
-        if (try_resume && !have_factor && lu.ck_row >= 0 && std::fabs(lu.shift_ - th) <= 1e-9 * tn &&
+        if (try_resume && !have_factor && lu.ck_row >= 0 && std::fabs(lu.shift_ - th) <= 1e-6 * tn &&
             ((th >= 0) ? (lu.shift_ < th) : (lu.shift_ > th)) && lu.resume(T)) {
             have_factor = true;
             sigma = lu.shift_;
@@ -819,6 +846,25 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
                 pos = N - wk.lu.nneg;
             }
             out.larger = (cnt_sigma - 1) + pos;
+        } else if (try_resume) {
+            // the shift in hand is on the outer side: one more factorisation just inside the Ritz value gives the
+            // rigorous rank bound and is what the next check extends (BandLU::resume)
+            const double delta = std::max(1e-10 * std::fabs(th), 1e-12 * tn);
+            const double sg = th < 0 ? -1.0 : 1.0;
+            lu.factor(T, th - sg * delta);
+            ++wk.nfac;
+            int64_t other = 0;
+            if (sg > 0) {
+                other = neg_side(std::fabs(th));
+                out.larger = (N - lu.nneg - 1) + other;
+            } else {
+                if (std::fabs(th) <= T.gersh_hi) {
+                    wk.lu.factor(T, std::fabs(th));
+                    ++wk.nfac;
+                    other = N - wk.lu.nneg;
+                }
+                out.larger = (lu.nneg - 1) + other;
+            }
         } else {
             const double delta = std::max(1e-12 * std::fabs(th), 1e-14 * tn);
             out.larger = count_abs_above(std::fabs(th) + delta).above;
@@ -853,6 +899,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         }
     }
 
+    stage_now = 1;
     // ---- stage 2: a pair found from a shift x with a <= #{|lambda| > x} <= hi (hi <= k-1) ----------------
     // The eigenvalue nearest to such an x has rank <= hi+1 <= k on either side of x, so whatever inverse
     // iteration at x converges to is one of the k wanted pairs.  First a target a little inside the wanted
@@ -921,6 +968,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
 
     // ---- stage 3: all k pairs of largest |lambda| --------------------------------------------------------
     ++full_checks;
+    stage_now = 2;
     std::vector<Pair> pairs;
     bool from_seeds = false;
     if ((int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N &&

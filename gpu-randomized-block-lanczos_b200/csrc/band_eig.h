@@ -50,6 +50,8 @@ struct BandLU {
 
 private:
     void run(const BandSym& T, int64_t r_start);
+    template <int KD>
+    void run_t(const BandSym& T, int64_t r_start);
     int P_ = 1;
 
 public:
@@ -79,7 +81,10 @@ public:
     int threads = 1;
     int verbose = 0;
     int64_t total_factorizations = 0;
-    int64_t resumed_factorizations = 0;  // witness factorisations extended from the previous check instead of recomputed
+    int64_t resumed_factorizations = 0;
+    // where the decisions came from and what they cost (seconds): [0] witness, [1] bracketed pair, [2] full
+    int stage_hits[3] = {0, 0, 0};
+    double stage_sec[3] = {0, 0, 0};  // witness factorisations extended from the previous check instead of recomputed
     int full_checks = 0;
 
     // T: current N x N band matrix; bi: b x b upper-triangular B_i row-major (bi[r*b+c]); k wanted.

@@ -822,6 +822,10 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     stats.t_total = now_s() - t_begin;
     if (c.hqr.p->bad) status = RBL_BREAKDOWN;
     if (stats_out) *stats_out = stats;
+    if (opt.verbose)
+        std::fprintf(stderr, "[rbl] host checks: witness %d (%.3f s), bracketed %d (%.3f s), full %d (%.3f s); factorisations %lld (+%lld resumed)\n",
+                     checker.stage_hits[0], checker.stage_sec[0], checker.stage_hits[1], checker.stage_sec[1], checker.stage_hits[2],
+                     checker.stage_sec[2], (long long)checker.total_factorizations, (long long)checker.resumed_factorizations);
     if (opt.verbose) std::fprintf(stderr, "[rbl] seed job: started=%d pending=%d\n", (int)seed_started, (int)seed_job.valid());
     if (opt.verbose)
         std::fprintf(stderr, "[rbl] timeline: alloc %.3f  start+loop %.3f  final-check %.3f  ritz+d2h %.3f (d2h %.3f, h2d %.3f)\n",
