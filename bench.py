@@ -151,7 +151,7 @@ def cpu_reference(iterations_needed: int | None, budget_steps: int = 20):
     }
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, out=sys.stdout):
     if rank != 0:
         return
     cb = cpu_reference(None, budget_steps=args.ref_steps)
@@ -164,7 +164,8 @@ def run_reference(args, rank):
         "e2e": {"value": cb["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def config_dict(ngpu):
@@ -186,13 +187,16 @@ def main():
     ap.add_argument("--precision", default="mixed")
     ap.add_argument("--verbose", type=int, default=0)
     args = ap.parse_args()
-    # keep stdout to the one JSON line: NCCL prints its version banner to stdout at INFO/VERSION level
-    os.environ["NCCL_DEBUG"] = os.environ.get("RBL_NCCL_DEBUG", "WARN")
+    # keep stdout to the ONE JSON line: libraries (NCCL prints its version banner) write to fd 1, so point fd 1
+    # at stderr for the whole run and print the result line on the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, real_stdout)
         return
 
     import torch
@@ -370,7 +374,8 @@ def main():
                   "checks": int(round(agg["checks"] / steps)), "full_checks": int(round(agg["full_checks"] / steps)),
                   "max_rel_eig_err_vs_analytic": eig_err, "host_cores": cores},
     }
-    print(json.dumps(line))
+    real_stdout.write(json.dumps(line) + "\n")
+    real_stdout.flush()
     if dist is not None:
         dist.destroy_process_group()
 

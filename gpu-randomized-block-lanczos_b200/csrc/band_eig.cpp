@@ -972,7 +972,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     std::vector<Pair> pairs;
     bool from_seeds = false;
     if ((int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N &&
-        (int64_t)seeds_[0].v.size() * 5 >= N * 4) {  // seeds of a T at least 80% as large: close to the current pairs
+        (int64_t)seeds_[0].v.size() * 10 >= N * 7) {  // seeds of a T at least 70% as large: close to the current pairs
         // fast path: the k pairs of an earlier full solve (any earlier T) refined in parallel, then validated:
         // exactly k eigenvalues may have magnitude >= the smallest one found
         int64_t nf = 0;

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -26,48 +27,52 @@ using namespace rbl;
 
 namespace rbl {
 namespace {
-std::mutex g_slab_mu;
-std::vector<std::pair<int, std::pair<unsigned char*, size_t>>> g_slabs;  // (device, (ptr, bytes))
-}  // namespace
-void slab_cache_take(int device, DevBuf<unsigned char>& into) {
-    std::lock_guard<std::mutex> lk(g_slab_mu);
-    for (size_t i = 0; i < g_slabs.size(); ++i)
-        if (g_slabs[i].first == device) {
-            into.p = g_slabs[i].second.first;
-            into.count = g_slabs[i].second.second;
-            g_slabs.erase(g_slabs.begin() + i);
-            return;
-        }
+std::mutex g_ws_mu;
+std::vector<std::pair<int, Workspace*>> g_parked_ws;  // (device, workspace)
+size_t ws_bytes(const Workspace& w) {
+    return w.buf.count + w.ritzV.count + w.ritzS.count + w.Cmat.count + w.rpart.count + w.tc_scratch.count * 4 +
+           (w.X[0].count + w.X[1].count + w.X[2].count + w.omega.count + w.part.count + w.sendbuf.count) * 8;
 }
-void slab_cache_park(int device, DevBuf<unsigned char>& from) {
-    if (!from.p) return;
-    std::lock_guard<std::mutex> lk(g_slab_mu);
-    for (auto& e : g_slabs)
+}  // namespace
+Workspace* workspace_take(int device) {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    for (size_t i = 0; i < g_parked_ws.size(); ++i)
+        if (g_parked_ws[i].first == device) {
+            Workspace* w = g_parked_ws[i].second;
+            g_parked_ws.erase(g_parked_ws.begin() + i);
+            return w;
+        }
+    return new Workspace();
+}
+void workspace_park(int device, Workspace* ws) {
+    if (!ws) return;
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    for (auto& e : g_parked_ws)
         if (e.first == device) {  // keep the larger one
-            if (e.second.second >= from.count) return;  // `from` is freed by its destructor
-            cudaFree(e.second.first);
-            e.second = {from.p, from.count};
-            from.p = nullptr;
-            from.count = 0;
+            if (ws_bytes(*e.second) >= ws_bytes(*ws)) {
+                delete ws;
+            } else {
+                delete e.second;
+                e.second = ws;
+            }
             return;
         }
-    g_slabs.push_back({device, {from.p, from.count}});
-    from.p = nullptr;
-    from.count = 0;
+    g_parked_ws.push_back({device, ws});
 }
 void slab_cache_release_all() {
-    std::lock_guard<std::mutex> lk(g_slab_mu);
-    for (auto& e : g_slabs) {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    for (auto& e : g_parked_ws) {
         cudaSetDevice(e.first);
-        cudaFree(e.second.first);
+        delete e.second;
     }
-    g_slabs.clear();
+    g_parked_ws.clear();
 }
 }  // namespace rbl
 
 rbl_handle::~rbl_handle() {
     cudaSetDevice(device);
-    rbl::slab_cache_park(device, ws.buf);
+    rbl::workspace_park(device, wsp);
+    wsp = nullptr;
     for (auto e : event_pool) cudaEventDestroy(e);
     comm.destroy();
     if (stream) cudaStreamDestroy(stream);
@@ -115,6 +120,7 @@ rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, co
     if (dev >= ndev) throw Error(RBL_INVALID, "rbl_create: device ordinal out of range");
     h->device = dev;
     RBL_CUDA(cudaSetDevice(dev));
+    h->wsp = workspace_take(dev);
     RBL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->n = n; h->row0 = row0; h->nloc = nloc; h->nnz = nnz; h->rank = rank; h->world = world;
     const double t0 = now_s();
@@ -376,7 +382,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     if (k > h->n) throw Error(RBL_INVALID, "rbl_solve: k > n");
     if (!d_out || !v_out) throw Error(RBL_INVALID, "rbl_solve: null output");
     RBL_CUDA(cudaSetDevice(h->device));
-    Ctx c(h->ws);
+    Ctx c(h->ws_ref());
     c.h = h; c.st = h->stream; c.b = (int)b_in; c.B = padded_block(c.b); c.k = k;
     c.fp32 = opt.precision == RBL_PRECISION_MIXED;
     c.ssz = c.fp32 ? 4 : 8;
@@ -391,10 +397,9 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
 
     // ---- memory plan (gpu_buffer_size, RBL_gpu.jl:95-104: how many Krylov blocks fit) ---------------
     size_t free_b = 0, total_b = 0;
-    if (!c.buf.p) slab_cache_take(h->device, c.buf);
     RBL_CUDA(cudaMemGetInfo(&free_b, &total_b));
     {   // memory already held by this handle's workspace is available to this solve
-        const Workspace& w = h->ws;
+        const Workspace& w = h->ws_ref();
         free_b += w.buf.count + w.ritzS.count + w.ritzV.count + w.omega.count * 8 + (w.X[0].count + w.X[1].count + w.X[2].count + w.part.count + w.small.count + w.sendbuf.count) * 8 +
                   w.Cmat.count + w.rpart.count + w.tc_scratch.count * 4;
     }
@@ -437,7 +442,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     for (int i = 0; i < 3; ++i) RBL_CUDA(cudaMemsetAsync(c.X[i].p, 0, (size_t)c.next * B * 8, c.st));
 
     // ---- start block: Q1 = thin-Q of qr(A * Omega)                              RBL_gpu.jl:213-214 ----
-    DevBuf<double>& d_omega = h->ws.omega;
+    DevBuf<double>& d_omega = h->ws_ref().omega;
     const double* om_dev = nullptr;
     {
         const double t0 = now_s();
@@ -497,33 +502,77 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         T.update_norm();
     };
     double t_eig = 0.0;
-    // Once the witness pair is within two decades of the tolerance, a background full eigensolve of the current
-    // T provides seed pairs; the accepting check then only refines them (see BandTopK::refine_seeds).
-    std::future<TopKResult> seed_job;
-    bool seed_started = false;
+    // Shadow tracker (rank 0): once the witness bound drops below 1e5 * tol a background thread keeps computing
+    // ALL k Ritz pairs of the latest T snapshot - by slicing the first time, by refining its own previous pairs
+    // afterwards (BandTopK::refine_seeds) - so that the accepting check only has to refine fresh seeds instead of
+    // solving the eigenproblem from scratch while the device sits idle.
+    struct Shadow {
+        std::mutex mu;
+        std::condition_variable cv;
+        std::thread th;
+        bool active = false, stop = false, have_req = false, have_res = false;
+        BandSym req;
+        TopKResult res;
+    } shadow;
+    auto shadow_loop = [&shadow, k, b](int nthreads) {
+        BandTopK tracker;
+        tracker.threads = nthreads;
+        for (;;) {
+            BandSym Tc;
+            {
+                std::unique_lock<std::mutex> lk(shadow.mu);
+                shadow.cv.wait(lk, [&] { return shadow.stop || shadow.have_req; });
+                if (shadow.stop) return;
+                Tc = std::move(shadow.req);
+                shadow.have_req = false;
+            }
+            TopKResult r = tracker.check(Tc, nullptr, b, k, 0.0, true);
+            std::lock_guard<std::mutex> lk(shadow.mu);
+            if (r.have_all) {
+                shadow.res = std::move(r);
+                shadow.have_res = true;
+            }
+        }
+    };
+    struct ShadowJoin {  // stops the tracker on every exit path
+        Shadow& s;
+        ~ShadowJoin() {
+            {
+                std::lock_guard<std::mutex> lk(s.mu);
+                s.stop = true;
+            }
+            s.cv.notify_all();
+            if (s.th.joinable()) s.th.join();
+        }
+    } shadow_join{shadow};
     auto run_check = [&](int64_t it, bool force_full) -> TopKResult {
         cudaSetDevice(h->device);
         cudaEventSynchronize(step_event[it]);
         const double t0 = now_s();
         grow_T(it);
-        if (seed_job.valid() && seed_job.wait_for(std::chrono::seconds(0)) == std::future_status::ready) {
-            TopKResult sr = seed_job.get();
-            if (sr.have_all) checker.set_seeds(sr.d, sr.s, sr.N, k);
+        if (shadow.active) {
+            std::lock_guard<std::mutex> lk(shadow.mu);
+            if (shadow.have_res) {
+                checker.set_seeds(shadow.res.d, shadow.res.s, shadow.res.N, k);
+                shadow.have_res = false;
+            }
         }
         std::vector<double> Bi((size_t)b * b);
         const double* Bm = c.hB.p + (size_t)(it - 1) * B * B;
         for (int r = 0; r < b; ++r)
             for (int cc = 0; cc < b; ++cc) Bi[(size_t)r * b + cc] = Bm[r * B + cc];
         TopKResult r = checker.check(T, Bi.data(), b, k, opt.tol, force_full);
-        if (!r.converged && !seed_started && r.witness_rho >= 0.0 && r.witness_rho < 100.0 * opt.tol &&
-            T.N >= 512) {
-            seed_started = true;
-            const int nthreads = std::max(1, checker.threads - 1);
-            seed_job = std::async(std::launch::async, [Tc = T, k, b, nthreads]() {
-                BandTopK tmp;
-                tmp.threads = nthreads;
-                return tmp.check(Tc, nullptr, b, k, 0.0, true);
-            });
+        if (!r.converged && !shadow.active && r.witness_rho >= 0.0 && r.witness_rho < 1e5 * opt.tol && T.N >= 256) {
+            shadow.active = true;
+            shadow.th = std::thread(shadow_loop, std::max(1, checker.threads - 1));
+        }
+        if (!r.converged && shadow.active) {
+            {
+                std::lock_guard<std::mutex> lk(shadow.mu);
+                shadow.req = T;  // snapshot (a few MB)
+                shadow.have_req = true;
+            }
+            shadow.cv.notify_all();
         }
         t_eig += now_s() - t0;
         if (opt.verbose > 1)
@@ -777,7 +826,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
                     else reinterpret_cast<double*>(Sh.data())[idx] = v;
                 }
         const double tr0 = now_s();
-        DevBuf<unsigned char>&dS = h->ws.ritzS, &dV = h->ws.ritzV;
+        DevBuf<unsigned char>&dS = h->ws_ref().ritzS, &dV = h->ws_ref().ritzV;
         dS.ensure(Sh.size());
         RBL_CUDA(cudaMemcpyAsync(dS.p, Sh.data(), Sh.size(), cudaMemcpyHostToDevice, c.st));
         const size_t vsz = opt.v_fp32 ? 4 : 8;
@@ -826,7 +875,6 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         std::fprintf(stderr, "[rbl] host checks: witness %d (%.3f s), bracketed %d (%.3f s), full %d (%.3f s); factorisations %lld (+%lld resumed)\n",
                      checker.stage_hits[0], checker.stage_sec[0], checker.stage_hits[1], checker.stage_sec[1], checker.stage_hits[2],
                      checker.stage_sec[2], (long long)checker.total_factorizations, (long long)checker.resumed_factorizations);
-    if (opt.verbose) std::fprintf(stderr, "[rbl] seed job: started=%d pending=%d\n", (int)seed_started, (int)seed_job.valid());
     if (opt.verbose)
         std::fprintf(stderr, "[rbl] timeline: alloc %.3f  start+loop %.3f  final-check %.3f  ritz+d2h %.3f (d2h %.3f, h2d %.3f)\n",
                      t_alloc_done - t_begin, t_loop_done - t_alloc_done, t_final_done - t_loop_done,

@@ -96,14 +96,17 @@ struct Workspace {
     PinnedBuf<double> hA, hB;
     PinnedBuf<QrState> hqr;
 };
-void slab_cache_take(int device, DevBuf<unsigned char>& into);
-void slab_cache_park(int device, DevBuf<unsigned char>& from);
+// process-wide cache of whole workspaces (one per device): a destroyed handle parks its workspace, the next
+// handle on that device adopts it
+Workspace* workspace_take(int device);
+void workspace_park(int device, Workspace* ws);
 void slab_cache_release_all();
 }  // namespace rbl
 
 struct rbl_handle {
     rbl_options opt{};
-    rbl::Workspace ws;
+    rbl::Workspace* wsp = nullptr;   // adopted from / returned to the process-wide cache
+    rbl::Workspace& ws_ref() { return *wsp; }
     int device = 0;
     int64_t n = 0;      // global order
     int64_t row0 = 0;   // first owned row
