@@ -215,7 +215,7 @@ def main():
     n = L.shape[0]
     Om = omega(n, BLOCK)
     cores = os.cpu_count() or 1
-    host_threads = max(1, cores // max(world, 1))
+    host_threads = cores  # only rank 0 evaluates the host eigen-checks, so it may use every core of the box
     opt_kw = dict(max_kryl_sz=MAX_KRYL, precision=B.PRECISION_MIXED if args.precision == "mixed" else B.PRECISION_FP64,
                   op=B.OP_SHIFT_MINUS_A, sigma=SIGMA, device=local_rank, async_check=1, host_threads=host_threads,
                   verbose=args.verbose)

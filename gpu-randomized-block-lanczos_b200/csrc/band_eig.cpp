@@ -7,6 +7,7 @@
 #include "band_eig.h"
 
 #include <algorithm>
+#include <array>
 #if defined(__AVX2__)
 #include <immintrin.h>
 #endif
@@ -448,7 +449,10 @@ void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, boo
             for (size_t j = 0; j < X.size(); ++j) {
                 std::vector<std::vector<double>> head(X.begin(), X.begin() + j + 1);
                 double keep = mgs(head, j, none, T.N);
-                if (keep < 0.5) {
+                if (keep < 0.5 && dup) {  // seeded mode: two seeds collapsed onto one eigenvector - the caller must not trust the set
+                    *dup = true;
+                    X[j] = head[j];
+                } else if (keep < 0.5) {
                     double mu_c = 0.5 * (out[g0].theta + out[g1 - 1].theta);
                     wk2.lu.factor(T, mu_c + 5e-15 * tn);
                     ++wk2.nfac;
@@ -497,6 +501,39 @@ void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, boo
         }
     }
     nfac += wk2.nfac;
+}
+
+// One eigenpair with eigenvalue in (lo,hi) that is NOT in span(against): Rayleigh-quotient iteration started at the
+// middle of the interval, with the given (accurate) eigenvectors projected out of every iterate.
+bool deflated_rqi(const BandSym& T, Work& wk, double lo, double hi, const std::vector<const std::vector<double>*>& against,
+                  Pair& out) {
+    const int64_t N = T.N;
+    const double tn = std::max(T.norm_inf, 1e-300);
+    std::vector<std::vector<double>> X(1);
+    wk.random_unit(X[0], N);
+    mgs(X, 0, against, N);
+    double mu = 0.5 * (lo + hi);
+    double th = mu, rs = 1e300;
+    for (int round = 0; round < 10; ++round) {
+        wk.lu.factor(T, mu);
+        ++wk.nfac;
+        for (int it = 0; it < 2; ++it) {
+            wk.lu.solve(X[0].data());
+            const double nn = nrm2(X[0].data(), N);
+            if (!(nn > 0) || !std::isfinite(nn)) { wk.random_unit(X[0], N); }
+            else scal(X[0].data(), 1.0 / nn, N);
+            mgs(X, 0, against, N);
+        }
+        rayleigh(T, X[0], wk.t, th, rs);
+        if (rs <= 2e-13 * tn) break;
+        // stay inside the interval: a Ritz value outside means the iterate is still dominated by other directions
+        mu = (th > lo && th < hi) ? th : 0.5 * (lo + hi) + (round + 1) * 0.07 * (hi - lo) * ((round & 1) ? 1.0 : -1.0);
+    }
+    if (!(rs <= 1e-11 * tn) || !(th > lo && th < hi)) return false;
+    out.theta = th;
+    out.res = rs;
+    out.v = X[0];
+    return true;
 }
 
 struct Interval {
@@ -972,11 +1009,13 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     std::vector<Pair> pairs;
     bool from_seeds = false;
     if ((int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N &&
-        (int64_t)seeds_[0].v.size() * 10 >= N * 7) {  // seeds of a T at least 70% as large: close to the current pairs
+        (int64_t)seeds_[0].v.size() * 10 >= N * 5) {  // seeds of a T at least half as large; the validation below decides
         // fast path: the k pairs of an earlier full solve (any earlier T) refined in parallel, then validated:
         // exactly k eigenvalues may have magnitude >= the smallest one found
         int64_t nf = 0;
-        if (refine_seeds(T, k, pairs, nf)) {
+        int64_t dbg_chi = -1, dbg_found = -1, dbg_clo = -1;
+        const bool refined = refine_seeds(T, k, pairs, nf);
+        if (refined) {
             std::stable_sort(pairs.begin(), pairs.end(),
                              [](const Pair& a, const Pair& b2) { return std::fabs(a.theta) > std::fabs(b2.theta); });
             // validation: with t_k the smallest magnitude found, every eigenvalue strictly above the (possibly
@@ -989,10 +1028,86 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
             const int64_t c_hi = count_abs_above(tk + delta).above;
             const int64_t c_lo = count_abs_above(std::max(0.0, tk - delta)).above;
             from_seeds = (c_hi == found_above) && (c_lo >= k);
+            dbg_chi = c_hi; dbg_found = found_above; dbg_clo = c_lo;
+            if (!from_seeds && c_hi > found_above && c_hi - found_above <= 24 && pairs[k - 1].theta > 0 && neg_side(tk) == 0) {
+                // Repair: a few Ritz values have entered the wanted set since the seeds were computed.  With the
+                // found values f_1 >= f_2 >= ... the number of missing eigenvalues above f_j is
+                // a_j = #{lambda > f_j + delta} - #{found > f_j + delta} (non-decreasing in j): locate the gaps where it
+                // increases by bisection over j, then extract the missing pairs by deflated RQI inside each gap.
+                std::vector<double> f(k);
+                for (int64_t j = 0; j < k; ++j) f[j] = pairs[j].theta;
+                auto missing_above = [&](int64_t j) -> int64_t {  // j in [0,k): above f_j ; j == k: above t_k - delta
+                    const double x = (j < k) ? f[j] + delta : std::max(0.0, tk - delta);
+                    int64_t fa = 0;
+                    for (int64_t i = 0; i < k; ++i)
+                        if (f[i] > x) ++fa;
+                    wk.lu.factor(T, x);
+                    ++wk.nfac;
+                    return (N - wk.lu.nneg) - fa;
+                };
+                struct Gap { int64_t j; int64_t count; };  // missing eigenvalues between f_j (upper) and f_{j+1} (lower)
+                std::vector<Gap> gaps;
+                bool bad = false;
+                std::vector<std::array<int64_t, 4>> stack;  // (jlo, jhi, a_lo, a_hi)
+                const int64_t a0 = missing_above(0), aK = c_hi - found_above;
+                if (a0 > 0) gaps.push_back(Gap{-1, a0});  // above the largest found value
+                stack.push_back({0, k - 1, a0, aK});
+                // a at index k-1 ("above t_k + delta") equals aK by the counts already taken
+                while (!stack.empty() && !bad) {
+                    auto cur = stack.back();
+                    stack.pop_back();
+                    const int64_t jl = cur[0], jh = cur[1], al = cur[2], ah = cur[3];
+                    if (ah < al) { bad = true; break; }
+                    if (ah == al) continue;
+                    if (jh - jl == 1) { gaps.push_back(Gap{jl, ah - al}); continue; }
+                    const int64_t jm = (jl + jh) / 2;
+                    const int64_t am = missing_above(jm);
+                    stack.push_back({jl, jm, al, am});
+                    stack.push_back({jm, jh, am, ah});
+                }
+                std::vector<Pair> extra;
+                for (size_t gi = 0; gi < gaps.size() && !bad; ++gi) {
+                    const int64_t j = gaps[gi].j;
+                    const double hi_x = (j < 0) ? g : f[j] - delta;
+                    const double lo_x = (j < 0) ? f[0] + delta : f[j + 1] + delta;
+                    if (!(hi_x > lo_x)) { bad = true; break; }
+                    for (int64_t c = 0; c < gaps[gi].count && !bad; ++c) {
+                        std::vector<const std::vector<double>*> against;
+                        for (int64_t i = std::max<int64_t>(0, j - 3); i <= std::min<int64_t>(k - 1, j + 4); ++i) against.push_back(&pairs[i].v);
+                        for (auto& e : extra)
+                            if (e.theta > lo_x && e.theta < hi_x) against.push_back(&e.v);
+                        Pair np;
+                        if (!deflated_rqi(T, wk, lo_x, hi_x, against, np)) { bad = true; break; }
+                        extra.push_back(std::move(np));
+                    }
+                }
+                if (!bad && (int64_t)extra.size() == c_hi - found_above) {
+                    for (auto& e : extra) pairs.push_back(std::move(e));
+                    int64_t nf3 = 0;
+                    bool dup = false;
+                    finalize_pairs(T, pairs, nf3, &dup);
+                    wk.nfac += (int)nf3;
+                    std::stable_sort(pairs.begin(), pairs.end(),
+                                     [](const Pair& a, const Pair& b2) { return std::fabs(a.theta) > std::fabs(b2.theta); });
+                    pairs.resize(k);
+                    // re-validate the repaired set
+                    const double tk2 = std::fabs(pairs[k - 1].theta);
+                    int64_t fa2 = 0;
+                    for (int64_t j = 0; j < k; ++j)
+                        if (std::fabs(pairs[j].theta) > tk2 + delta) ++fa2;
+                    const int64_t c_hi2 = count_abs_above(tk2 + delta).above;
+                    const int64_t c_lo2 = count_abs_above(std::max(0.0, tk2 - delta)).above;
+                    from_seeds = !dup && (c_hi2 == fa2) && (c_lo2 >= k);
+                    if (verbose > 0) std::fprintf(stderr, "[rbl]   repaired %zu entrant(s): %s\n", gaps.size(), from_seeds ? "ok" : "failed");
+                }
+            }
         }
         wk.nfac += (int)nf;
         if (!from_seeds) pairs.clear();
-        if (verbose > 0) std::fprintf(stderr, "[rbl] full check N=%lld from seeds: %s\n", (long long)N, from_seeds ? "ok" : "rejected");
+        if (verbose > 0)
+            std::fprintf(stderr, "[rbl] full check N=%lld from seeds (N_seed=%lld): %s (refined=%d, above t_k: %lld found %lld, >= t_k: %lld, k=%lld)\n",
+                         (long long)N, (long long)seeds_[0].v.size(), from_seeds ? "ok" : "rejected", (int)refined,
+                         (long long)dbg_chi, (long long)dbg_found, (long long)dbg_clo, (long long)k);
     }
     // bracket the k-th largest |lambda|: largest x_lo with #{|lambda| > x_lo} >= k (within a modest surplus)
     double x_lo = 0.0, x_hi = g;

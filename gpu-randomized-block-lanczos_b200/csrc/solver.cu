@@ -502,7 +502,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         T.update_norm();
     };
     double t_eig = 0.0;
-    // Shadow tracker (rank 0): once the witness bound drops below 1e5 * tol a background thread keeps computing
+    // Shadow tracker (rank 0): from the first checks on a background thread keeps computing
     // ALL k Ritz pairs of the latest T snapshot - by slicing the first time, by refining its own previous pairs
     // afterwards (BandTopK::refine_seeds) - so that the accepting check only has to refine fresh seeds instead of
     // solving the eigenproblem from scratch while the device sits idle.
@@ -562,7 +562,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         for (int r = 0; r < b; ++r)
             for (int cc = 0; cc < b; ++cc) Bi[(size_t)r * b + cc] = Bm[r * B + cc];
         TopKResult r = checker.check(T, Bi.data(), b, k, opt.tol, force_full);
-        if (!r.converged && !shadow.active && r.witness_rho >= 0.0 && r.witness_rho < 1e5 * opt.tol && T.N >= 256) {
+        if (!r.converged && !shadow.active && T.N >= 2 * k) {
             shadow.active = true;
             shadow.th = std::thread(shadow_loop, std::max(1, checker.threads - 1));
         }

@@ -208,3 +208,27 @@ def test_seeded_full_check_matches_dsbev(rbl):
         M = rbl_oracle.dense_band_from_T(T)
         assert np.max(np.linalg.norm(M @ S - S * r["D"][None, :], axis=0)) < 1e-10 * 12
     assert r["converged"] == oks[-1]
+
+
+@pytest.mark.parametrize("grid,k,b", [(16, 40, 8), (20, 60, 16)])
+def test_stale_seeds_are_refined_repaired_or_rejected(rbl, grid, k, b):
+    """Seeds taken from a much earlier (smaller) T: the seeded full check must return dsbev's eigenvalues and an
+    orthonormal basis, whether it refines them, repairs missing entrants, or falls back to slicing
+    (regression: two stale seeds once collapsed onto one eigenvector and were accepted)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from tools.replay_checks import capture
+    A = matrices.shifted(matrices.laplacian_3d(grid), 12.0)
+    Om = np.random.default_rng(0).standard_normal((grid ** 3, b))
+    Ts, Bs, oks = capture(A, k, b, Om)
+    w, z = rbl_oracle.dsbev(Ts[-1])
+    Dr, _ = rbl_oracle.sort_eig_abs(w, z, k)
+    for frac in (0.5, 0.55, 0.6, 0.75, 0.9):
+        i0 = int(frac * len(Ts))
+        ck = rbl.Checker(threads=2)
+        assert ck.check(Ts[i0], k, Bs[i0], force_full=True)["have_all"]
+        r = ck.check(Ts[-1], k, Bs[-1], force_full=True)
+        assert r["have_all"]
+        assert np.max(np.abs(r["D"] - Dr[::-1])) < 1e-11 * 12
+        S = r["S"]
+        assert np.max(np.abs(S.T @ S - np.eye(k))) < 1e-8
