@@ -1113,19 +1113,22 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     double x_lo = 0.0, x_hi = g;
     Cnt c_lo{0, 0, N};
     bool have_clo = false;
-    for (int it = 0; it < 60 && !from_seeds; ++it) {
-        if (c_lo.above >= k && c_lo.above <= k + std::max<int64_t>(2, k / 8)) break;
-        if (x_hi - x_lo <= 1e-13 * tn) break;
-        const double xm = 0.5 * (x_lo + x_hi);
-        const Cnt cm = count_abs_above(xm);
-        if (cm.above >= k) { x_lo = xm; c_lo = cm; have_clo = true; } else { x_hi = xm; }
-    }
     std::vector<Interval> roots;
-    if (x_lo > 0 && have_clo) {
-        roots.push_back(Interval{x_lo, g, c_lo.below_pos, N});
-        if (c_lo.below_neg > 0) roots.push_back(Interval{-g, -x_lo, 0, c_lo.below_neg});
-    } else {
-        roots.push_back(Interval{-g, g, 0, N});
+    const bool hinted = false;
+    if (!hinted) {
+        for (int it = 0; it < 60 && !from_seeds; ++it) {
+            if (c_lo.above >= k && c_lo.above <= k + std::max<int64_t>(2, k / 8)) break;
+            if (x_hi - x_lo <= 1e-13 * tn) break;
+            const double xm = 0.5 * (x_lo + x_hi);
+            const Cnt cm = count_abs_above(xm);
+            if (cm.above >= k) { x_lo = xm; c_lo = cm; have_clo = true; } else { x_hi = xm; }
+        }
+        if (x_lo > 0 && have_clo) {
+            roots.push_back(Interval{x_lo, g, c_lo.below_pos, N});
+            if (c_lo.below_neg > 0) roots.push_back(Interval{-g, -x_lo, 0, c_lo.below_neg});
+        } else {
+            roots.push_back(Interval{-g, g, 0, N});
+        }
     }
     if (!from_seeds) {
         int64_t nf = 0;
@@ -1169,7 +1172,8 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         if (stepB_ <= 0) stepB_ = 1e-5 * tn;
     }
     if (verbose > 0)
-        std::fprintf(stderr, "[rbl] full check N=%lld found=%lld worst rho=%.3e conv=%d (nfac=%d)\n", (long long)N,
+        std::fprintf(stderr, "[rbl] full check N=%lld (%s) found=%lld worst rho=%.3e conv=%d (nfac=%d)\n", (long long)N,
+                     from_seeds ? "seeds refined" : (hinted ? "hinted slicing" : "slicing"),
                      (long long)kk, order.empty() ? 0.0 : order[0].first, (int)(all_ok && bi != nullptr), wk.nfac);
     return finish(all_ok && bi != nullptr);
 }
