@@ -473,6 +473,12 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         a.n = c.nloc; a.y = cur; a.do_gram = 1; a.partials = c.part.p;
         c.rowop(a);
         c.block_qr(cur, 1);
+        // a start block of rank 0 (Omega = 0, or A*Omega = 0) spans no Krylov space: report it instead of
+        // iterating on zero columns (the reference's Householder QR would continue with arbitrary unit vectors)
+        RBL_CUDA(cudaMemcpyAsync(c.hqr.p, c.qr.p, sizeof(QrState), cudaMemcpyDeviceToHost, c.st));
+        RBL_CUDA(cudaStreamSynchronize(c.st));
+        if (c.hqr.p->bad) throw Error(RBL_INVALID, "rbl_solve: A*Omega contains non-finite values");
+        if (c.hqr.p->ndeflated >= B) throw Error(RBL_BREAKDOWN, "rbl_solve: the start block A*Omega has rank 0");
     }
 
     // ---- host-side T bookkeeping (insertA!/insertB!, common.jl:9-26) ---------------------------------
