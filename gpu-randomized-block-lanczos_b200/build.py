@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "librbl_b200.so")
-SOURCES = ["kernels.cu", "reorth_tc.cu", "reorth_tc16.cu", "microbench.cu", "solver.cu", "capi.cu", "band_eig.cpp", "comm.cpp", "partition.cpp"]
+SOURCES = ["kernels.cu", "reorth_tc.cu", "reorth_tc16.cu", "reorth_f64.cu", "microbench.cu", "solver.cu", "capi.cu", "band_eig.cpp", "comm.cpp", "partition.cpp"]
 HEADERS = ["kernels.h", "solver.h", "band_eig.h", "comm.h", "partition.h", os.path.join("..", "..", "include", "rbl_b200.h")]
 
 

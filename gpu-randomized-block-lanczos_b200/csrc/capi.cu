@@ -282,7 +282,11 @@ int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qb
         ReorthPlan p = reorth_plan(B, storage_fp32, n, m);
         dC.alloc((size_t)m * B * 2 * B * ssz);
         dpart.alloc(p.partial_elems * ssz);
-        if (tc && impl != 2) {
+        if (impl != 1 && reorth_d_supported(B, storage_fp32)) {
+            launch_reorth_gram_d(p, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, 0);
+            launch_reorth_update_d(p, dbuf.p, n * B, dC.p, W0.dev.p, W1.dev.p, nullptr, 0);
+            RBL_CUDA(cudaDeviceSynchronize());
+        } else if (tc && impl != 2) {
             DevBuf<float> scratch;
             scratch.alloc(reorth_h_scratch_words(B, n, m));
             launch_reorth_gram_h(p, n, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, scratch.p, m, 0);

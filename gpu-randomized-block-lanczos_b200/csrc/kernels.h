@@ -103,6 +103,13 @@ void launch_reorth_coeff_h(const ReorthPlan& p, const void* C, float* scratch, i
 void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t block_stride_elems,
                             double* w0, double* w1, void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st);
 
+// all-fp64 mode: FP64 tensor-core MMA (mma.sync.m8n8k4.f64) + cp.async rings, B = 16 (reorth_f64.cu)
+bool reorth_d_supported(int B, int fp32);
+void launch_reorth_gram_d(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, const double* w0,
+                          const double* w1, void* partials, void* C, cudaStream_t st);
+void launch_reorth_update_d(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, const void* C, double* w0,
+                            double* w1, void* store_w1, cudaStream_t st);
+
 // ---- K6 Ritz vectors -----------------------------------------------------------------------------
 // V[:, t] = sum_j buf_j * S[(j*B .. j*B+B), t];  S device, row-major (m*B) x kpad in the buffer's type;
 // V column-major n x k (ldv), float or double as the buffer.                  RBL_gpu.jl:106-132

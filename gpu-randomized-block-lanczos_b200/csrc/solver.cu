@@ -275,6 +275,7 @@ struct Ctx {
           tc_scratch(ws.tc_scratch), sendbuf(ws.sendbuf), hA(ws.hA), hB(ws.hB), hqr(ws.hqr) {}
     bool use_tc = false;
     bool use_h = false;   // FP16-split tensor-core kernels (default when supported); else TF32x3
+    bool use_d = false;   // all-fp64 mode: FP64 tensor-core kernels
     int rgrid = 1;
     int64_t launches = 0;
     PhaseTimer tm;
@@ -431,6 +432,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     if (opt.reorth_impl == 3 && !c.use_tc)
         throw Error(RBL_INVALID, "rbl_solve: tensor-core reorth needs precision=mixed and padded block size 16");
     c.use_h = c.use_tc && opt.reorth_impl != 2;
+    c.use_d = reorth_d_supported(B, c.fp32) && opt.reorth_impl != 1;
     if (c.use_tc) c.tc_scratch.ensure(std::max(reorth_tc_scratch_floats(B, c.nloc, m_cap), reorth_h_scratch_words(B, c.nloc, m_cap)));
     if (h->comm.active()) c.sendbuf.ensure(std::max<int64_t>(1, h->send_ptr[h->world]) * (size_t)B);
     c.hA.ensure((size_t)m_cap * B * B);
@@ -694,7 +696,17 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             const int64_t m = i - 2;
             ReorthPlan p = reorth_plan(B, c.fp32, c.nloc, m);
             c.tm.mark(PH_RGRAM);
-            if (c.use_h) {
+            if (c.use_d) {
+                launch_reorth_gram_d(p, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.st);
+                c.launches += 2;
+                if (h->comm.active()) {
+                    std::string err;
+                    c.nccl(h->comm.allreduce_f64((double*)c.Cmat.p, (size_t)m * B * 2 * B, c.st, err), err);
+                }
+                c.tm.mark(PH_RUPD);
+                launch_reorth_update_d(p, c.buf.p, c.bstride, c.Cmat.p, cur, prev, c.slot(i - 2), c.st);
+                ++c.launches;
+            } else if (c.use_h) {
                 launch_reorth_gram_h(p, h->n, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.tc_scratch.p, m_cap, c.st);
                 c.launches += 4;
                 if (h->comm.active()) {

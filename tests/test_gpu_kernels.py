@@ -109,6 +109,13 @@ def test_reorth_simt_and_tensor_core_paths(gpu, impl, n, b, m):
     _reorth_case(gpu, n, b, m, True, impl=impl)
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("n,b,m", [(4000, 16, 5), (10007, 16, 70), (700, 16, 33), (70000, 16, 3), (5000, 13, 9), (64, 16, 1)])
+def test_reorth_fp64_simt_and_dmma_paths(gpu, impl, n, b, m):
+    """All-fp64 mode (the reference as shipped): SIMT DFMA kernels (impl 1) and FP64 tensor-core kernels (impl 0)."""
+    _reorth_case(gpu, n, b, m, False, impl=impl)
+
+
 def _reorth_case(gpu, n, b, m, fp32, impl):
     rng = np.random.default_rng(n + m)
     blocks, W0, W1 = _krylov_like(n, b, m, rng)
