@@ -577,7 +577,7 @@ ReorthPlan reorth_plan(int B, int fp32, int64_t n, int64_t m) {
     p.jt = 256 / tpb;
     p.chunks = (int)((m + p.jt - 1) / p.jt);
     if (p.chunks < 1) p.chunks = 1;
-    int64_t target_ctas = (int64_t)num_sms() * 4;
+    int64_t target_ctas = (int64_t)num_sms() * 16;  // >= 8 waves of 1-CTA/SM kernels: short tail
     int64_t ranges = (target_ctas + p.chunks - 1) / p.chunks;
     int64_t max_ranges = std::max<int64_t>(1, n / 256);
     ranges = std::max<int64_t>(1, std::min<int64_t>(ranges, max_ranges));
