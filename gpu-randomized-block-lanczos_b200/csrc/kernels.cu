@@ -804,11 +804,18 @@ __global__ void __launch_bounds__(256) ritz_kernel(int64_t n, int64_t m, int k, 
         rows[u] = (int64_t)blockIdx.x * RL * RPT + u * RL + rl;
         valid[u] = worker && rows[u] < n;
     }
+    // fp32 buffers: every shared-memory chunk (JC stored blocks) is accumulated in fp32 and the chunk sums in
+    // fp64 - a single fp32 accumulator over all m*B terms loses ~sqrt(m*B) ulps and was measured to push the Ritz
+    // residual of a b = 32 problem to 1.3e-6 ||A|| (bar: 1e-6)
+    double dacc[RPT][TT];
     S acc[RPT][TT];
 #pragma unroll
     for (int u = 0; u < RPT; ++u)
 #pragma unroll
-        for (int t = 0; t < TT; ++t) acc[u][t] = S(0);
+        for (int t = 0; t < TT; ++t) {
+            acc[u][t] = S(0);
+            dacc[u][t] = 0.0;
+        }
 
     for (int64_t j0 = 0; j0 < m; j0 += JC) {
         const int jn = (int)min((int64_t)JC, m - j0);
@@ -844,6 +851,13 @@ __global__ void __launch_bounds__(256) ritz_kernel(int64_t n, int64_t m, int k, 
                     for (int t = 0; t < TT; ++t) acc[u][t] = fma(bv[u][c], sv[t], acc[u][t]);
             }
         }
+#pragma unroll
+        for (int u = 0; u < RPT; ++u)
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
+                dacc[u][t] += (double)acc[u][t];
+                acc[u][t] = S(0);
+            }
     }
     if (!worker) return;
 #pragma unroll
@@ -852,7 +866,7 @@ __global__ void __launch_bounds__(256) ritz_kernel(int64_t n, int64_t m, int k, 
 #pragma unroll
         for (int t = 0; t < TT; ++t) {
             const int col = tg * TT + t;
-            if (col < k) V[(size_t)col * ldv + rows[u]] = (VT)acc[u][t];
+            if (col < k) V[(size_t)col * ldv + rows[u]] = (VT)dacc[u][t];
         }
     }
 }

@@ -112,3 +112,32 @@ def test_device_rng_start_block(gpu):
     A, eig = matrices.slow_decay(400, 5)
     d, V = gpu.RBL_gpu(A, 5, 5)
     assert np.linalg.norm((d - eig) / eig) < 1e-12
+
+
+def test_config4_reduced_image_graph_laplacian(gpu):
+    """Image-grid graph Laplacian with 8-neighbour weights (config 4 at 64x64): 10 smallest eigenpairs via
+    sigma*I - L, b = 16, mixed precision (tensor-core reorth path), against a dense eigensolve."""
+    H = W = 64
+    L = matrices.image_graph_laplacian(H, W, seed=1)
+    sigma = float(2.0 * L.diagonal().max())               # Gershgorin: lambda_max(L) <= 2 max degree
+    A = matrices.shifted(L, sigma)
+    k, b = 10, 16
+    Om = np.random.default_rng(4).standard_normal((H * W, b))
+    D, V, st = gpu.RBL_gpu(L, k, b, Omega=Om, shift=sigma, precision="mixed", max_kryl_sz=4096, return_stats=True)
+    assert st.converged
+    w = np.linalg.eigvalsh(L.toarray())[:k]
+    assert np.max(np.abs((sigma - D) - w)) < 1e-8 * sigma
+    assert np.max(rbl_oracle.ritz_residuals(A, D, V, norm_a=sigma)) < 1e-6
+    assert abs(sigma - D[0]) < 1e-8 * sigma                # the constant vector: lambda_min(L) = 0
+
+
+def test_config3_reduced_er_b32_mixed(gpu):
+    """Erdos-Renyi, b = 32 (config 3's block size), mixed precision (SIMT fp32 reorth path for B = 32)."""
+    n, k, b = 20000, 16, 32
+    A = matrices.erdos_renyi_sym(n, 32, seed=7)
+    Om = np.random.default_rng(7).standard_normal((n, b))
+    D, V, st = gpu.RBL_gpu(A, k, b, Omega=Om, precision="mixed", max_kryl_sz=6000, return_stats=True)
+    Do, Vo = rbl_oracle.RBL(A, k, b, Om, max_kryl_sz=6000)
+    assert st.converged
+    assert np.max(np.abs(D - Do) / np.abs(Do)) < 1e-8
+    assert np.max(rbl_oracle.ritz_residuals(A, D, V)) < 1e-6
