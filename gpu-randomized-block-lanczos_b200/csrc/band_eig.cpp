@@ -449,9 +449,13 @@ void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, boo
             for (size_t j = 0; j < X.size(); ++j) {
                 std::vector<std::vector<double>> head(X.begin(), X.begin() + j + 1);
                 double keep = mgs(head, j, none, T.N);
-                if (keep < 0.5 && dup) {  // seeded mode: two seeds collapsed onto one eigenvector - the caller must not trust the set
+                if (keep < 0.5 && dup) {  // seeded mode: two seeds collapsed onto one eigenvector - drop the second
                     *dup = true;
-                    X[j] = head[j];
+                    X.erase(X.begin() + j);
+                    out.erase(out.begin() + g0 + j);
+                    --g1;
+                    --j;
+                    continue;
                 } else if (keep < 0.5) {
                     double mu_c = 0.5 * (out[g0].theta + out[g1 - 1].theta);
                     wk2.lu.factor(T, mu_c + 5e-15 * tn);
@@ -496,7 +500,12 @@ void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, boo
         }
         if (touched) {
             double nn = nrm2(out[j].v.data(), T.N);
-            if (nn < 0.5 && dup) *dup = true;
+            if (nn < 0.5 && dup) {  // the same eigenvector twice: drop this copy
+                *dup = true;
+                out.erase(out.begin() + j);
+                --j;
+                continue;
+            }
             if (nn > 0) scal(out[j].v.data(), 1.0 / nn, T.N);
         }
     }
@@ -724,7 +733,7 @@ bool BandTopK::refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pair
             std::vector<double> x(N, 0.0);
             std::copy(seeds_[j].v.begin(), seeds_[j].v.end(), x.begin());
             const double nn = nrm2(x.data(), N);
-            if (!(nn > 0)) { failed = true; break; }
+            if (!(nn > 0)) continue;  // dropped (pairs[j].v stays empty)
             scal(x.data(), 1.0 / nn, N);
             double th, rs;
             rayleigh(T, x, wk.t, th, rs);
@@ -748,7 +757,7 @@ bool BandTopK::refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pair
                 }
                 if (!ok && rs <= 1e-11 * tn && round >= 1) ok = true;
             }
-            if (!ok) { failed = true; break; }
+            if (!ok) continue;        // dropped: the caller's count-based repair looks for what is missing
             pairs[j].theta = th;
             pairs[j].res = rs;
             pairs[j].v.swap(x);
@@ -764,12 +773,13 @@ bool BandTopK::refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pair
         for (auto& t : th) t.join();
     }
     nfac += fac.load();
-    if (failed.load()) return false;
+    pairs.erase(std::remove_if(pairs.begin(), pairs.end(), [](const Pair& p) { return p.v.empty(); }), pairs.end());
+    if ((int64_t)pairs.size() * 4 < k * 3) return false;  // too little survived: slicing from scratch is cheaper
     bool dup = false;
     int64_t nf2 = 0;
-    finalize_pairs(T, pairs, nf2, &dup);
+    finalize_pairs(T, pairs, nf2, &dup);  // seeded mode: duplicates are erased, not regenerated
     nfac += nf2;
-    return !dup;
+    return (int64_t)pairs.size() * 4 >= k * 3;
 }
 
 // Decision procedure (identical outcome to dsbev + sort_eig_abs + check_convergence, common.jl:36-65):
@@ -1009,105 +1019,153 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     std::vector<Pair> pairs;
     bool from_seeds = false;
     if ((int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N &&
-        (int64_t)seeds_[0].v.size() * 10 >= N * 5) {  // seeds of a T at least half as large; the validation below decides
-        // fast path: the k pairs of an earlier full solve (any earlier T) refined in parallel, then validated:
-        // exactly k eigenvalues may have magnitude >= the smallest one found
+        (int64_t)seeds_[0].v.size() * 10 >= N * 5) {  // seeds of a T at least half as large; the counts below decide
+        // Fast path: the k pairs of an earlier full solve are refined in parallel (seeds that do not converge or that
+        // collapse onto the same eigenvector are dropped).  Sturm counts then say exactly how many eigenvalues are
+        // missing and where - above the smallest value found (Ritz values that entered the wanted set), inside its
+        // cluster, or below it - and those are extracted by deflated RQI.  A final count validates the set.
         int64_t nf = 0;
-        int64_t dbg_chi = -1, dbg_found = -1, dbg_clo = -1;
+        const int64_t nseed = (int64_t)seeds_[0].v.size();
         const bool refined = refine_seeds(T, k, pairs, nf);
-        if (refined) {
-            std::stable_sort(pairs.begin(), pairs.end(),
-                             [](const Pair& a, const Pair& b2) { return std::fabs(a.theta) > std::fabs(b2.theta); });
-            // validation: with t_k the smallest magnitude found, every eigenvalue strictly above the (possibly
-            // degenerate) cluster at t_k must have been found, and the cluster must reach rank k
-            const double tk = std::fabs(pairs[k - 1].theta);
+        wk.nfac += (int)nf;
+        int64_t n_extra = 0;
+        const char* why = refined ? "" : "too few seeds survived";
+        bool good = refined;
+        auto by_mag = [](const Pair& a, const Pair& b2) { return std::fabs(a.theta) > std::fabs(b2.theta); };
+        if (good) {
+            std::stable_sort(pairs.begin(), pairs.end(), by_mag);
+            const int64_t kf = (int64_t)pairs.size();
+            const double tk = std::fabs(pairs[kf - 1].theta);
             const double delta = std::max(1e-10 * tk, 1e-12 * tn);
-            int64_t found_above = 0;
-            for (int64_t j = 0; j < k; ++j)
-                if (std::fabs(pairs[j].theta) > tk + delta) ++found_above;
-            const int64_t c_hi = count_abs_above(tk + delta).above;
-            const int64_t c_lo = count_abs_above(std::max(0.0, tk - delta)).above;
-            from_seeds = (c_hi == found_above) && (c_lo >= k);
-            dbg_chi = c_hi; dbg_found = found_above; dbg_clo = c_lo;
-            if (!from_seeds && c_hi > found_above && c_hi - found_above <= 24 && pairs[k - 1].theta > 0 && neg_side(tk) == 0) {
-                // Repair: a few Ritz values have entered the wanted set since the seeds were computed.  With the
-                // found values f_1 >= f_2 >= ... the number of missing eigenvalues above f_j is
-                // a_j = #{lambda > f_j + delta} - #{found > f_j + delta} (non-decreasing in j): locate the gaps where it
-                // increases by bisection over j, then extract the missing pairs by deflated RQI inside each gap.
-                std::vector<double> f(k);
-                for (int64_t j = 0; j < k; ++j) f[j] = pairs[j].theta;
-                auto missing_above = [&](int64_t j) -> int64_t {  // j in [0,k): above f_j ; j == k: above t_k - delta
-                    const double x = (j < k) ? f[j] + delta : std::max(0.0, tk - delta);
-                    int64_t fa = 0;
-                    for (int64_t i = 0; i < k; ++i)
-                        if (f[i] > x) ++fa;
+            if (!(pairs[kf - 1].theta > 0) || neg_side(std::max(0.0, tk - delta)) != 0) {
+                // two-sided spectra: only the plain (nothing missing) case is handled here
+                int64_t fa = 0;
+                for (int64_t j = 0; j < kf; ++j)
+                    if (std::fabs(pairs[j].theta) > tk + delta) ++fa;
+                good = (kf == k) && (count_abs_above(tk + delta).above == fa) && (count_abs_above(std::max(0.0, tk - delta)).above >= k);
+                if (!good) why = "two-sided spectrum with missing pairs";
+            } else {
+                std::vector<double> f(kf);
+                for (int64_t j = 0; j < kf; ++j) f[j] = pairs[j].theta;
+                std::vector<Pair> extra;
+                auto above = [&](double x) -> int64_t {  // #{lambda > x}
+                    if (x > T.gersh_hi) return 0;
                     wk.lu.factor(T, x);
                     ++wk.nfac;
-                    return (N - wk.lu.nneg) - fa;
+                    return N - wk.lu.nneg;
                 };
-                struct Gap { int64_t j; int64_t count; };  // missing eigenvalues between f_j (upper) and f_{j+1} (lower)
-                std::vector<Gap> gaps;
-                bool bad = false;
-                std::vector<std::array<int64_t, 4>> stack;  // (jlo, jhi, a_lo, a_hi)
-                const int64_t a0 = missing_above(0), aK = c_hi - found_above;
-                if (a0 > 0) gaps.push_back(Gap{-1, a0});  // above the largest found value
-                stack.push_back({0, k - 1, a0, aK});
-                // a at index k-1 ("above t_k + delta") equals aK by the counts already taken
-                while (!stack.empty() && !bad) {
-                    auto cur = stack.back();
-                    stack.pop_back();
-                    const int64_t jl = cur[0], jh = cur[1], al = cur[2], ah = cur[3];
-                    if (ah < al) { bad = true; break; }
-                    if (ah == al) continue;
-                    if (jh - jl == 1) { gaps.push_back(Gap{jl, ah - al}); continue; }
-                    const int64_t jm = (jl + jh) / 2;
-                    const int64_t am = missing_above(jm);
-                    stack.push_back({jl, jm, al, am});
-                    stack.push_back({jm, jh, am, ah});
-                }
-                std::vector<Pair> extra;
-                for (size_t gi = 0; gi < gaps.size() && !bad; ++gi) {
-                    const int64_t j = gaps[gi].j;
-                    const double hi_x = (j < 0) ? g : f[j] - delta;
-                    const double lo_x = (j < 0) ? f[0] + delta : f[j + 1] + delta;
-                    if (!(hi_x > lo_x)) { bad = true; break; }
-                    for (int64_t c = 0; c < gaps[gi].count && !bad; ++c) {
+                auto found_above = [&](double x) -> int64_t {
+                    int64_t c = 0;
+                    for (int64_t i = 0; i < kf; ++i)
+                        if (f[i] > x) ++c;
+                    return c;
+                };
+                // `count` eigenpairs inside (lo,hi) that are not among the found/extra ones
+                auto fill = [&](double lo, double hi, int64_t count) -> bool {
+                    if (!(hi > lo)) return false;
+                    const double pad = hi - lo;
+                    for (int64_t c = 0; c < count; ++c) {
                         std::vector<const std::vector<double>*> against;
-                        for (int64_t i = std::max<int64_t>(0, j - 3); i <= std::min<int64_t>(k - 1, j + 4); ++i) against.push_back(&pairs[i].v);
+                        for (int64_t i = 0; i < kf; ++i)
+                            if (f[i] > lo - pad && f[i] < hi + pad) against.push_back(&pairs[i].v);
                         for (auto& e : extra)
-                            if (e.theta > lo_x && e.theta < hi_x) against.push_back(&e.v);
+                            if (e.theta > lo - pad && e.theta < hi + pad) against.push_back(&e.v);
                         Pair np;
-                        if (!deflated_rqi(T, wk, lo_x, hi_x, against, np)) { bad = true; break; }
+                        if (!deflated_rqi(T, wk, lo, hi, against, np)) return false;
                         extra.push_back(std::move(np));
                     }
+                    return true;
+                };
+                const int64_t c_hi = above(tk + delta), c_lo = above(std::max(0.0, tk - delta));
+                const int64_t fa_hi = found_above(tk + delta);
+                const int64_t miss_above = c_hi - fa_hi;                      // entrants above the smallest found value
+                const int64_t miss_clu = (c_lo - c_hi) - (kf - fa_hi);        // missing members of its cluster
+                if (miss_above < 0 || miss_clu < 0 || miss_above > 32) {
+                    good = false;
+                    why = "counts inconsistent with the refined set";
                 }
-                if (!bad && (int64_t)extra.size() == c_hi - found_above) {
+                if (good && miss_above > 0) {
+                    // a_j = #{lambda > f_j + delta} - #{found > f_j + delta} is non-decreasing in j: bisect over j for the
+                    // gaps where it increases
+                    struct Gap { int64_t j; int64_t count; };
+                    std::vector<Gap> gaps;
+                    std::vector<std::array<int64_t, 4>> stack;
+                    const int64_t a0 = above(f[0] + delta) - found_above(f[0] + delta);
+                    if (a0 > 0) gaps.push_back(Gap{-1, a0});
+                    stack.push_back({0, kf - 1, a0, miss_above});
+                    while (!stack.empty() && good) {
+                        auto cur = stack.back();
+                        stack.pop_back();
+                        const int64_t jl = cur[0], jh = cur[1], al = cur[2], ah = cur[3];
+                        if (ah < al) { good = false; why = "non-monotone missing counts"; break; }
+                        if (ah == al) continue;
+                        if (jh - jl <= 1) { gaps.push_back(Gap{jl, ah - al}); continue; }
+                        const int64_t jm = (jl + jh) / 2;
+                        const int64_t am = above(f[jm] + delta) - found_above(f[jm] + delta);
+                        stack.push_back({jl, jm, al, am});
+                        stack.push_back({jm, jh, am, ah});
+                    }
+                    for (size_t gi = 0; gi < gaps.size() && good; ++gi) {
+                        const int64_t j = gaps[gi].j;
+                        const double hi_x = (j < 0) ? g : f[j] - delta;
+                        const double lo_x = (j < 0) ? f[0] + delta : f[j + 1] + delta;
+                        if (!fill(lo_x, hi_x, gaps[gi].count)) { good = false; why = "could not extract an entrant"; }
+                    }
+                }
+                int64_t have = kf + (int64_t)extra.size();
+                if (good && have < k && miss_clu > 0) {  // only as many cluster members as are needed to reach k
+                    const int64_t need = std::min<int64_t>(miss_clu, k - have);
+                    if (!fill(std::max(0.0, tk - 2 * delta), tk + 2 * delta, need)) {
+                        good = false;
+                        why = "could not complete the boundary cluster";
+                    }
+                    have = kf + (int64_t)extra.size();
+                }
+                if (good && have < k) {
+                    // still short: take everything between the smallest found value and the first x with >= k above it
+                    double xl = std::max(0.0, tk - delta), step = std::max(1e-6 * tn, 4 * delta);
+                    int64_t cx = c_lo;
+                    for (int it = 0; it < 60 && cx < k; ++it) {
+                        xl = std::max(0.0, xl - step);
+                        cx = above(xl);
+                        step *= 2.0;
+                        if (xl == 0.0) break;
+                    }
+                    if (cx < k || cx - c_lo > 32) { good = false; why = "too many pairs missing below the refined set"; }
+                    else if (!fill(xl, std::max(0.0, tk - delta), cx - c_lo)) { good = false; why = "could not extract the pairs below the refined set"; }
+                }
+                if (good) {
+                    n_extra = (int64_t)extra.size();
                     for (auto& e : extra) pairs.push_back(std::move(e));
-                    int64_t nf3 = 0;
-                    bool dup = false;
-                    finalize_pairs(T, pairs, nf3, &dup);
-                    wk.nfac += (int)nf3;
-                    std::stable_sort(pairs.begin(), pairs.end(),
-                                     [](const Pair& a, const Pair& b2) { return std::fabs(a.theta) > std::fabs(b2.theta); });
+                    if (n_extra > 0) {
+                        int64_t nf3 = 0;
+                        bool dup = false;
+                        finalize_pairs(T, pairs, nf3, &dup);
+                        wk.nfac += (int)nf3;
+                        if (dup) { good = false; why = "duplicate after repair"; }
+                    }
+                }
+                if (good) {
+                    std::stable_sort(pairs.begin(), pairs.end(), by_mag);
+                    if ((int64_t)pairs.size() < k) { good = false; why = "fewer than k pairs after repair"; }
+                }
+                if (good) {
                     pairs.resize(k);
-                    // re-validate the repaired set
+                    // final validation: every eigenvalue strictly above the (possibly degenerate) k-th one is in the set
                     const double tk2 = std::fabs(pairs[k - 1].theta);
                     int64_t fa2 = 0;
                     for (int64_t j = 0; j < k; ++j)
                         if (std::fabs(pairs[j].theta) > tk2 + delta) ++fa2;
-                    const int64_t c_hi2 = count_abs_above(tk2 + delta).above;
-                    const int64_t c_lo2 = count_abs_above(std::max(0.0, tk2 - delta)).above;
-                    from_seeds = !dup && (c_hi2 == fa2) && (c_lo2 >= k);
-                    if (verbose > 0) std::fprintf(stderr, "[rbl]   repaired %zu entrant(s): %s\n", gaps.size(), from_seeds ? "ok" : "failed");
+                    good = (above(tk2 + delta) == fa2) && (above(std::max(0.0, tk2 - delta)) >= k);
+                    if (!good) why = "final count validation failed";
                 }
             }
         }
-        wk.nfac += (int)nf;
+        from_seeds = good;
         if (!from_seeds) pairs.clear();
         if (verbose > 0)
-            std::fprintf(stderr, "[rbl] full check N=%lld from seeds (N_seed=%lld): %s (refined=%d, above t_k: %lld found %lld, >= t_k: %lld, k=%lld)\n",
-                         (long long)N, (long long)seeds_[0].v.size(), from_seeds ? "ok" : "rejected", (int)refined,
-                         (long long)dbg_chi, (long long)dbg_found, (long long)dbg_clo, (long long)k);
+            std::fprintf(stderr, "[rbl] full check N=%lld from seeds (N_seed=%lld): %s%s%s, %lld repaired\n", (long long)N,
+                         (long long)nseed, from_seeds ? "ok" : "rejected", from_seeds ? "" : ": ", why, (long long)n_extra);
     }
     // bracket the k-th largest |lambda|: largest x_lo with #{|lambda| > x_lo} >= k (within a modest surplus)
     double x_lo = 0.0, x_hi = g;
