@@ -1019,7 +1019,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     std::vector<Pair> pairs;
     bool from_seeds = false;
     if ((int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N &&
-        (int64_t)seeds_[0].v.size() * 10 >= N * 5) {  // seeds of a T at least half as large; the counts below decide
+        (int64_t)seeds_[0].v.size() * 20 >= N * 17) {  // seeds of a T at least 85% as large (staler ones rarely survive)
         // Fast path: the k pairs of an earlier full solve are refined in parallel (seeds that do not converge or that
         // collapse onto the same eigenvector are dropped).  Sturm counts then say exactly how many eigenvalues are
         // missing and where - above the smallest value found (Ritz values that entered the wanted set), inside its
