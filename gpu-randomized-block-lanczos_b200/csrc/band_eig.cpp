@@ -16,8 +16,10 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <random>
 #include <thread>
@@ -534,6 +536,7 @@ bool deflated_rqi(const BandSym& T, Work& wk, double lo, double hi, const std::v
             mgs(X, 0, against, N);
         }
         rayleigh(T, X[0], wk.t, th, rs);
+        if (getenv("RBL_DEBUG_RQI")) std::fprintf(stderr, "    drqi round %d mu=%.15g th=%.15g rs=%.2e (lo=%.15g hi=%.15g, against %zu)\n", round, mu, th, rs, lo, hi, against.size());
         if (rs <= 2e-13 * tn) break;
         // stay inside the interval: a Ritz value outside means the iterate is still dominated by other directions
         mu = (th > lo && th < hi) ? th : 0.5 * (lo + hi) + (round + 1) * 0.07 * (hi - lo) * ((round & 1) ? 1.0 : -1.0);
@@ -1060,27 +1063,54 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
                         if (f[i] > x) ++c;
                     return c;
                 };
-                // `count` eigenpairs inside (lo,hi) that are not among the found/extra ones
-                auto fill = [&](double lo, double hi, int64_t count) -> bool {
-                    if (!(hi > lo)) return false;
-                    const double pad = hi - lo;
-                    for (int64_t c = 0; c < count; ++c) {
-                        std::vector<const std::vector<double>*> against;
-                        for (int64_t i = 0; i < kf; ++i)
-                            if (f[i] > lo - pad && f[i] < hi + pad) against.push_back(&pairs[i].v);
-                        for (auto& e : extra)
-                            if (e.theta > lo - pad && e.theta < hi + pad) against.push_back(&e.v);
-                        Pair np;
-                        if (!deflated_rqi(T, wk, lo, hi, against, np)) return false;
-                        extra.push_back(std::move(np));
-                    }
+                // number of eigenvalues above x that are neither found nor already extracted
+                auto miss = [&](double x) -> int64_t {
+                    int64_t ex = 0;
+                    for (auto& e : extra)
+                        if (e.theta > x) ++ex;
+                    return above(x) - found_above(x) - ex;
+                };
+                auto try_one = [&](double lo, double hi) -> bool {
+                    const double pad = std::max(hi - lo, 1e-6 * tn);
+                    std::vector<const std::vector<double>*> against;
+                    for (int64_t i = 0; i < kf; ++i)
+                        if (f[i] > lo - pad && f[i] < hi + pad) against.push_back(&pairs[i].v);
+                    for (auto& e : extra)
+                        if (e.theta > lo - pad && e.theta < hi + pad) against.push_back(&e.v);
+                    Pair np;
+                    if (!deflated_rqi(T, wk, lo, hi, against, np)) return false;
+                    extra.push_back(std::move(np));
                     return true;
+                };
+                // `count` eigenpairs inside (lo,hi) that are not among the found/extra ones: bisect on the missing
+                // counts until a deflated iteration started in the interval locks onto the missing eigenvalue
+                std::function<bool(double, double, int64_t, int64_t, int)> fill_rec =
+                    [&](double lo, double hi, int64_t m_lo, int64_t m_hi, int depth) -> bool {
+                    const int64_t c = m_lo - m_hi;  // missing inside (lo,hi)
+                    if (c <= 0) return c == 0;
+                    if (!(hi > lo)) return false;
+                    if (c == 1 && try_one(lo, hi)) return true;
+                    if (hi - lo <= 1e-9 * tn || depth > 40) {  // a cluster of missing values: one after the other
+                        for (int64_t q = 0; q < c; ++q)
+                            if (!try_one(lo, hi)) return false;
+                        return true;
+                    }
+                    const double mid = 0.5 * (lo + hi);
+                    const int64_t m_mid = miss(mid);
+                    if (m_mid > m_lo || m_mid < m_hi) return false;
+                    return fill_rec(mid, hi, m_mid, m_hi, depth + 1) && fill_rec(lo, mid, m_lo, m_mid, depth + 1);
+                };
+                auto fill = [&](double lo, double hi, int64_t count) -> bool {
+                    if (count <= 0) return true;
+                    if (!(hi > lo)) return false;
+                    const int64_t m_hi = miss(hi);
+                    return fill_rec(lo, hi, m_hi + count, m_hi, 0);
                 };
                 const int64_t c_hi = above(tk + delta), c_lo = above(std::max(0.0, tk - delta));
                 const int64_t fa_hi = found_above(tk + delta);
                 const int64_t miss_above = c_hi - fa_hi;                      // entrants above the smallest found value
                 const int64_t miss_clu = (c_lo - c_hi) - (kf - fa_hi);        // missing members of its cluster
-                if (miss_above < 0 || miss_clu < 0 || miss_above > 32) {
+                if (miss_above < 0 || miss_clu < 0 || miss_above > 6) {
                     good = false;
                     why = "counts inconsistent with the refined set";
                 }
