@@ -262,7 +262,8 @@ int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qb
         if (!qbuf || !w0 || !w1 || b < 1 || b > 32 || n < 1 || m < 1) throw Error(RBL_INVALID, "rbl_reorth: bad arguments");
         const int B = padded_block((int)b);
         const bool tc = impl != 1 && reorth_tc_supported(B, storage_fp32);
-        if (impl >= 2 && !tc) throw Error(RBL_INVALID, "rbl_reorth: tensor-core path needs fp32 storage and padded block size 16");
+        const bool hs = impl != 1 && impl != 2 && reorth_h_supported(B, storage_fp32);
+        if ((impl == 2 && !tc) || (impl == 3 && !hs)) throw Error(RBL_INVALID, "rbl_reorth: tensor-core path needs fp32 storage and padded block size 16");
         const size_t ssz = storage_fp32 ? 4 : 8;
         // pad the stored blocks
         std::vector<unsigned char> hb((size_t)m * n * B * ssz, 0);
@@ -286,7 +287,7 @@ int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qb
             launch_reorth_gram_d(p, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, 0);
             launch_reorth_update_d(p, dbuf.p, n * B, dC.p, W0.dev.p, W1.dev.p, nullptr, 0);
             RBL_CUDA(cudaDeviceSynchronize());
-        } else if (tc && impl != 2) {
+        } else if (hs) {
             DevBuf<float> scratch;
             scratch.alloc(reorth_h_scratch_words(B, n, m));
             launch_reorth_gram_h(p, n, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, scratch.p, m, 0);

@@ -94,6 +94,7 @@ void launch_reorth_update_tc(const ReorthPlan& p, const void* buf, int64_t block
 
 // scaled two-term FP16 split on mma.sync m16n8k16 (reorth_tc16.cu): same interface, half the tensor-pipe time.
 // `n_global` fixes the power-of-two operand scale (orthonormal columns of global length n_global).
+bool reorth_h_supported(int B, int fp32);   // fp32 buffer, B = 16 or 32
 size_t reorth_h_scratch_words(int B, int64_t n, int64_t m_cap);
 void launch_reorth_gram_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t block_stride_elems,
                           const double* w0, const double* w1, void* partials, void* C, float* scratch, int64_t m_cap,

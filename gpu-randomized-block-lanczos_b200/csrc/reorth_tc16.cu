@@ -77,14 +77,17 @@ __global__ void split_targets_h_kernel(int64_t n, const double* __restrict__ w0,
 
 // =================================================================================================
 // Gram.  MMA roles: M = 16 Krylov columns of a stored block, N = 8 targets, K = 16 rows.
+// B = 16: 16 warps x 2 stored blocks; B = 32: 16 warps x 1 stored block (two m-tiles, n-tiles in two halves).
 // =================================================================================================
 template <int B>
 struct GramH {
     static constexpr int NW = 16;                // warps per CTA (ncu: with 8 the schedulers had 0.6 eligible warps/cycle)
-    static constexpr int WB = 2;                 // stored blocks per warp
-    static constexpr int JT = NW * WB;           // stored blocks per CTA (= reorth_plan's chunk size)
-    static constexpr int NT = (2 * B) / 8;
-    static constexpr int PA = B;                 // unpadded 64-byte rows, permuted + swizzled (see gram_slot)
+    static constexpr int WB = 32 / B;            // stored blocks per warp
+    static constexpr int JT = NW * WB;           // stored blocks per CTA
+    static constexpr int MT = B / 16;            // m-tiles per stored block
+    static constexpr int NT = (2 * B) / 8;       // n-tiles
+    static constexpr int NH = NT / 4;            // n-tiles are processed four at a time (register budget)
+    static constexpr int PA = B;                 // unpadded rows, permuted + swizzled (see gram_slot)
     static constexpr int PW = 2 * B + 8;         // words per staged target row-pair
     static constexpr int NST = 5;
     static constexpr int RS = 16;                // rows per stage
@@ -96,14 +99,16 @@ struct GramH {
 };
 
 // Shared-memory slot of element (row r of a 16-row stage, column c) of a stored block, in floats.
-// Rows keep their 64 contiguous bytes (a multiple of 32 B: both 16-byte halves of a global 32-byte sector land
+// Rows keep their B*4 contiguous bytes (a multiple of 32 B: both 16-byte halves of a global 32-byte sector land
 // in one shared-memory sector, so cp.async fetches every sector once - a padded 80-byte pitch was measured to
 // fetch 1.47x the sectors from L2).  Bank conflicts of the fragment loads (rows 2t / 2t+1 / 2t+8 / 2t+9,
-// columns g / g+8) are removed by storing row r at position p = (r&1)*8 + (r>>1) and swapping the two 32-byte
-// halves of the row when p&2.
+// columns g + 8i) are removed by storing row r at position p = (r&1)*8 + (r>>1) and XOR-ing the 16-byte chunk
+// index with an even number derived from p (even: 32-byte sector pairs stay together).
+template <int B>
 __device__ __forceinline__ int gram_slot(int r, int c) {
     const int p = ((r & 1) << 3) + (r >> 1);
-    return p * 16 + ((((c >> 2) ^ (p & 2))) << 2) + (c & 3);
+    if constexpr (B == 16) return p * 16 + ((((c >> 2) ^ (p & 2))) << 2) + (c & 3);
+    else return p * 32 + ((((c >> 2) ^ ((p & 3) << 1))) << 2) + (c & 3);
 }
 
 template <int B>
@@ -112,9 +117,9 @@ __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
                          const unsigned* __restrict__ wh, const unsigned* __restrict__ wl, float scale,
                          float inv_scale2, float* __restrict__ partials, int64_t rows_per_range) {
     using C = GramH<B>;
-    constexpr int NW = C::NW, WB = C::WB, JT = C::JT, NT = C::NT, PA = C::PA, PW = C::PW, NST = C::NST, RS = C::RS,
-                  RW = C::RW, STAGE = C::STAGE, WBUF = C::WBUF, NCP = C::NCP, NTHR = NW * 32;
-    static_assert(B == 16, "instantiated for B = 16");
+    constexpr int NW = C::NW, WB = C::WB, JT = C::JT, MT = C::MT, NT = C::NT, NH = C::NH, PA = C::PA, PW = C::PW,
+                  NST = C::NST, RS = C::RS, RW = C::RW, STAGE = C::STAGE, WBUF = C::WBUF, NCP = C::NCP, NTHR = NW * 32;
+    static_assert(B == 16 || B == 32, "instantiated for B = 16, 32");
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -125,13 +130,15 @@ __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
     const int64_t rend = min(n, rbeg + rows_per_range);
     const int64_t nrows = rend - rbeg;
 
-    float acc[WB][NT][4];
+    float acc[WB][MT][NT][4];
 #pragma unroll
     for (int b = 0; b < WB; ++b)
 #pragma unroll
-        for (int x = 0; x < NT; ++x)
+        for (int a = 0; a < MT; ++a)
 #pragma unroll
-            for (int y = 0; y < 4; ++y) acc[b][x][y] = 0.f;
+            for (int x = 0; x < NT; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[b][a][x][y] = 0.f;
 
     if (nrows > 0) {
         const int nks = (int)((nrows + RS - 1) / RS);
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
             const int row = rem / (B / 4), c4 = rem % (B / 4);
             blk_ok[u] = (jbase + blk) < m;
             row0[u] = row;
-            dst0[u] = blk * RS * PA + gram_slot(row, c4 * 4);
+            dst0[u] = blk * RS * PA + gram_slot<B>(row, c4 * 4);
             src0[u] = buf + (size_t)(blk_ok[u] ? jbase + blk : 0) * bstride + (size_t)(rbeg + row) * B + c4 * 4;
         }
         auto issue_a = [&](int ks) {
@@ -162,17 +169,22 @@ __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
                 cp_async16(st + dst0[u], ok ? src0[u] + adv : buf, ok ? 16 : 0);
             }
         };
-        auto issue_w = [&](int chunk) {  // whole CTA: RW/2 row pairs x 2B words; threads < 256 copy hi, the rest lo
-            const int half = tid / 256, q = tid % 256;
-            unsigned* dst = sW + (size_t)((chunk & 1) * 2 + half) * WBUF;
-            const unsigned* srcb = half ? wl : wh;
+        auto issue_w = [&](int chunk) {  // whole CTA: RW/2 row pairs x 2B words, hi and lo
+            constexpr int PER = (RW / 2) * (2 * B / 4);  // 16-byte copies per array
             const int64_t rp0 = (rbeg + (int64_t)chunk * RW) / 2;
             const int64_t rp_end = (rend + 1) / 2;
-            const int rp = q / (2 * B / 4), c4 = q % (2 * B / 4);
-            const bool ok = (rp0 + rp < rp_end);
-            cp_async16(dst + rp * PW + c4 * 4, ok ? srcb + (size_t)(rp0 + rp) * 2 * B + c4 * 4 : srcb, ok ? 16 : 0);
+#pragma unroll
+            for (int u = 0; u < (2 * PER) / NTHR; ++u) {
+                const int idx = tid + NTHR * u;
+                const int half = idx / PER, q = idx % PER;
+                unsigned* dst = sW + (size_t)((chunk & 1) * 2 + half) * WBUF;
+                const unsigned* srcb = half ? wl : wh;
+                const int rp = q / (2 * B / 4), c4 = q % (2 * B / 4);
+                const bool ok = (rp0 + rp < rp_end);
+                cp_async16(dst + rp * PW + c4 * 4, ok ? srcb + (size_t)(rp0 + rp) * 2 * B + c4 * 4 : srcb, ok ? 16 : 0);
+            }
         };
-        static_assert(((RW / 2) * 2 * B / 4) == 256 && NTHR == 512, "target chunk copy assumes 512 threads");
+        static_assert((2 * (RW / 2) * (2 * B / 4)) % NTHR == 0, "target chunk copy must tile the CTA");
         issue_w(0);
         issue_a(0);
         cp_async_commit();
@@ -193,29 +205,44 @@ __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
             const int chunk = ks / KPC;
             const unsigned* ph = sW + (size_t)((chunk & 1) * 2 + 0) * WBUF + (size_t)(ks % KPC) * 8 * PW;
             const unsigned* pl = sW + (size_t)((chunk & 1) * 2 + 1) * WBUF + (size_t)(ks % KPC) * 8 * PW;
-            unsigned bh[NT][2], bl[NT][2];
+            unsigned bh[4][2], bl[4][2];
+            auto load_b = [&](int nh) {
 #pragma unroll
-            for (int x = 0; x < NT; ++x) {
-                bh[x][0] = ph[t * PW + x * 8 + g];
-                bh[x][1] = ph[(t + 4) * PW + x * 8 + g];
-                bl[x][0] = pl[t * PW + x * 8 + g];
-                bl[x][1] = pl[(t + 4) * PW + x * 8 + g];
-            }
+                for (int x = 0; x < 4; ++x) {
+                    const int col = (nh * 4 + x) * 8 + g;
+                    bh[x][0] = ph[t * PW + col];
+                    bh[x][1] = ph[(t + 4) * PW + col];
+                    bl[x][0] = pl[t * PW + col];
+                    bl[x][1] = pl[(t + 4) * PW + col];
+                }
+            };
+            if constexpr (NH == 1) load_b(0);
 #pragma unroll
             for (int b = 0; b < WB; ++b) {
                 const float* a = st + b * RS * PA;
-                unsigned ah[4], al[4];
-                // A[m = column][k = row]: register halves are rows 2t, 2t+1 (and +8) of columns g / g+8
-                split_h2(a[gram_slot(2 * t, g)], a[gram_slot(2 * t + 1, g)], scale, ah[0], al[0]);
-                split_h2(a[gram_slot(2 * t, g + 8)], a[gram_slot(2 * t + 1, g + 8)], scale, ah[1], al[1]);
-                split_h2(a[gram_slot(2 * t + 8, g)], a[gram_slot(2 * t + 9, g)], scale, ah[2], al[2]);
-                split_h2(a[gram_slot(2 * t + 8, g + 8)], a[gram_slot(2 * t + 9, g + 8)], scale, ah[3], al[3]);
+                unsigned ah[MT][4], al[MT][4];
 #pragma unroll
-                for (int x = 0; x < NT; ++x) mma_f16(acc[b][x], al, bh[x]);
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int c0 = mt * 16 + g;
+                    // A[m = column][k = row]: register halves are rows 2t, 2t+1 (and +8) of columns c0 / c0+8
+                    split_h2(a[gram_slot<B>(2 * t, c0)], a[gram_slot<B>(2 * t + 1, c0)], scale, ah[mt][0], al[mt][0]);
+                    split_h2(a[gram_slot<B>(2 * t, c0 + 8)], a[gram_slot<B>(2 * t + 1, c0 + 8)], scale, ah[mt][1], al[mt][1]);
+                    split_h2(a[gram_slot<B>(2 * t + 8, c0)], a[gram_slot<B>(2 * t + 9, c0)], scale, ah[mt][2], al[mt][2]);
+                    split_h2(a[gram_slot<B>(2 * t + 8, c0 + 8)], a[gram_slot<B>(2 * t + 9, c0 + 8)], scale, ah[mt][3], al[mt][3]);
+                }
 #pragma unroll
-                for (int x = 0; x < NT; ++x) mma_f16(acc[b][x], ah, bl[x]);
+                for (int nh = 0; nh < NH; ++nh) {
+                    if constexpr (NH > 1) load_b(nh);
 #pragma unroll
-                for (int x = 0; x < NT; ++x) mma_f16(acc[b][x], ah, bh[x]);
+                    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) mma_f16(acc[b][mt][nh * 4 + x], al[mt], bh[x]);
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) mma_f16(acc[b][mt][nh * 4 + x], ah[mt], bl[x]);
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) mma_f16(acc[b][mt][nh * 4 + x], ah[mt], bh[x]);
+                    }
+                }
             }
         }
         cp_async_wait<0>();
@@ -226,12 +253,14 @@ __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
         if (j >= m) continue;
         float* out = partials + ((size_t)blockIdx.y * m * B + (size_t)j * B) * (2 * B);
 #pragma unroll
-        for (int x = 0; x < NT; ++x) {
-            *reinterpret_cast<float2*>(out + (size_t)g * 2 * B + x * 8 + 2 * t) =
-                make_float2(acc[b][x][0] * inv_scale2, acc[b][x][1] * inv_scale2);
-            *reinterpret_cast<float2*>(out + (size_t)(g + 8) * 2 * B + x * 8 + 2 * t) =
-                make_float2(acc[b][x][2] * inv_scale2, acc[b][x][3] * inv_scale2);
-        }
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int x = 0; x < NT; ++x) {
+                *reinterpret_cast<float2*>(out + (size_t)(mt * 16 + g) * 2 * B + x * 8 + 2 * t) =
+                    make_float2(acc[b][mt][x][0] * inv_scale2, acc[b][mt][x][1] * inv_scale2);
+                *reinterpret_cast<float2*>(out + (size_t)(mt * 16 + g + 8) * 2 * B + x * 8 + 2 * t) =
+                    make_float2(acc[b][mt][x][2] * inv_scale2, acc[b][mt][x][3] * inv_scale2);
+            }
     }
 }
 
@@ -278,20 +307,24 @@ __global__ void split_coeff_h_kernel(size_t nwords, int B, const float* __restri
 }
 
 // =================================================================================================
-// Update.  MMA roles: M = 16 rows, N = 8 targets, K = 16 Krylov columns (one k-step per stored block).
+// Update.  MMA roles: M = 16 rows, N = 8 targets, K = 16 Krylov columns (B/16 k-steps per stored block).
+// Every warp owns 32 rows; B = 16: 16 warps, B = 32: 8 warps (shared memory).
 // =================================================================================================
 template <int B>
 struct UpdH {
-    static constexpr int NW = 16;                // warps per CTA
+    static constexpr int NW = (B == 16) ? 16 : 8;  // warps per CTA
     static constexpr int MT = 2;
     static constexpr int NT = (2 * B) / 8;
+    static constexpr int NH = NT / 4;
+    static constexpr int KS = B / 16;
     static constexpr int PA = B + 8;             // floats per staged row: conflict-free float2 A fragments, 32-byte multiple
     static constexpr int PC = 2 * B + 8;         // words per staged coefficient row pair
-    static constexpr int JC = 8;
+    static constexpr int JC = (B == 16) ? 8 : 4;
     static constexpr int NST = 3;
     static constexpr int STAGE = 32 * PA;
     static constexpr int CBUF = JC * (B / 2) * PC;
     static constexpr int ROWS_CTA = NW * 32;
+    static constexpr int NCP = (32 * (B / 4)) / 32;
     static constexpr size_t smem_bytes = (size_t)(NW * NST * STAGE + 4 * CBUF) * sizeof(float);
 };
 
@@ -302,9 +335,9 @@ __global__ void __launch_bounds__(UpdH<B>::NW * 32, 1)
                            const float* __restrict__ scale_c_ptr, double* __restrict__ w0, double* __restrict__ w1,
                            float* __restrict__ store_w1) {
     using C = UpdH<B>;
-    constexpr int NW = C::NW, MT = C::MT, NT = C::NT, PA = C::PA, PC = C::PC, JC = C::JC, NST = C::NST, STAGE = C::STAGE,
-                  CBUF = C::CBUF, NTHR = NW * 32;
-    static_assert(B == 16, "instantiated for B = 16");
+    constexpr int NW = C::NW, MT = C::MT, NT = C::NT, NH = C::NH, KS = C::KS, PA = C::PA, PC = C::PC, JC = C::JC,
+                  NST = C::NST, STAGE = C::STAGE, CBUF = C::CBUF, NCP = C::NCP, NTHR = NW * 32;
+    static_assert(B == 16 || B == 32, "instantiated for B = 16, 32");
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -321,8 +354,7 @@ __global__ void __launch_bounds__(UpdH<B>::NW * 32, 1)
 #pragma unroll
             for (int y = 0; y < 4; ++y) acc[a][x][y] = 0.f;
 
-    // per-lane constants of the 4 copies of a stage (32 rows x B floats of one stored block)
-    constexpr int NCP = (32 * (B / 4)) / 32;
+    // per-lane constants of the copies of a stage (32 rows x B floats of one stored block)
     const float* src0[NCP];
     int dst0[NCP];
     bool row_ok[NCP];
@@ -343,21 +375,22 @@ __global__ void __launch_bounds__(UpdH<B>::NW * 32, 1)
             cp_async16(st + dst0[u], ok ? src0[u] + adv : buf, ok ? 16 : 0);
         }
     };
-    auto issue_c = [&](int chunk) {  // JC blocks x B/2 column pairs x 2B words; threads < 256 copy hi, the rest lo
-        const int half = tid / 256, q0 = tid % 256;
-        unsigned* dst = sC + (size_t)((chunk & 1) * 2 + half) * CBUF;
-        const unsigned* srcb = half ? Cl : Ch;
+    auto issue_c = [&](int chunk) {  // JC blocks x B/2 column pairs x 2B words, hi and lo
+        constexpr int PER = JC * (B / 2) * (2 * B / 4);  // 16-byte copies per array
         const int j0 = chunk * JC;
 #pragma unroll
-        for (int u = 0; u < (JC * (B / 2) * (2 * B / 4)) / 256; ++u) {
-            const int q = q0 + 256 * u;
+        for (int u = 0; u < (2 * PER) / NTHR; ++u) {
+            const int idx = tid + NTHR * u;
+            const int half = idx / PER, q = idx % PER;
+            unsigned* dst = sC + (size_t)((chunk & 1) * 2 + half) * CBUF;
+            const unsigned* srcb = half ? Cl : Ch;
             const int rowc = q / (2 * B / 4), c4 = q % (2 * B / 4);  // rowc = jb*(B/2) + c/2
             const bool ok = (j0 * (B / 2) + rowc) < mi * (B / 2);
             const size_t off = ((size_t)j0 * (B / 2) + rowc) * (2 * B) + c4 * 4;
             cp_async16(dst + rowc * PC + c4 * 4, ok ? srcb + off : srcb, ok ? 16 : 0);
         }
     };
-    static_assert(NTHR == 512, "coefficient chunk copy assumes 512 threads");
+    static_assert((2 * JC * (B / 2) * (2 * B / 4)) % NTHR == 0, "coefficient chunk copy must tile the CTA");
     issue_c(0);
     issue_a(0);
     cp_async_commit();
@@ -378,33 +411,43 @@ __global__ void __launch_bounds__(UpdH<B>::NW * 32, 1)
         const int chunk = j / JC;
         const unsigned* ph = sC + (size_t)((chunk & 1) * 2 + 0) * CBUF + (size_t)(j % JC) * (B / 2) * PC;
         const unsigned* pl = sC + (size_t)((chunk & 1) * 2 + 1) * CBUF + (size_t)(j % JC) * (B / 2) * PC;
-        unsigned bh[NT][2], bl[NT][2];
 #pragma unroll
-        for (int x = 0; x < NT; ++x) {
-            bh[x][0] = ph[t * PC + x * 8 + g];
-            bh[x][1] = ph[(t + 4) * PC + x * 8 + g];
-            bl[x][0] = pl[t * PC + x * 8 + g];
-            bl[x][1] = pl[(t + 4) * PC + x * 8 + g];
-        }
+        for (int ks = 0; ks < KS; ++ks) {
+            unsigned ah[MT][4], al[MT][4];
 #pragma unroll
-        for (int a = 0; a < MT; ++a) {
-            const float* ap = st + (a * 16) * PA;
-            // A[m = row][k = column]: register halves are columns 2t, 2t+1 (and +8) of rows g / g+8
-            const float2 v0 = *reinterpret_cast<const float2*>(ap + g * PA + 2 * t);
-            const float2 v1 = *reinterpret_cast<const float2*>(ap + (g + 8) * PA + 2 * t);
-            const float2 v2 = *reinterpret_cast<const float2*>(ap + g * PA + 2 * t + 8);
-            const float2 v3 = *reinterpret_cast<const float2*>(ap + (g + 8) * PA + 2 * t + 8);
-            unsigned ah[4], al[4];
-            split_h2(v0.x, v0.y, scale_a, ah[0], al[0]);
-            split_h2(v1.x, v1.y, scale_a, ah[1], al[1]);
-            split_h2(v2.x, v2.y, scale_a, ah[2], al[2]);
-            split_h2(v3.x, v3.y, scale_a, ah[3], al[3]);
+            for (int a = 0; a < MT; ++a) {
+                const float* ap = st + (a * 16) * PA + ks * 16;
+                // A[m = row][k = column]: register halves are columns 2t, 2t+1 (and +8) of rows g / g+8
+                const float2 v0 = *reinterpret_cast<const float2*>(ap + g * PA + 2 * t);
+                const float2 v1 = *reinterpret_cast<const float2*>(ap + (g + 8) * PA + 2 * t);
+                const float2 v2 = *reinterpret_cast<const float2*>(ap + g * PA + 2 * t + 8);
+                const float2 v3 = *reinterpret_cast<const float2*>(ap + (g + 8) * PA + 2 * t + 8);
+                split_h2(v0.x, v0.y, scale_a, ah[a][0], al[a][0]);
+                split_h2(v1.x, v1.y, scale_a, ah[a][1], al[a][1]);
+                split_h2(v2.x, v2.y, scale_a, ah[a][2], al[a][2]);
+                split_h2(v3.x, v3.y, scale_a, ah[a][3], al[a][3]);
+            }
 #pragma unroll
-            for (int x = 0; x < NT; ++x) mma_f16(acc[a][x], al, bh[x]);
+            for (int nh = 0; nh < NH; ++nh) {
+                unsigned bh[4][2], bl[4][2];
 #pragma unroll
-            for (int x = 0; x < NT; ++x) mma_f16(acc[a][x], ah, bl[x]);
+                for (int x = 0; x < 4; ++x) {
+                    const int col = (nh * 4 + x) * 8 + g;
+                    bh[x][0] = ph[(ks * 8 + t) * PC + col];
+                    bh[x][1] = ph[(ks * 8 + t + 4) * PC + col];
+                    bl[x][0] = pl[(ks * 8 + t) * PC + col];
+                    bl[x][1] = pl[(ks * 8 + t + 4) * PC + col];
+                }
 #pragma unroll
-            for (int x = 0; x < NT; ++x) mma_f16(acc[a][x], ah, bh[x]);
+                for (int a = 0; a < MT; ++a) {
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) mma_f16(acc[a][nh * 4 + x], al[a], bh[x]);
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) mma_f16(acc[a][nh * 4 + x], ah[a], bl[x]);
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) mma_f16(acc[a][nh * 4 + x], ah[a], bh[x]);
+                }
+            }
         }
     }
     cp_async_wait<0>();
@@ -471,9 +514,11 @@ static HScratch h_layout(float* scratch, int B, int64_t n, int64_t m_cap) {
     return s;
 }
 
-void launch_reorth_gram_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, const double* w0,
+bool reorth_h_supported(int B, int fp32) { return fp32 && (B == 16 || B == 32); }
+
+template <int B>
+static void gram_h_launch(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, const double* w0,
                           const double* w1, void* partials, void* Cmat, float* scratch, int64_t m_cap, cudaStream_t st) {
-    constexpr int B = 16;
     using G = GramH<B>;
     HScratch s = h_layout(scratch, B, p.n, m_cap);
     static bool configured = false;
@@ -491,12 +536,18 @@ void launch_reorth_gram_h(const ReorthPlan& p, int64_t n_global, const void* buf
     cudaMemsetAsync(s.cmax, 0, 4, st);
     int64_t rpr = (p.n + p.ranges - 1) / p.ranges;
     rpr = (rpr + G::RW - 1) / G::RW * G::RW;
-    dim3 grid(p.chunks, p.ranges);
+    dim3 grid((unsigned)((p.m + G::JT - 1) / G::JT), p.ranges);
     reorth_gram_h_kernel<B><<<grid, G::NW * 32, G::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.wh, s.wl, scale,
                                                                1.0f / (scale * scale), (float*)partials, rpr);
     const size_t count = (size_t)p.m * B * 2 * B;
     reorth_reduce_max_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>((const float*)partials, p.ranges, count,
                                                                                (float*)Cmat, s.cmax);
+}
+
+void launch_reorth_gram_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, const double* w0,
+                          const double* w1, void* partials, void* Cmat, float* scratch, int64_t m_cap, cudaStream_t st) {
+    if (p.B == 16) gram_h_launch<16>(p, n_global, buf, bstride, w0, w1, partials, Cmat, scratch, m_cap, st);
+    else gram_h_launch<32>(p, n_global, buf, bstride, w0, w1, partials, Cmat, scratch, m_cap, st);
 }
 
 // (re)build the packed coefficient words from C - after the all-reduce of C in a row-sharded run the local
@@ -511,7 +562,7 @@ __global__ void coeff_max_kernel(size_t count, const float* __restrict__ Cin, un
 
 void launch_reorth_coeff_h(const ReorthPlan& p, const void* Cmat, float* scratch, int64_t m_cap, int recompute_max,
                            cudaStream_t st) {
-    constexpr int B = 16;
+    const int B = p.B;
     HScratch s = h_layout(scratch, B, p.n, m_cap);
     const size_t count = (size_t)p.m * B * 2 * B;
     if (recompute_max) {
@@ -523,9 +574,9 @@ void launch_reorth_coeff_h(const ReorthPlan& p, const void* Cmat, float* scratch
                                                                             s.scale_c);
 }
 
-void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, double* w0,
+template <int B>
+static void update_h_launch(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, double* w0,
                             double* w1, void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st) {
-    constexpr int B = 16;
     using U = UpdH<B>;
     HScratch s = h_layout(scratch, B, p.n, m_cap);
     static bool configured = false;
@@ -536,6 +587,12 @@ void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* b
     const unsigned grid = (unsigned)((p.n + U::ROWS_CTA - 1) / U::ROWS_CTA);
     reorth_update_h_kernel<B><<<grid, U::NW * 32, U::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.ch, s.cl,
                                                                  pick_scale(n_global), s.scale_c, w0, w1, (float*)store_w1);
+}
+
+void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, double* w0,
+                            double* w1, void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st) {
+    if (p.B == 16) update_h_launch<16>(p, n_global, buf, bstride, w0, w1, store_w1, scratch, m_cap, st);
+    else update_h_launch<32>(p, n_global, buf, bstride, w0, w1, store_w1, scratch, m_cap, st);
 }
 
 }  // namespace rbl

@@ -429,11 +429,11 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     c.use_tc = reorth_tc_supported(B, c.fp32) && opt.reorth_impl != 1;
     if (opt.reorth_impl == 2 && !c.use_tc)
         throw Error(RBL_INVALID, "rbl_solve: tensor-core reorth needs precision=mixed and padded block size 16");
-    if (opt.reorth_impl == 3 && !c.use_tc)
-        throw Error(RBL_INVALID, "rbl_solve: tensor-core reorth needs precision=mixed and padded block size 16");
-    c.use_h = c.use_tc && opt.reorth_impl != 2;
+    if (opt.reorth_impl == 3 && !reorth_h_supported(B, c.fp32))
+        throw Error(RBL_INVALID, "rbl_solve: FP16-split tensor-core reorth needs precision=mixed and padded block size 16 or 32");
+    c.use_h = reorth_h_supported(B, c.fp32) && opt.reorth_impl != 1 && !(opt.reorth_impl == 2 && c.use_tc);
     c.use_d = reorth_d_supported(B, c.fp32) && opt.reorth_impl != 1;
-    if (c.use_tc) c.tc_scratch.ensure(std::max(reorth_tc_scratch_floats(B, c.nloc, m_cap), reorth_h_scratch_words(B, c.nloc, m_cap)));
+    if (c.use_tc || c.use_h) c.tc_scratch.ensure(std::max(reorth_tc_scratch_floats(B, c.nloc, m_cap), reorth_h_scratch_words(B, c.nloc, m_cap)));
     if (h->comm.active()) c.sendbuf.ensure(std::max<int64_t>(1, h->send_ptr[h->world]) * (size_t)B);
     c.hA.ensure((size_t)m_cap * B * B);
     c.hB.ensure((size_t)m_cap * B * B);

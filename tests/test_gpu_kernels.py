@@ -109,6 +109,14 @@ def test_reorth_simt_and_tensor_core_paths(gpu, impl, n, b, m):
     _reorth_case(gpu, n, b, m, True, impl=impl)
 
 
+@pytest.mark.parametrize("impl", [1, 3])
+@pytest.mark.parametrize("n,b,m", [(4000, 32, 5), (10007, 32, 37), (700, 32, 17), (70000, 32, 3), (5000, 27, 9), (128, 32, 1),
+                                   (20000, 32, 66)])
+def test_reorth_b32_simt_and_fp16_split_paths(gpu, impl, n, b, m):
+    """Config 3's block size: the scaled 2-term FP16 MMA kernels (impl 3, the default) against the SIMT kernels."""
+    _reorth_case(gpu, n, b, m, True, impl=impl)
+
+
 @pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("n,b,m", [(4000, 16, 5), (10007, 16, 70), (700, 16, 33), (70000, 16, 3), (5000, 13, 9), (64, 16, 1)])
 def test_reorth_fp64_simt_and_dmma_paths(gpu, impl, n, b, m):

@@ -132,7 +132,7 @@ def test_config4_reduced_image_graph_laplacian(gpu):
 
 
 def test_config3_reduced_er_b32_mixed(gpu):
-    """Erdos-Renyi, b = 32 (config 3's block size), mixed precision (SIMT fp32 reorth path for B = 32)."""
+    """Erdos-Renyi, b = 32 (config 3's block size), mixed precision (FP16-split tensor-core reorth, B = 32)."""
     n, k, b = 20000, 16, 32
     A = matrices.erdos_renyi_sym(n, 32, seed=7)
     Om = np.random.default_rng(7).standard_normal((n, b))
