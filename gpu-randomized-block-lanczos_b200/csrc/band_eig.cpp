@@ -84,6 +84,7 @@ void BandSym::matvec(const double* x, double* y) const {
 //     sign det T_r = (-1)^{#swaps} prod_{i<=r} sign U_ii ;
 // the number of sign changes along r is the number of eigenvalues of T below the shift (Sturm).
 void BandLU::factor(const BandSym& T, double shift) {
+    if (T.cancel && T.cancel->load(std::memory_order_relaxed)) throw Cancelled{};
     N = T.N;
     kd = T.kd;
     shift_ = shift;
@@ -563,6 +564,7 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
     std::deque<Interval> queue;
     std::vector<Interval> clusters;
     int active = 0;
+    bool cancelled = false;  // under mu: a worker saw T.cancel; everybody drains
     for (auto& r : roots)
         if (r.chi > r.clo && r.hi > r.lo) queue.push_back(r);
     std::atomic<int64_t> fac{0};
@@ -575,8 +577,8 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
             Interval iv;
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return !queue.empty() || active == 0; });
-                if (queue.empty()) break;
+                cv.wait(lk, [&] { return !queue.empty() || active == 0 || cancelled; });
+                if (queue.empty() || cancelled) break;
                 iv = queue.front();
                 queue.pop_front();
                 ++active;
@@ -641,15 +643,25 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
         for (auto& p : local) out.push_back(std::move(p));
     };
 
+    auto guarded_worker = [&](int seed) {
+        try {
+            worker(seed);
+        } catch (const Cancelled&) {
+            std::lock_guard<std::mutex> lk(mu);
+            cancelled = true;
+            cv.notify_all();
+        }
+    };
     int nt = std::max(1, threads);
     if (T.N < 400) nt = 1;
     if (nt == 1) {
-        worker(0);
+        guarded_worker(0);
     } else {
         std::vector<std::thread> th;
-        for (int t = 0; t < nt; ++t) th.emplace_back(worker, t);
+        for (int t = 0; t < nt; ++t) th.emplace_back(guarded_worker, t);
         for (auto& t : th) t.join();
     }
+    if (cancelled) throw Cancelled{};
 
     // tight clusters (degenerate Ritz values), in parallel: each orthogonal to the already accepted single
     // vectors within a few ctol; clusters that a bisection point split in two are repaired by the final pass
@@ -673,14 +685,24 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
             }
             fac += wk.nfac;
         };
+        std::atomic<bool> ccancel{false};
+        auto guarded_cworker = [&](int seed) {
+            try {
+                cworker(seed);
+            } catch (const Cancelled&) {
+                ccancel = true;
+                next = clusters.size();
+            }
+        };
         const int ct = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, clusters.size()));
         if (ct <= 1) {
-            cworker(0);
+            guarded_cworker(0);
         } else {
             std::vector<std::thread> th;
-            for (int t = 0; t < ct; ++t) th.emplace_back(cworker, t);
+            for (int t = 0; t < ct; ++t) th.emplace_back(guarded_cworker, t);
             for (auto& t : th) t.join();
         }
+        if (ccancel) throw Cancelled{};
         for (auto& f : found)
             for (auto& p : f) out.push_back(std::move(p));
     }
@@ -767,14 +789,23 @@ bool BandTopK::refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pair
         }
         fac += wk.nfac;
     };
+    std::atomic<bool> rcancel{false};
+    auto guarded_worker = [&]() {
+        try {
+            worker();
+        } catch (const Cancelled&) {
+            rcancel = true;
+        }
+    };
     const int nt = (int)std::min<int64_t>(std::max(1, threads), k);
     if (nt <= 1) {
-        worker();
+        guarded_worker();
     } else {
         std::vector<std::thread> th;
-        for (int t = 0; t < nt; ++t) th.emplace_back(worker);
+        for (int t = 0; t < nt; ++t) th.emplace_back(guarded_worker);
         for (auto& t : th) t.join();
     }
+    if (rcancel) throw Cancelled{};
     nfac += fac.load();
     pairs.erase(std::remove_if(pairs.begin(), pairs.end(), [](const Pair& p) { return p.v.empty(); }), pairs.end());
     if ((int64_t)pairs.size() * 4 < k * 3) return false;  // too little survived: slicing from scratch is cheaper

@@ -7,18 +7,23 @@
 // Sturm counts from a row-wise elimination with pairwise pivoting (leading-principal-minor signs),
 // inverse / Rayleigh-quotient iteration with the same factorisation for the vectors.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <vector>
 
 namespace rbl {
 
 // Symmetric band matrix, half-bandwidth kd, stored as full band rows: F[r*(2kd+1) + (c - r + kd)].
+// thrown out of BandTopK::check when BandSym::cancel was raised (background tracker being stopped)
+struct Cancelled {};
+
 struct BandSym {
     int64_t N = 0;
     int kd = 0;
     std::vector<double> F;
     double norm_inf = 0.0;
     double gersh_lo = 0.0, gersh_hi = 0.0;  // Gershgorin interval containing the spectrum
+    const std::atomic<bool>* cancel = nullptr;  // polled at every factorisation; set -> Cancelled is thrown
 
     void reset(int64_t n, int kd_);
     inline double& at(int64_t r, int64_t c) { return F[(size_t)r * (2 * kd + 1) + (size_t)(c - r + kd)]; }

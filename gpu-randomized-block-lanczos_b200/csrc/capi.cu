@@ -263,7 +263,7 @@ int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qb
         const int B = padded_block((int)b);
         const bool tc = impl != 1 && reorth_tc_supported(B, storage_fp32);
         const bool hs = impl != 1 && impl != 2 && reorth_h_supported(B, storage_fp32);
-        if ((impl == 2 && !tc) || (impl == 3 && !hs)) throw Error(RBL_INVALID, "rbl_reorth: tensor-core path needs fp32 storage and padded block size 16");
+        if ((impl == 2 && !tc) || (impl >= 3 && !hs)) throw Error(RBL_INVALID, "rbl_reorth: tensor-core path needs fp32 storage and padded block size 16");
         const size_t ssz = storage_fp32 ? 4 : 8;
         // pad the stored blocks
         std::vector<unsigned char> hb((size_t)m * n * B * ssz, 0);
@@ -290,9 +290,17 @@ int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qb
         } else if (hs) {
             DevBuf<float> scratch;
             scratch.alloc(reorth_h_scratch_words(B, n, m));
-            launch_reorth_gram_h(p, n, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, scratch.p, m, 0);
+            const int presplit = impl != 3;   // default: the split16 slab format the solver uses (split16.h)
+            DevBuf<unsigned char> dsplit;
+            const void* slab = dbuf.p;
+            if (presplit) {
+                dsplit.alloc(hb.size());
+                launch_encode_split(B, n * m, (const float*)dbuf.p, dsplit.p, reorth_h_scale(n), 0);
+                slab = dsplit.p;
+            }
+            launch_reorth_gram_h(p, n, slab, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, scratch.p, m, presplit, 0);
             launch_reorth_coeff_h(p, dC.p, scratch.p, m, 0, 0);
-            launch_reorth_update_h(p, n, dbuf.p, n * B, W0.dev.p, W1.dev.p, nullptr, scratch.p, m, 0);
+            launch_reorth_update_h(p, n, slab, n * B, W0.dev.p, W1.dev.p, nullptr, scratch.p, m, presplit, 0);
             RBL_CUDA(cudaDeviceSynchronize());
         } else if (tc) {
             DevBuf<float> scratch;
@@ -353,7 +361,7 @@ int rbl_ritz(int64_t n, int64_t b, int64_t m, int64_t k, int storage_fp32, const
         dV.alloc((size_t)n * k * ssz);
         RBL_CUDA(cudaMemcpy(dbuf.p, hb.data(), hb.size(), cudaMemcpyHostToDevice));
         RBL_CUDA(cudaMemcpy(dS.p, hs.data(), hs.size(), cudaMemcpyHostToDevice));
-        launch_ritz(B, storage_fp32, n, m, (int)k, kpad, dbuf.p, n * B, dS.p, dV.p, n, storage_fp32, 0);
+        launch_ritz(B, storage_fp32, n, m, (int)k, kpad, dbuf.p, n * B, dS.p, dV.p, n, storage_fp32, 0.f, 0);
         RBL_CUDA(cudaDeviceSynchronize());
         RBL_CUDA(cudaMemcpy(v_out, dV.p, (size_t)n * k * ssz, cudaMemcpyDeviceToHost));
         return (int)RBL_OK;

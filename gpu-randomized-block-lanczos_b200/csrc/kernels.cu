@@ -9,6 +9,7 @@
 //   reorth_gram/update   hybrid_part_reorth! / part_reorth_gpu_async!      :59-81,:29-47 (4 cuBLAS gemm per block)
 //   ritz_kernel          recover_eigvec                                    :106-132
 #include "kernels.h"
+#include "split16.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -228,7 +229,16 @@ __global__ void __launch_bounds__(RowOpCfg<B>::TR) rowop_kernel(RowOpArgs a) {
             }
         }
         if (a.store != nullptr) {
-            if (a.store_fp32) {
+            if (a.store_fp32 && a.store_split_scale != 0.f) {
+                unsigned* gw = reinterpret_cast<unsigned*>(a.store) + (size_t)r0 * B;
+                for (int idx = tid; idx < nvec; idx += TR) {
+                    const int r = idx / (B / 2), p = idx % (B / 2);
+                    unsigned hi, lo;
+                    split_h2((float)sY[r * P + 2 * p], (float)sY[r * P + 2 * p + 1], a.store_split_scale, hi, lo);
+                    gw[r * B + p] = hi;
+                    gw[r * B + B / 2 + p] = lo;
+                }
+            } else if (a.store_fp32) {
                 float2* gs = reinterpret_cast<float2*>(reinterpret_cast<float*>(a.store) + (size_t)r0 * B);
                 for (int idx = tid; idx < nvec; idx += TR) {
                     const int r = idx / (B / 2), c = (idx % (B / 2)) * 2;
@@ -784,10 +794,10 @@ void launch_reorth_update(const ReorthPlan& p, const void* buf, int64_t bstride,
 // K6: Ritz vectors  V = Qbuf * S  (SIMT version; ~1% of a solve).  A thread owns RPT rows x 16 targets;
 // consecutive lanes are consecutive rows so that the column-major V stores coalesce.
 // =================================================================================================
-template <int B, typename S, typename VT>
+template <int B, typename S, typename VT, bool SPLIT>
 __global__ void __launch_bounds__(256) ritz_kernel(int64_t n, int64_t m, int k, int kpad, const S* __restrict__ buf,
                                                    int64_t bstride, const S* __restrict__ Smat, VT* __restrict__ V,
-                                                   int64_t ldv, int RL, int JC) {
+                                                   int64_t ldv, int RL, int JC, float split_inv_scale) {
     constexpr int RPT = 2;
     constexpr int TT = 16;
     constexpr int VW = 16 / sizeof(S);
@@ -834,8 +844,20 @@ __global__ void __launch_bounds__(256) ritz_kernel(int64_t n, int64_t m, int k, 
             S bv[RPT][B];
 #pragma unroll
             for (int u = 0; u < RPT; ++u) {
-                if (valid[u]) load_vec<S, B>(buf + (size_t)(j0 + jb) * bstride + (size_t)rows[u] * B, bv[u]);
-                else {
+                if (valid[u]) {
+                    load_vec<S, B>(buf + (size_t)(j0 + jb) * bstride + (size_t)rows[u] * B, bv[u]);
+                    if constexpr (SPLIT && sizeof(S) == 4) {  // split16 row: words [hi pairs | lo pairs]
+                        float dec[B];
+#pragma unroll
+                        for (int p = 0; p < B / 2; ++p) {
+                            const float2 x = join_h2(__float_as_uint(bv[u][p]), __float_as_uint(bv[u][B / 2 + p]), split_inv_scale);
+                            dec[2 * p] = x.x;
+                            dec[2 * p + 1] = x.y;
+                        }
+#pragma unroll
+                        for (int c = 0; c < B; ++c) bv[u][c] = dec[c];
+                    }
+                } else {
 #pragma unroll
                     for (int c = 0; c < B; ++c) bv[u][c] = S(0);
                 }
@@ -871,9 +893,9 @@ __global__ void __launch_bounds__(256) ritz_kernel(int64_t n, int64_t m, int k, 
     }
 }
 
-template <int B, typename S, typename VT>
+template <int B, typename S, typename VT, bool SPLIT = false>
 static void ritz_launch_t(int64_t n, int64_t m, int k, int kpad, const void* buf, int64_t bstride, const void* Smat,
-                          void* V, int64_t ldv, cudaStream_t st) {
+                          void* V, int64_t ldv, cudaStream_t st, float split_inv_scale = 0.f) {
     const int KG = kpad / 16;
     int RL = 256 / KG;
     if (RL > 32) RL = (RL / 32) * 32;   // whole warps share a target group (broadcast smem reads)
@@ -882,17 +904,24 @@ static void ritz_launch_t(int64_t n, int64_t m, int k, int kpad, const void* buf
     if (JC < 1) JC = 1;
     if (JC > 16) JC = 16;
     const size_t smem = (size_t)JC * B * kpad * sizeof(S);
-    cudaFuncSetAttribute(ritz_kernel<B, S, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(ritz_kernel<B, S, VT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     unsigned grid = (unsigned)((n + (int64_t)RL * 2 - 1) / ((int64_t)RL * 2));
-    ritz_kernel<B, S, VT><<<grid, 256, smem, st>>>(n, m, k, kpad, (const S*)buf, bstride, (const S*)Smat, (VT*)V, ldv, RL, JC);
+    ritz_kernel<B, S, VT, SPLIT><<<grid, 256, smem, st>>>(n, m, k, kpad, (const S*)buf, bstride, (const S*)Smat, (VT*)V, ldv, RL,
+                                                         JC, split_inv_scale);
 }
 
 void launch_ritz(int B, int fp32, int64_t n, int64_t m, int k, int kpad, const void* buf, int64_t bstride,
-                 const void* Smat, void* V, int64_t ldv, int v_fp32, cudaStream_t st) {
+                 const void* Smat, void* V, int64_t ldv, int v_fp32, float split_scale, cudaStream_t st) {
     if (kpad / 16 > 256) { std::fprintf(stderr, "rbl: k too large for ritz kernel\n"); std::abort(); }
     dispatch_B(B, [&](auto bc) {
         constexpr int BB = decltype(bc)::value;
-        if (fp32) {
+        if (fp32 && split_scale != 0.f) {
+            if constexpr (BB >= 16) {
+                const float inv = 1.0f / split_scale;
+                if (v_fp32) ritz_launch_t<BB, float, float, true>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st, inv);
+                else ritz_launch_t<BB, float, double, true>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st, inv);
+            }
+        } else if (fp32) {
             if (v_fp32) ritz_launch_t<BB, float, float>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st);
             else ritz_launch_t<BB, float, double>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st);
         } else {
@@ -944,7 +973,32 @@ void launch_convert_s(int64_t count, const double* src, void* dst, int fp32, cud
     if (fp32) convert_kernel<float><<<grid, 256, 0, st>>>(count, src, (float*)dst);
     else convert_kernel<double><<<grid, 256, 0, st>>>(count, src, (double*)dst);
 }
-void launch_store_block(int B, int64_t n, const double* src, void* dst, int fp32, cudaStream_t st) {
+template <typename T>
+__global__ void encode_split_kernel(int B, int64_t rows, const T* __restrict__ src, unsigned* __restrict__ dst, float scale) {
+    const int hb = B / 2;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one column pair per thread
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < rows * hb; i += stride) {
+        const int64_t r = i / hb;
+        const int p = (int)(i % hb);
+        unsigned hi, lo;
+        split_h2((float)src[r * B + 2 * p], (float)src[r * B + 2 * p + 1], scale, hi, lo);
+        dst[r * B + p] = hi;
+        dst[r * B + hb + p] = lo;
+    }
+}
+void launch_encode_split(int B, int64_t rows, const float* src, void* dst, float scale, cudaStream_t st) {
+    if (rows <= 0) return;
+    int grid = (int)std::min<int64_t>((rows * (B / 2) + 255) / 256, (int64_t)num_sms() * 16);
+    encode_split_kernel<float><<<grid, 256, 0, st>>>(B, rows, src, (unsigned*)dst, scale);
+}
+void launch_store_block(int B, int64_t n, const double* src, void* dst, int fp32, float split_scale, cudaStream_t st) {
+    if (fp32 && split_scale != 0.f) {
+        if (n <= 0) return;
+        int grid = (int)std::min<int64_t>((n * (B / 2) + 255) / 256, (int64_t)num_sms() * 16);
+        encode_split_kernel<double><<<grid, 256, 0, st>>>(B, n, src, (unsigned*)dst, split_scale);
+        return;
+    }
     launch_convert_s(n * B, src, dst, fp32, st);
 }
 void launch_load_block(int B, int64_t n, const void* src, int fp32, double* dst, cudaStream_t st) {

@@ -38,6 +38,7 @@ struct RowOpArgs {
     int write_y = 0;
     void* store = nullptr;
     int store_fp32 = 0;
+    float store_split_scale = 0.f;  // != 0 (with store_fp32): write the split16 row format (split16.h) with this scale
     const double* gram_z = nullptr;
     int do_gram = 0;
     double* partials = nullptr;   // [grid][B*B]
@@ -98,11 +99,14 @@ bool reorth_h_supported(int B, int fp32);   // fp32 buffer, B = 16 or 32
 size_t reorth_h_scratch_words(int B, int64_t n, int64_t m_cap);
 void launch_reorth_gram_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t block_stride_elems,
                           const double* w0, const double* w1, void* partials, void* C, float* scratch, int64_t m_cap,
-                          cudaStream_t st);
+                          int presplit, cudaStream_t st);
+float reorth_h_scale(int64_t n_global);   // the operand scale S; the split16 slab is written with it
 void launch_reorth_coeff_h(const ReorthPlan& p, const void* C, float* scratch, int64_t m_cap, int recompute_max,
                            cudaStream_t st);
 void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t block_stride_elems,
-                            double* w0, double* w1, void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st);
+                            double* w0, double* w1, void* store_w1, float* scratch, int64_t m_cap, int presplit,
+                            cudaStream_t st);
+// `presplit`: buf (and store_w1) hold split16 rows (split16.h) instead of fp32 values
 
 // all-fp64 mode: FP64 tensor-core MMA (mma.sync.m8n8k4.f64) + cp.async rings, B = 16 (reorth_f64.cu)
 bool reorth_d_supported(int B, int fp32);
@@ -115,13 +119,16 @@ void launch_reorth_update_d(const ReorthPlan& p, const void* buf, int64_t block_
 // V[:, t] = sum_j buf_j * S[(j*B .. j*B+B), t];  S device, row-major (m*B) x kpad in the buffer's type;
 // V column-major n x k (ldv), float or double as the buffer.                  RBL_gpu.jl:106-132
 void launch_ritz(int B, int fp32, int64_t n, int64_t m, int k, int kpad, const void* buf, int64_t block_stride_elems,
-                 const void* S, void* V, int64_t ldv, int v_fp32, cudaStream_t st);
+                 const void* S, void* V, int64_t ldv, int v_fp32, float split_scale, cudaStream_t st);
+// split_scale != 0: the fp32 buffer holds split16 rows written with that scale
 
 // ---- layout / conversion helpers -------------------------------------------------------------------
 // column-major n x b (ld) fp64  ->  row-major n x B fp64 (zero padded)
 void launch_colmajor_to_block(int B, int64_t n, int b, const double* src, int64_t ld, double* dst, cudaStream_t st);
 void launch_block_to_colmajor(int B, int64_t n, int b, const double* src, double* dst, int64_t ld, cudaStream_t st);
-void launch_store_block(int B, int64_t n, const double* src, void* dst, int fp32, cudaStream_t st);
+void launch_store_block(int B, int64_t n, const double* src, void* dst, int fp32, float split_scale, cudaStream_t st);
+// fp32 rows -> split16 rows (out of place)
+void launch_encode_split(int B, int64_t rows, const float* src, void* dst, float scale, cudaStream_t st);
 void launch_load_block(int B, int64_t n, const void* src, int fp32, double* dst, cudaStream_t st);
 void launch_randn(int64_t count, uint64_t seed, uint64_t offset, double* dst, cudaStream_t st);
 void launch_convert_s(int64_t count, const double* src, void* dst, int fp32, cudaStream_t st);

@@ -17,6 +17,7 @@
 #include <cstdio>
 
 #include "kernels.h"
+#include "split16.h"
 
 namespace rbl {
 
@@ -32,14 +33,24 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// two scaled fp32 values -> packed (hi, hi) and (lo, lo) f16x2 words; element 0 in the low half
-__device__ __forceinline__ void split_h2(float x0, float x1, float scale, unsigned& hi, unsigned& lo) {
-    const float s0 = x0 * scale, s1 = x1 * scale;
-    const __half2 h = __floats2half2_rn(s0, s1);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
-    hi = *reinterpret_cast<const unsigned*>(&h);
-    lo = *reinterpret_cast<const unsigned*>(&l);
+// four 8x8 b16 matrices from shared memory; every lane supplies one 16-byte row address (lanes 8i..8i+7: matrix i)
+__device__ __forceinline__ void ldmatrix_x4(unsigned (&r)[4], const void* smem_row) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem_row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(unsigned (&r)[4], const void* smem_row) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem_row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+// Pre-split slab rows (split16.h) staged in shared memory: a row keeps its 4B contiguous bytes (B/4 chunks of
+// 16 bytes: hi columns first, then lo); chunk q of row r sits at position q ^ swz(r), which makes the eight row
+// addresses of every ldmatrix 8x8 tile fall into eight different 16-byte bank groups.
+template <int B>
+__device__ __forceinline__ int split_swz(int r) {
+    if constexpr (B == 16) return (r >> 1) & 3;
+    else return r & 7;
 }
 
 // D(16x8) += A(16x16, row) * B(16x8, col), f16 inputs, fp32 accumulate
@@ -111,7 +122,7 @@ __device__ __forceinline__ int gram_slot(int r, int c) {
     else return p * 32 + ((((c >> 2) ^ ((p & 3) << 1))) << 2) + (c & 3);
 }
 
-template <int B>
+template <int B, bool PS>
 __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
     reorth_gram_h_kernel(int64_t n, int64_t m, const float* __restrict__ buf, int64_t bstride,
                          const unsigned* __restrict__ wh, const unsigned* __restrict__ wl, float scale,
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
             const int row = rem / (B / 4), c4 = rem % (B / 4);
             blk_ok[u] = (jbase + blk) < m;
             row0[u] = row;
-            dst0[u] = blk * RS * PA + gram_slot<B>(row, c4 * 4);
+            dst0[u] = PS ? blk * RS * PA + row * B + ((c4 ^ split_swz<B>(row)) << 2) : blk * RS * PA + gram_slot<B>(row, c4 * 4);
             src0[u] = buf + (size_t)(blk_ok[u] ? jbase + blk : 0) * bstride + (size_t)(rbeg + row) * B + c4 * 4;
         }
         auto issue_a = [&](int ks) {
@@ -223,12 +234,22 @@ __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
                 unsigned ah[MT][4], al[MT][4];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                    const int c0 = mt * 16 + g;
-                    // A[m = column][k = row]: register halves are rows 2t, 2t+1 (and +8) of columns c0 / c0+8
-                    split_h2(a[gram_slot<B>(2 * t, c0)], a[gram_slot<B>(2 * t + 1, c0)], scale, ah[mt][0], al[mt][0]);
-                    split_h2(a[gram_slot<B>(2 * t, c0 + 8)], a[gram_slot<B>(2 * t + 1, c0 + 8)], scale, ah[mt][1], al[mt][1]);
-                    split_h2(a[gram_slot<B>(2 * t + 8, c0)], a[gram_slot<B>(2 * t + 9, c0)], scale, ah[mt][2], al[mt][2]);
-                    split_h2(a[gram_slot<B>(2 * t + 8, c0 + 8)], a[gram_slot<B>(2 * t + 9, c0 + 8)], scale, ah[mt][3], al[mt][3]);
+                    if constexpr (PS) {
+                        // the slab already holds (hi | lo) f16 rows: four transposed 8x8 tiles per m-tile and part.
+                        // lanes 8i..8i+7 address tile i: rows (i>>1)*8.., column chunk 2mt + (i&1)
+                        const int row = (lane & 7) + ((lane >> 4) << 3);
+                        const int q = 2 * mt + ((lane >> 3) & 1);
+                        const float* rowp = a + row * B;
+                        ldmatrix_x4_trans(ah[mt], rowp + ((q ^ split_swz<B>(row)) << 2));
+                        ldmatrix_x4_trans(al[mt], rowp + (((q + B / 8) ^ split_swz<B>(row)) << 2));
+                    } else {
+                        const int c0 = mt * 16 + g;
+                        // A[m = column][k = row]: register halves are rows 2t, 2t+1 (and +8) of columns c0 / c0+8
+                        split_h2(a[gram_slot<B>(2 * t, c0)], a[gram_slot<B>(2 * t + 1, c0)], scale, ah[mt][0], al[mt][0]);
+                        split_h2(a[gram_slot<B>(2 * t, c0 + 8)], a[gram_slot<B>(2 * t + 1, c0 + 8)], scale, ah[mt][1], al[mt][1]);
+                        split_h2(a[gram_slot<B>(2 * t + 8, c0)], a[gram_slot<B>(2 * t + 9, c0)], scale, ah[mt][2], al[mt][2]);
+                        split_h2(a[gram_slot<B>(2 * t + 8, c0 + 8)], a[gram_slot<B>(2 * t + 9, c0 + 8)], scale, ah[mt][3], al[mt][3]);
+                    }
                 }
 #pragma unroll
                 for (int nh = 0; nh < NH; ++nh) {
@@ -310,17 +331,19 @@ __global__ void split_coeff_h_kernel(size_t nwords, int B, const float* __restri
 // Update.  MMA roles: M = 16 rows, N = 8 targets, K = 16 Krylov columns (B/16 k-steps per stored block).
 // Every warp owns 32 rows; B = 16: 16 warps, B = 32: 8 warps (shared memory).
 // =================================================================================================
-template <int B>
+template <int B, bool PS>
 struct UpdH {
     static constexpr int NW = (B == 16) ? 16 : 8;  // warps per CTA
     static constexpr int MT = 2;
     static constexpr int NT = (2 * B) / 8;
     static constexpr int NH = NT / 4;
     static constexpr int KS = B / 16;
-    static constexpr int PA = B + 8;             // floats per staged row: conflict-free float2 A fragments, 32-byte multiple
+    // words per staged row.  fp32 slab: B + 8 (conflict-free float2 A fragments, 32-byte multiple);
+    // pre-split slab: B, swizzled for ldmatrix (split_swz)
+    static constexpr int PA = PS ? B : B + 8;
     static constexpr int PC = 2 * B + 8;         // words per staged coefficient row pair
     static constexpr int JC = (B == 16) ? 8 : 4;
-    static constexpr int NST = 3;
+    static constexpr int NST = PS ? 4 : 3;
     static constexpr int STAGE = 32 * PA;
     static constexpr int CBUF = JC * (B / 2) * PC;
     static constexpr int ROWS_CTA = NW * 32;
@@ -328,13 +351,13 @@ struct UpdH {
     static constexpr size_t smem_bytes = (size_t)(NW * NST * STAGE + 4 * CBUF) * sizeof(float);
 };
 
-template <int B>
-__global__ void __launch_bounds__(UpdH<B>::NW * 32, 1)
+template <int B, bool PS>
+__global__ void __launch_bounds__(UpdH<B, PS>::NW * 32, 1)
     reorth_update_h_kernel(int64_t n, int64_t m, const float* __restrict__ buf, int64_t bstride,
                            const unsigned* __restrict__ Ch, const unsigned* __restrict__ Cl, float scale_a,
                            const float* __restrict__ scale_c_ptr, double* __restrict__ w0, double* __restrict__ w1,
                            float* __restrict__ store_w1) {
-    using C = UpdH<B>;
+    using C = UpdH<B, PS>;
     constexpr int NW = C::NW, MT = C::MT, NT = C::NT, NH = C::NH, KS = C::KS, PA = C::PA, PC = C::PC, JC = C::JC,
                   NST = C::NST, STAGE = C::STAGE, CBUF = C::CBUF, NCP = C::NCP, NTHR = NW * 32;
     static_assert(B == 16 || B == 32, "instantiated for B = 16, 32");
@@ -363,7 +386,7 @@ __global__ void __launch_bounds__(UpdH<B>::NW * 32, 1)
         const int q = lane + 32 * u;
         const int row = q / (B / 4), c4 = q % (B / 4);
         row_ok[u] = (r0 + row) < n;
-        dst0[u] = row * PA + c4 * 4;
+        dst0[u] = PS ? row * PA + ((c4 ^ split_swz<B>(row)) << 2) : row * PA + c4 * 4;
         src0[u] = buf + (size_t)(row_ok[u] ? r0 + row : 0) * B + c4 * 4;
     }
     auto issue_a = [&](int j) {
@@ -416,16 +439,25 @@ __global__ void __launch_bounds__(UpdH<B>::NW * 32, 1)
             unsigned ah[MT][4], al[MT][4];
 #pragma unroll
             for (int a = 0; a < MT; ++a) {
-                const float* ap = st + (a * 16) * PA + ks * 16;
-                // A[m = row][k = column]: register halves are columns 2t, 2t+1 (and +8) of rows g / g+8
-                const float2 v0 = *reinterpret_cast<const float2*>(ap + g * PA + 2 * t);
-                const float2 v1 = *reinterpret_cast<const float2*>(ap + (g + 8) * PA + 2 * t);
-                const float2 v2 = *reinterpret_cast<const float2*>(ap + g * PA + 2 * t + 8);
-                const float2 v3 = *reinterpret_cast<const float2*>(ap + (g + 8) * PA + 2 * t + 8);
-                split_h2(v0.x, v0.y, scale_a, ah[a][0], al[a][0]);
-                split_h2(v1.x, v1.y, scale_a, ah[a][1], al[a][1]);
-                split_h2(v2.x, v2.y, scale_a, ah[a][2], al[a][2]);
-                split_h2(v3.x, v3.y, scale_a, ah[a][3], al[a][3]);
+                if constexpr (PS) {
+                    // lanes 8i..8i+7 address tile i: rows 16a + (i&1)*8.., column chunk 2ks + (i>>1)
+                    const int row = a * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                    const int q = 2 * ks + (lane >> 4);
+                    const float* rowp = st + row * PA;
+                    ldmatrix_x4(ah[a], rowp + ((q ^ split_swz<B>(row)) << 2));
+                    ldmatrix_x4(al[a], rowp + (((q + B / 8) ^ split_swz<B>(row)) << 2));
+                } else {
+                    const float* ap = st + (a * 16) * PA + ks * 16;
+                    // A[m = row][k = column]: register halves are columns 2t, 2t+1 (and +8) of rows g / g+8
+                    const float2 v0 = *reinterpret_cast<const float2*>(ap + g * PA + 2 * t);
+                    const float2 v1 = *reinterpret_cast<const float2*>(ap + (g + 8) * PA + 2 * t);
+                    const float2 v2 = *reinterpret_cast<const float2*>(ap + g * PA + 2 * t + 8);
+                    const float2 v3 = *reinterpret_cast<const float2*>(ap + (g + 8) * PA + 2 * t + 8);
+                    split_h2(v0.x, v0.y, scale_a, ah[a][0], al[a][0]);
+                    split_h2(v1.x, v1.y, scale_a, ah[a][1], al[a][1]);
+                    split_h2(v2.x, v2.y, scale_a, ah[a][2], al[a][2]);
+                    split_h2(v3.x, v3.y, scale_a, ah[a][3], al[a][3]);
+                }
             }
 #pragma unroll
             for (int nh = 0; nh < NH; ++nh) {
@@ -474,8 +506,17 @@ __global__ void __launch_bounds__(UpdH<B>::NW * 32, 1)
                     v.x -= (double)d0;
                     v.y -= (double)d1;
                     *p = v;
-                    if (store_w1 != nullptr)
-                        *reinterpret_cast<float2*>(store_w1 + (size_t)row * B + (tgt - B)) = make_float2((float)v.x, (float)v.y);
+                    if (store_w1 != nullptr) {
+                        if constexpr (PS) {
+                            unsigned hi, lo;
+                            split_h2((float)v.x, (float)v.y, scale_a, hi, lo);
+                            unsigned* srow = reinterpret_cast<unsigned*>(store_w1) + (size_t)row * B;
+                            srow[(tgt - B) >> 1] = hi;
+                            srow[B / 2 + ((tgt - B) >> 1)] = lo;
+                        } else {
+                            *reinterpret_cast<float2*>(store_w1 + (size_t)row * B + (tgt - B)) = make_float2((float)v.x, (float)v.y);
+                        }
+                    }
                 }
             }
         }
@@ -516,14 +557,14 @@ static HScratch h_layout(float* scratch, int B, int64_t n, int64_t m_cap) {
 
 bool reorth_h_supported(int B, int fp32) { return fp32 && (B == 16 || B == 32); }
 
-template <int B>
+template <int B, bool PS>
 static void gram_h_launch(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, const double* w0,
                           const double* w1, void* partials, void* Cmat, float* scratch, int64_t m_cap, cudaStream_t st) {
     using G = GramH<B>;
     HScratch s = h_layout(scratch, B, p.n, m_cap);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(reorth_gram_h_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
+        cudaFuncSetAttribute(reorth_gram_h_kernel<B, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
         configured = true;
     }
     int sms = 148, dev = 0;
@@ -537,7 +578,7 @@ static void gram_h_launch(const ReorthPlan& p, int64_t n_global, const void* buf
     int64_t rpr = (p.n + p.ranges - 1) / p.ranges;
     rpr = (rpr + G::RW - 1) / G::RW * G::RW;
     dim3 grid((unsigned)((p.m + G::JT - 1) / G::JT), p.ranges);
-    reorth_gram_h_kernel<B><<<grid, G::NW * 32, G::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.wh, s.wl, scale,
+    reorth_gram_h_kernel<B, PS><<<grid, G::NW * 32, G::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.wh, s.wl, scale,
                                                                1.0f / (scale * scale), (float*)partials, rpr);
     const size_t count = (size_t)p.m * B * 2 * B;
     reorth_reduce_max_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>((const float*)partials, p.ranges, count,
@@ -545,10 +586,18 @@ static void gram_h_launch(const ReorthPlan& p, int64_t n_global, const void* buf
 }
 
 void launch_reorth_gram_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, const double* w0,
-                          const double* w1, void* partials, void* Cmat, float* scratch, int64_t m_cap, cudaStream_t st) {
-    if (p.B == 16) gram_h_launch<16>(p, n_global, buf, bstride, w0, w1, partials, Cmat, scratch, m_cap, st);
-    else gram_h_launch<32>(p, n_global, buf, bstride, w0, w1, partials, Cmat, scratch, m_cap, st);
+                          const double* w1, void* partials, void* Cmat, float* scratch, int64_t m_cap, int presplit,
+                          cudaStream_t st) {
+    if (p.B == 16) {
+        if (presplit) gram_h_launch<16, true>(p, n_global, buf, bstride, w0, w1, partials, Cmat, scratch, m_cap, st);
+        else gram_h_launch<16, false>(p, n_global, buf, bstride, w0, w1, partials, Cmat, scratch, m_cap, st);
+    } else {
+        if (presplit) gram_h_launch<32, true>(p, n_global, buf, bstride, w0, w1, partials, Cmat, scratch, m_cap, st);
+        else gram_h_launch<32, false>(p, n_global, buf, bstride, w0, w1, partials, Cmat, scratch, m_cap, st);
+    }
 }
+
+float reorth_h_scale(int64_t n_global) { return pick_scale(n_global); }
 
 // (re)build the packed coefficient words from C - after the all-reduce of C in a row-sharded run the local
 // maxima differ, so `recompute_max` rescans C first
@@ -574,25 +623,30 @@ void launch_reorth_coeff_h(const ReorthPlan& p, const void* Cmat, float* scratch
                                                                             s.scale_c);
 }
 
-template <int B>
+template <int B, bool PS>
 static void update_h_launch(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, double* w0,
                             double* w1, void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st) {
-    using U = UpdH<B>;
+    using U = UpdH<B, PS>;
     HScratch s = h_layout(scratch, B, p.n, m_cap);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(reorth_update_h_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::smem_bytes);
+        cudaFuncSetAttribute(reorth_update_h_kernel<B, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::smem_bytes);
         configured = true;
     }
     const unsigned grid = (unsigned)((p.n + U::ROWS_CTA - 1) / U::ROWS_CTA);
-    reorth_update_h_kernel<B><<<grid, U::NW * 32, U::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.ch, s.cl,
+    reorth_update_h_kernel<B, PS><<<grid, U::NW * 32, U::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.ch, s.cl,
                                                                  pick_scale(n_global), s.scale_c, w0, w1, (float*)store_w1);
 }
 
 void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, double* w0,
-                            double* w1, void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st) {
-    if (p.B == 16) update_h_launch<16>(p, n_global, buf, bstride, w0, w1, store_w1, scratch, m_cap, st);
-    else update_h_launch<32>(p, n_global, buf, bstride, w0, w1, store_w1, scratch, m_cap, st);
+                            double* w1, void* store_w1, float* scratch, int64_t m_cap, int presplit, cudaStream_t st) {
+    if (p.B == 16) {
+        if (presplit) update_h_launch<16, true>(p, n_global, buf, bstride, w0, w1, store_w1, scratch, m_cap, st);
+        else update_h_launch<16, false>(p, n_global, buf, bstride, w0, w1, store_w1, scratch, m_cap, st);
+    } else {
+        if (presplit) update_h_launch<32, true>(p, n_global, buf, bstride, w0, w1, store_w1, scratch, m_cap, st);
+        else update_h_launch<32, false>(p, n_global, buf, bstride, w0, w1, store_w1, scratch, m_cap, st);
+    }
 }
 
 }  // namespace rbl

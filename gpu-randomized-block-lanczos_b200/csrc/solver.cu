@@ -15,6 +15,7 @@
 #include <condition_variable>
 #include <cmath>
 #include <cstdio>
+#include <atomic>
 #include <cstring>
 #include <future>
 #include <memory>
@@ -275,6 +276,7 @@ struct Ctx {
           tc_scratch(ws.tc_scratch), sendbuf(ws.sendbuf), hA(ws.hA), hB(ws.hB), hqr(ws.hqr) {}
     bool use_tc = false;
     bool use_h = false;   // FP16-split tensor-core kernels (default when supported); else TF32x3
+    float split_scale = 0.f;  // != 0: the Krylov slab holds split16 rows (split16.h) written with this scale
     bool use_d = false;   // all-fp64 mode: FP64 tensor-core kernels
     int rgrid = 1;
     int64_t launches = 0;
@@ -429,9 +431,10 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     c.use_tc = reorth_tc_supported(B, c.fp32) && opt.reorth_impl != 1;
     if (opt.reorth_impl == 2 && !c.use_tc)
         throw Error(RBL_INVALID, "rbl_solve: tensor-core reorth needs precision=mixed and padded block size 16");
-    if (opt.reorth_impl == 3 && !reorth_h_supported(B, c.fp32))
+    if (opt.reorth_impl >= 3 && !reorth_h_supported(B, c.fp32))
         throw Error(RBL_INVALID, "rbl_solve: FP16-split tensor-core reorth needs precision=mixed and padded block size 16 or 32");
     c.use_h = reorth_h_supported(B, c.fp32) && opt.reorth_impl != 1 && !(opt.reorth_impl == 2 && c.use_tc);
+    c.split_scale = (c.use_h && opt.reorth_impl != 3) ? reorth_h_scale(h->n) : 0.f;
     c.use_d = reorth_d_supported(B, c.fp32) && opt.reorth_impl != 1;
     if (c.use_tc || c.use_h) c.tc_scratch.ensure(std::max(reorth_tc_scratch_floats(B, c.nloc, m_cap), reorth_h_scratch_words(B, c.nloc, m_cap)));
     if (h->comm.active()) c.sendbuf.ensure(std::max<int64_t>(1, h->send_ptr[h->world]) * (size_t)B);
@@ -519,10 +522,12 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         std::condition_variable cv;
         std::thread th;
         bool active = false, stop = false, have_req = false, have_res = false;
+        std::atomic<bool> cancel{false};   // raised with `stop`: the tracker abandons the eigensolve it is in
         BandSym req;
         TopKResult res;
     } shadow;
-    auto shadow_loop = [&shadow, k, b](int nthreads) {
+    const int shadow_verbose = opt.verbose;
+    auto shadow_loop = [&shadow, k, b, shadow_verbose](int nthreads) {
         BandTopK tracker;
         tracker.threads = nthreads;
         for (;;) {
@@ -534,7 +539,18 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
                 Tc = std::move(shadow.req);
                 shadow.have_req = false;
             }
-            TopKResult r = tracker.check(Tc, nullptr, b, k, 0.0, true);
+            Tc.cancel = &shadow.cancel;
+            TopKResult r;
+            const double ts0 = now_s();
+            const int64_t f0 = tracker.total_factorizations;
+            try {
+                r = tracker.check(Tc, nullptr, b, k, 0.0, true);
+            } catch (const Cancelled&) {
+                return;
+            }
+            if (shadow_verbose > 1)
+                std::fprintf(stderr, "[rbl] tracker N=%lld: %.1f ms, %lld factorisations, all pairs %d\n", (long long)Tc.N,
+                             (now_s() - ts0) * 1e3, (long long)(tracker.total_factorizations - f0), (int)r.have_all);
             std::lock_guard<std::mutex> lk(shadow.mu);
             if (r.have_all) {
                 shadow.res = std::move(r);
@@ -548,6 +564,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             {
                 std::lock_guard<std::mutex> lk(s.mu);
                 s.stop = true;
+                s.cancel = true;
             }
             s.cv.notify_all();
             if (s.th.joinable()) s.th.join();
@@ -596,7 +613,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         RBL_CUDA(cudaMemcpyAsync(c.hB.p + (size_t)(it - 1) * B * B, c.qr.p->R, (size_t)B * B * 8, cudaMemcpyDeviceToHost, c.st));
     };
     c.tm.mark(PH_LOC);
-    launch_store_block(B, c.nloc, cur, c.slot(0), c.fp32, c.st);
+    launch_store_block(B, c.nloc, cur, c.slot(0), c.fp32, c.split_scale, c.st);
     ++c.launches;
     c.tm.mark(PH_SPMM);
     c.spmm(cur, U);
@@ -707,7 +724,8 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
                 launch_reorth_update_d(p, c.buf.p, c.bstride, c.Cmat.p, cur, prev, c.slot(i - 2), c.st);
                 ++c.launches;
             } else if (c.use_h) {
-                launch_reorth_gram_h(p, h->n, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.tc_scratch.p, m_cap, c.st);
+                launch_reorth_gram_h(p, h->n, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.tc_scratch.p, m_cap,
+                                     c.split_scale != 0.f, c.st);
                 c.launches += 4;
                 if (h->comm.active()) {
                     std::string err;
@@ -717,7 +735,8 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
                 launch_reorth_coeff_h(p, c.Cmat.p, c.tc_scratch.p, m_cap, h->comm.active() ? 1 : 0, c.st);
                 ++c.launches;
                 c.tm.mark(PH_RUPD);
-                launch_reorth_update_h(p, h->n, c.buf.p, c.bstride, cur, prev, c.slot(i - 2), c.tc_scratch.p, m_cap, c.st);
+                launch_reorth_update_h(p, h->n, c.buf.p, c.bstride, cur, prev, c.slot(i - 2), c.tc_scratch.p, m_cap,
+                                       c.split_scale != 0.f, c.st);
                 ++c.launches;
             } else if (c.use_tc) {
                 launch_reorth_gram_tc(p, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.tc_scratch.p, m_cap, c.st);
@@ -762,7 +781,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             c.finish_gram(c.Gloc());
             RowOpArgs a2;
             a2.n = c.nloc; a2.y = cur; a2.x1 = prev; a2.m1 = c.Gloc(); a2.write_y = 1;
-            a2.store = c.slot(i - 1); a2.store_fp32 = c.fp32;
+            a2.store = c.slot(i - 1); a2.store_fp32 = c.fp32; a2.store_split_scale = c.split_scale;
             c.rowop(a2);
         }
         c.tm.mark(PH_SPMM);
@@ -855,7 +874,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         }
         const double tr1 = now_s();
         c.tm.mark(PH_RITZ);
-        launch_ritz(B, c.fp32, c.nloc, mfin, (int)k, kpad, c.buf.p, c.bstride, dS.p, Vdev, c.nloc, opt.v_fp32, c.st);
+        launch_ritz(B, c.fp32, c.nloc, mfin, (int)k, kpad, c.buf.p, c.bstride, dS.p, Vdev, c.nloc, opt.v_fp32, c.split_scale, c.st);
         ++c.launches;
         c.tm.mark(PH_NONE);
         RBL_CUDA(cudaStreamSynchronize(c.st));

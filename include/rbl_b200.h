@@ -59,7 +59,8 @@ typedef struct {
     int32_t host_threads;  /* worker threads for the final host eigensolve (0: hardware)          */
     int32_t v_fp32;        /* 1: V_out is float (reference's FLOAT=Float32 build), else double    */
     int32_t verbose;
-    int32_t reorth_impl;   /* 0: auto; 1: SIMT; 2: tensor-core TF32x3; 3: tensor-core scaled FP16 split */
+    int32_t reorth_impl;   /* 0: auto; 1: SIMT; 2: tensor-core TF32x3; 3: tensor-core scaled FP16 split of an
+                              fp32 buffer; 4: the same with the buffer stored pre-split (auto picks 4)     */
     int32_t reserved[7];
 } rbl_options;
 
