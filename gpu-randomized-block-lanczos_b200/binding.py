@@ -74,7 +74,7 @@ SIGNATURES = {
     "rbl_gram": (C.c_int, [C.c_int64, C.c_int64, _PD, _PD, _PD]),
     "rbl_block_qr": (C.c_int, [C.c_int64, C.c_int64, _PD, _PD, _P32]),
     "rbl_reorth": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, _PD, _PD, C.c_void_p, C.c_int]),
-    "rbl_ritz": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, _PD, C.c_void_p]),
+    "rbl_ritz": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, _PD, C.c_void_p, C.c_int]),
     "rbl_band_eig_topk": (C.c_int, [C.c_int64, C.c_int64, _PD, C.c_int64, _PD, C.c_int64, C.c_double, C.c_int, _PD,
                                     _PD, _PD, _P32]),
     "rbl_checker_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
@@ -260,14 +260,14 @@ def k_reorth(Qbuf, W0, W1, fp32: bool, impl: int = 0):
     return w0, w1, Cm
 
 
-def k_ritz(Qbuf, S, fp32: bool):
+def k_ritz(Qbuf, S, fp32: bool, impl: int = 0):
     dt = np.float32 if fp32 else np.float64
     Qb = np.ascontiguousarray(Qbuf, dtype=dt)
     m, n, b = Qb.shape
     S = np.ascontiguousarray(S, dtype=np.float64)
     k = S.shape[1]
     V = np.zeros((n, k), dtype=dt, order="F")
-    _check(lib().rbl_ritz(n, b, m, k, int(fp32), Qb.ctypes.data_as(C.c_void_p), _pd(S), V.ctypes.data_as(C.c_void_p)))
+    _check(lib().rbl_ritz(n, b, m, k, int(fp32), Qb.ctypes.data_as(C.c_void_p), _pd(S), V.ctypes.data_as(C.c_void_p), impl))
     return V
 
 

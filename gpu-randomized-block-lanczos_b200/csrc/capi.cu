@@ -332,7 +332,7 @@ int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qb
 }
 
 int rbl_ritz(int64_t n, int64_t b, int64_t m, int64_t k, int storage_fp32, const void* qbuf, const double* s,
-             void* v_out) {
+             void* v_out, int impl) {
     return guarded([&] {
         need_device();
         if (!qbuf || !s || !v_out || b < 1 || b > 32 || n < 1 || m < 1 || k < 1) throw Error(RBL_INVALID, "rbl_ritz: bad arguments");
@@ -361,7 +361,20 @@ int rbl_ritz(int64_t n, int64_t b, int64_t m, int64_t k, int storage_fp32, const
         dV.alloc((size_t)n * k * ssz);
         RBL_CUDA(cudaMemcpy(dbuf.p, hb.data(), hb.size(), cudaMemcpyHostToDevice));
         RBL_CUDA(cudaMemcpy(dS.p, hs.data(), hs.size(), cudaMemcpyHostToDevice));
-        launch_ritz(B, storage_fp32, n, m, (int)k, kpad, dbuf.p, n * B, dS.p, dV.p, n, storage_fp32, 0.f, 0);
+        const bool hs = impl != 1 && reorth_h_supported(B, storage_fp32);
+        if (impl == 4 && !hs) throw Error(RBL_INVALID, "rbl_ritz: tensor-core path needs fp32 storage and padded block size 16 or 32");
+        if (hs) {
+            DevBuf<unsigned char> dsplit;
+            DevBuf<unsigned> words;
+            dsplit.alloc(hb.size());
+            words.alloc(ritz_h_scratch_words(B, m, kpad));
+            const float scale = reorth_h_scale(n);
+            launch_encode_split(B, n * m, (const float*)dbuf.p, dsplit.p, scale, 0);
+            launch_ritz_h(B, n, m, (int)k, kpad, dsplit.p, n * B, dS.p, dV.p, n, storage_fp32, scale, words.p, 0);
+            RBL_CUDA(cudaDeviceSynchronize());
+        } else {
+            launch_ritz(B, storage_fp32, n, m, (int)k, kpad, dbuf.p, n * B, dS.p, dV.p, n, storage_fp32, 0.f, 0);
+        }
         RBL_CUDA(cudaDeviceSynchronize());
         RBL_CUDA(cudaMemcpy(v_out, dV.p, (size_t)n * k * ssz, cudaMemcpyDeviceToHost));
         return (int)RBL_OK;

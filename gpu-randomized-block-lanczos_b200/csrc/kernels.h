@@ -122,6 +122,11 @@ void launch_ritz(int B, int fp32, int64_t n, int64_t m, int k, int kpad, const v
                  const void* S, void* V, int64_t ldv, int v_fp32, float split_scale, cudaStream_t st);
 // split_scale != 0: the fp32 buffer holds split16 rows written with that scale
 
+// tensor-core K6 for a split16 buffer (reorth_tc16.cu): B = 16 or 32, S fp32; scratch: ritz_h_scratch_words words
+size_t ritz_h_scratch_words(int B, int64_t m, int kpad);
+void launch_ritz_h(int B, int64_t n, int64_t m, int k, int kpad, const void* buf, int64_t block_stride_elems, const void* S,
+                   void* V, int64_t ldv, int v_fp32, float split_scale, unsigned* scratch, cudaStream_t st);
+
 // ---- layout / conversion helpers -------------------------------------------------------------------
 // column-major n x b (ld) fp64  ->  row-major n x B fp64 (zero padded)
 void launch_colmajor_to_block(int B, int64_t n, int b, const double* src, int64_t ld, double* dst, cudaStream_t st);

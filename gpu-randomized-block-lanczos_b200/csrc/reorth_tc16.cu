@@ -649,4 +649,233 @@ void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* b
     }
 }
 
+// =================================================================================================
+// K6 on the split16 slab: V = Q * S with the same scaled two-term FP16 products.  MMA roles as in the update
+// (M = 16 rows, N = 8 Ritz columns, K = 16 Krylov columns).  Every warp owns 16 rows and NT*8 columns; grid.y
+// walks column groups.  V is an O(1) quantity (unlike the reorth corrections), so accumulation is two-level:
+// every k-step's three products start from a zero accumulator and are added to an fp32 sum with round-to-nearest
+// (the tensor core's own accumulation truncates), and the fp32 sums are flushed into fp64 every JC stored blocks.
+// =================================================================================================
+template <int B, int NT>
+struct RitzH {
+    static constexpr int NW = 8;
+    static constexpr int KS = B / 16;
+    static constexpr int PA = B;
+    static constexpr int NCOL = NT * 8;
+    static constexpr int PC = NCOL + 8;          // == 8 or 24 mod 32: conflict-free B-fragment loads
+    static constexpr int JC = (B == 16) ? 8 : 4;
+    static constexpr int NST = 4;
+    static constexpr int STAGE = 16 * PA;
+    static constexpr int CBUF = JC * (B / 2) * PC;
+    static constexpr int ROWS_CTA = NW * 16;
+    static constexpr int NCP = (16 * (B / 4)) / 32;
+    static constexpr size_t smem_bytes = (size_t)(NW * NST * STAGE + 4 * CBUF) * sizeof(float);
+};
+
+// S (row-major (m*B) x kpad floats) -> column-pair interleaved f16x2 words  Sp[(r/2) * ncols + t] = (S[r][t], S[r+1][t])
+__global__ void split_ritz_coeff_kernel(size_t nwords, int kpad, int ncols, const float* __restrict__ S, float scale,
+                                        unsigned* __restrict__ sh, unsigned* __restrict__ sl) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nwords) return;
+    const size_t pr = e / ncols;
+    const int t = (int)(e % ncols);
+    const float x0 = (t < kpad) ? S[(pr * 2) * kpad + t] : 0.f;
+    const float x1 = (t < kpad) ? S[(pr * 2 + 1) * kpad + t] : 0.f;
+    unsigned hi, lo;
+    split_h2(x0, x1, scale, hi, lo);
+    sh[e] = hi;
+    sl[e] = lo;
+}
+
+template <int B, int NT, typename VT>
+__global__ void __launch_bounds__(RitzH<B, NT>::NW * 32)
+    ritz_h_kernel(int64_t n, int64_t m, const float* __restrict__ buf, int64_t bstride, const unsigned* __restrict__ Sh,
+                  const unsigned* __restrict__ Sl, int ncols, float inv_scale, VT* __restrict__ V, int64_t ldv, int k) {
+    using C = RitzH<B, NT>;
+    constexpr int NW = C::NW, KS = C::KS, PA = C::PA, NCOL = C::NCOL, PC = C::PC, JC = C::JC, NST = C::NST,
+                  STAGE = C::STAGE, CBUF = C::CBUF, NCP = C::NCP, NTHR = NW * 32;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    float* sA = smem + (size_t)warp * NST * STAGE;
+    unsigned* sC = reinterpret_cast<unsigned*>(smem + (size_t)NW * NST * STAGE);  // [2][hi,lo][JC][B/2][PC]
+    const int64_t r0 = (int64_t)blockIdx.x * C::ROWS_CTA + (int64_t)warp * 16;
+    const int col0 = blockIdx.y * NCOL;
+    const int mi = (int)m;
+
+    float acc[NT][4];
+    double dacc[NT][4];
+#pragma unroll
+    for (int x = 0; x < NT; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            acc[x][y] = 0.f;
+            dacc[x][y] = 0.0;
+        }
+
+    const float* src0[NCP];
+    int dst0[NCP];
+    bool row_ok[NCP];
+#pragma unroll
+    for (int u = 0; u < NCP; ++u) {
+        const int q = lane + 32 * u;
+        const int row = q / (B / 4), c4 = q % (B / 4);
+        row_ok[u] = (r0 + row) < n;
+        dst0[u] = row * PA + ((c4 ^ split_swz<B>(row)) << 2);
+        src0[u] = buf + (size_t)(row_ok[u] ? r0 + row : 0) * B + c4 * 4;
+    }
+    auto issue_a = [&](int j) {
+        float* st = sA + (size_t)(j % NST) * STAGE;
+        const size_t adv = (size_t)j * bstride;
+#pragma unroll
+        for (int u = 0; u < NCP; ++u) {
+            const bool ok = row_ok[u] && (j < mi);
+            cp_async16(st + dst0[u], ok ? src0[u] + adv : buf, ok ? 16 : 0);
+        }
+    };
+    auto issue_c = [&](int chunk) {  // JC blocks x B/2 column pairs x NCOL words, hi and lo
+        constexpr int PER = JC * (B / 2) * (NCOL / 4);
+        static_assert((2 * PER) % NTHR == 0, "coefficient chunk copy must tile the CTA");
+        const int j0 = chunk * JC;
+#pragma unroll
+        for (int u = 0; u < (2 * PER) / NTHR; ++u) {
+            const int idx = tid + NTHR * u;
+            const int half = idx / PER, q = idx % PER;
+            unsigned* dst = sC + (size_t)((chunk & 1) * 2 + half) * CBUF;
+            const unsigned* srcb = half ? Sl : Sh;
+            const int rowc = q / (NCOL / 4), c4 = q % (NCOL / 4);
+            const bool ok = (j0 * (B / 2) + rowc) < mi * (B / 2);
+            const size_t off = ((size_t)j0 * (B / 2) + rowc) * ncols + col0 + c4 * 4;
+            cp_async16(dst + rowc * PC + c4 * 4, ok ? srcb + off : srcb, ok ? 16 : 0);
+        }
+    };
+    issue_c(0);
+    issue_a(0);
+    cp_async_commit();
+#pragma unroll
+    for (int s = 1; s < NST - 1; ++s) {
+        issue_a(s);
+        cp_async_commit();
+    }
+    const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < mi; ++j) {
+        cp_async_wait<NST - 2>();
+        if ((j % JC) == 0) {
+            __syncthreads();
+#pragma unroll
+            for (int x = 0; x < NT; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    dacc[x][y] += (double)acc[x][y];
+                    acc[x][y] = 0.f;
+                }
+        } else {
+            __syncwarp();
+        }
+        if ((j % JC) == 0 && (j / JC + 1) * JC < mi) issue_c(j / JC + 1);
+        issue_a(j + NST - 1);
+        cp_async_commit();
+
+        const float* st = sA + (size_t)(j % NST) * STAGE;
+        const int chunk = j / JC;
+        const unsigned* ph = sC + (size_t)((chunk & 1) * 2 + 0) * CBUF + (size_t)(j % JC) * (B / 2) * PC;
+        const unsigned* pl = sC + (size_t)((chunk & 1) * 2 + 1) * CBUF + (size_t)(j % JC) * (B / 2) * PC;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            unsigned ah[4], al[4];
+            {
+                const int row = (lane & 7) + (((lane >> 3) & 1) << 3);
+                const int q = 2 * ks + (lane >> 4);
+                const float* rowp = st + row * PA;
+                ldmatrix_x4(ah, rowp + ((q ^ split_swz<B>(row)) << 2));
+                ldmatrix_x4(al, rowp + (((q + B / 8) ^ split_swz<B>(row)) << 2));
+            }
+#pragma unroll
+            for (int x = 0; x < NT; ++x) {
+                unsigned bh[2], bl[2];
+                const int col = x * 8 + g;
+                bh[0] = ph[(ks * 8 + t) * PC + col];
+                bh[1] = ph[(ks * 8 + t + 4) * PC + col];
+                bl[0] = pl[(ks * 8 + t) * PC + col];
+                bl[1] = pl[(ks * 8 + t + 4) * PC + col];
+                float d[4] = {zero4[0], zero4[1], zero4[2], zero4[3]};
+                mma_f16(d, al, bh);
+                mma_f16(d, ah, bl);
+                mma_f16(d, ah, bh);
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] += d[y];
+            }
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int64_t row = r0 + g + 8 * h;
+        if (row >= n) continue;
+#pragma unroll
+        for (int x = 0; x < NT; ++x) {
+            const int col = col0 + x * 8 + 2 * t;
+            const double v0 = (dacc[x][2 * h] + (double)acc[x][2 * h]) * (double)inv_scale;
+            const double v1 = (dacc[x][2 * h + 1] + (double)acc[x][2 * h + 1]) * (double)inv_scale;
+            if (col < k) V[(size_t)col * ldv + row] = (VT)v0;
+            if (col + 1 < k) V[(size_t)(col + 1) * ldv + row] = (VT)v1;
+        }
+    }
+}
+
+template <int B, int NT, typename VT>
+static void ritz_h_launch_t(int64_t n, int64_t m, int k, const void* buf, int64_t bstride, const unsigned* sh,
+                            const unsigned* sl, int ncols, int groups, float inv_scale, void* V, int64_t ldv,
+                            cudaStream_t st) {
+    using R = RitzH<B, NT>;
+    cudaFuncSetAttribute(ritz_h_kernel<B, NT, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::smem_bytes);
+    dim3 grid((unsigned)((n + R::ROWS_CTA - 1) / R::ROWS_CTA), (unsigned)groups);
+    ritz_h_kernel<B, NT, VT><<<grid, R::NW * 32, R::smem_bytes, st>>>(n, m, (const float*)buf, bstride, sh, sl, ncols, inv_scale,
+                                                                     (VT*)V, ldv, k);
+}
+
+// column groups of at most 64 Ritz columns; NT n-tiles per group from {2, 4, 6, 7, 8}
+static void ritz_h_shape(int kpad, int& groups, int& nt) {
+    const int tiles = kpad / 8;
+    groups = (tiles + 7) / 8;
+    const int need = (tiles + groups - 1) / groups;
+    nt = need <= 2 ? 2 : need <= 4 ? 4 : need <= 6 ? 6 : need <= 7 ? 7 : 8;
+}
+
+size_t ritz_h_scratch_words(int B, int64_t m, int kpad) {
+    int groups, nt;
+    ritz_h_shape(kpad, groups, nt);
+    return 2 * (size_t)m * (B / 2) * (size_t)(groups * nt * 8);
+}
+
+void launch_ritz_h(int B, int64_t n, int64_t m, int k, int kpad, const void* buf, int64_t bstride, const void* Smat,
+                   void* V, int64_t ldv, int v_fp32, float split_scale, unsigned* scratch, cudaStream_t st) {
+    int groups, nt;
+    ritz_h_shape(kpad, groups, nt);
+    const int ncols = groups * nt * 8;
+    const size_t nwords = (size_t)m * (B / 2) * ncols;
+    unsigned* sh = scratch;
+    unsigned* sl = scratch + nwords;
+    const float scale_s = 2048.f;  // |S| <= 1 (unit eigenvectors of T)
+    split_ritz_coeff_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(nwords, kpad, ncols, (const float*)Smat, scale_s, sh, sl);
+    const float inv = 1.0f / (split_scale * scale_s);
+    auto go = [&](auto bc, auto ntc) {
+        constexpr int BB = decltype(bc)::value;
+        constexpr int NN = decltype(ntc)::value;
+        if (v_fp32) ritz_h_launch_t<BB, NN, float>(n, m, k, buf, bstride, sh, sl, ncols, groups, inv, V, ldv, st);
+        else ritz_h_launch_t<BB, NN, double>(n, m, k, buf, bstride, sh, sl, ncols, groups, inv, V, ldv, st);
+    };
+    auto by_nt = [&](auto bc) {
+        switch (nt) {
+            case 2: go(bc, std::integral_constant<int, 2>()); break;
+            case 4: go(bc, std::integral_constant<int, 4>()); break;
+            case 6: go(bc, std::integral_constant<int, 6>()); break;
+            case 7: go(bc, std::integral_constant<int, 7>()); break;
+            default: go(bc, std::integral_constant<int, 8>()); break;
+        }
+    };
+    if (B == 16) by_nt(std::integral_constant<int, 16>());
+    else by_nt(std::integral_constant<int, 32>());
+}
+
 }  // namespace rbl

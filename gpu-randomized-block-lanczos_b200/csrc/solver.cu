@@ -874,7 +874,15 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         }
         const double tr1 = now_s();
         c.tm.mark(PH_RITZ);
-        launch_ritz(B, c.fp32, c.nloc, mfin, (int)k, kpad, c.buf.p, c.bstride, dS.p, Vdev, c.nloc, opt.v_fp32, c.split_scale, c.st);
+        DevBuf<unsigned> ritz_words;
+        if (c.split_scale != 0.f) {
+            ritz_words.alloc(ritz_h_scratch_words(B, mfin, kpad));
+            launch_ritz_h(B, c.nloc, mfin, (int)k, kpad, c.buf.p, c.bstride, dS.p, Vdev, c.nloc, opt.v_fp32, c.split_scale,
+                          ritz_words.p, c.st);
+            ++c.launches;
+        } else {
+            launch_ritz(B, c.fp32, c.nloc, mfin, (int)k, kpad, c.buf.p, c.bstride, dS.p, Vdev, c.nloc, opt.v_fp32, 0.f, c.st);
+        }
         ++c.launches;
         c.tm.mark(PH_NONE);
         RBL_CUDA(cudaStreamSynchronize(c.st));

@@ -181,9 +181,11 @@ int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qb
                void* c_out, int impl);
 
 /* K6: V = Qbuf * S - replaces recover_eigvec (RBL_gpu.jl:106-132).  s: (m*b) x k row-major fp64,
- * v_out: n x k column-major (double, or float when storage_fp32). */
+ * v_out: n x k column-major (double, or float when storage_fp32).
+ *   impl   0 auto, 1 SIMT, 4 tensor-core scaled FP16 split on the pre-split buffer format (fp32 storage, padded
+ *          block size 16 or 32; what the solver uses in mixed precision; auto picks it when available) */
 int rbl_ritz(int64_t n, int64_t b, int64_t m, int64_t k, int storage_fp32, const void* qbuf, const double* s,
-             void* v_out);
+             void* v_out, int impl);
 
 /* Host side of the path (no device needed) ---------------------------------------------------- */
 

@@ -146,10 +146,22 @@ def _reorth_case(gpu, n, b, m, fp32, impl):
 @pytest.mark.parametrize("n,b,m,k,fp32", [(3000, 16, 6, 100, True), (3000, 16, 6, 100, False), (5001, 4, 50, 10, True),
                                            (2000, 32, 5, 50, False), (1000, 8, 9, 64, True), (700, 5, 4, 7, False)])
 def test_ritz(gpu, n, b, m, k, fp32):
+    _ritz_case(gpu, n, b, m, k, fp32, 0)
+
+
+@pytest.mark.parametrize("impl", [1, 4])
+@pytest.mark.parametrize("n,b,m,k", [(3000, 16, 6, 100), (5003, 16, 41, 37), (2000, 32, 9, 64), (777, 13, 5, 3), (4100, 27, 20, 130),
+                                     (300, 16, 1, 16)])
+def test_ritz_simt_and_tensor_core_paths(gpu, impl, n, b, m, k):
+    """K6 on an fp32 buffer: SIMT kernel (1) and the FP16-split tensor-core kernel on the pre-split format (4)."""
+    _ritz_case(gpu, n, b, m, k, True, impl)
+
+
+def _ritz_case(gpu, n, b, m, k, fp32, impl):
     rng = np.random.default_rng(k)
     blocks = rng.standard_normal((m, n, b))
     S = rng.standard_normal((m * b, k))
-    V = gpu.k_ritz(blocks, S, fp32)
+    V = gpu.k_ritz(blocks, S, fp32, impl=impl)
     dt = np.float32 if fp32 else np.float64
     ref = blocks.astype(dt).astype(np.float64).transpose(1, 0, 2).reshape(n, m * b) @ S.astype(dt).astype(np.float64)
     tol = (2e-5 if fp32 else 1e-12) * np.max(np.abs(ref))
