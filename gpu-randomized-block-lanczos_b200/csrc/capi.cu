@@ -361,9 +361,9 @@ int rbl_ritz(int64_t n, int64_t b, int64_t m, int64_t k, int storage_fp32, const
         dV.alloc((size_t)n * k * ssz);
         RBL_CUDA(cudaMemcpy(dbuf.p, hb.data(), hb.size(), cudaMemcpyHostToDevice));
         RBL_CUDA(cudaMemcpy(dS.p, hs.data(), hs.size(), cudaMemcpyHostToDevice));
-        const bool hs = impl != 1 && reorth_h_supported(B, storage_fp32);
-        if (impl == 4 && !hs) throw Error(RBL_INVALID, "rbl_ritz: tensor-core path needs fp32 storage and padded block size 16 or 32");
-        if (hs) {
+        const bool use_tc = impl != 1 && reorth_h_supported(B, storage_fp32);
+        if (impl == 4 && !use_tc) throw Error(RBL_INVALID, "rbl_ritz: tensor-core path needs fp32 storage and padded block size 16 or 32");
+        if (use_tc) {
             DevBuf<unsigned char> dsplit;
             DevBuf<unsigned> words;
             dsplit.alloc(hb.size());
