@@ -116,10 +116,11 @@ struct RowOpCfg {
     static constexpr int NC = B / TT;
     static constexpr int NS = TR / (NC * NC);
     static constexpr size_t smem_bytes = (size_t)(3 * TR * P + 2 * B * B) * sizeof(double);
+    static constexpr int CTAS_PER_SM = (B == 32) ? 3 : 4;   // B <= 16: 56 KB and <= 128 registers per thread
 };
 
 template <int B>
-__global__ void __launch_bounds__(RowOpCfg<B>::TR) rowop_kernel(RowOpArgs a) {
+__global__ void __launch_bounds__(RowOpCfg<B>::TR, RowOpCfg<B>::CTAS_PER_SM) rowop_kernel(RowOpArgs a) {
     using C = RowOpCfg<B>;
     constexpr int TR = C::TR, P = C::P, TT = C::TT, NC = C::NC, NS = C::NS;
     if (a.skip_flag != nullptr && *a.skip_flag == 0) return;
@@ -155,30 +156,40 @@ __global__ void __launch_bounds__(RowOpCfg<B>::TR) rowop_kernel(RowOpArgs a) {
         const int nvec = rows * (B / 2);
         __syncthreads();  // previous tile fully consumed (also orders the sM1/sRi fill)
         {
+            // full tiles: constant trip count, the VPT 16-byte loads of an array are issued before the first
+            // shared-memory store - bytes in flight, not a loop-carried load->store dependency, set the bandwidth
+            constexpr int VPT = B / 2;  // 16-byte vectors per thread and array
             const double2* gy = reinterpret_cast<const double2*>(a.y + (size_t)r0 * B);
-            for (int idx = tid; idx < nvec; idx += TR) {
-                const double2 v = gy[idx];
+            const double2* gx = reinterpret_cast<const double2*>(a.x1 + (size_t)r0 * B);
+            const double2* gz = reinterpret_cast<const double2*>(a.gram_z + (size_t)r0 * B);
+            auto put = [&](double* dst, int idx, const double2& v) {
                 const int r = idx / (B / 2), c = (idx % (B / 2)) * 2;
-                sY[r * P + c] = v.x;
-                sY[r * P + c + 1] = v.y;
-            }
-            if (a.x1 != nullptr) {
-                const double2* gx = reinterpret_cast<const double2*>(a.x1 + (size_t)r0 * B);
-                for (int idx = tid; idx < nvec; idx += TR) {
-                    const double2 v = __ldg(gx + idx);
-                    const int r = idx / (B / 2), c = (idx % (B / 2)) * 2;
-                    sX[r * P + c] = v.x;
-                    sX[r * P + c + 1] = v.y;
+                dst[r * P + c] = v.x;
+                dst[r * P + c + 1] = v.y;
+            };
+            if (rows == TR) {
+                auto stage = [&](double* dst, const double2* src) {
+                    double2 v[VPT];
+#pragma unroll
+                    for (int u = 0; u < VPT; ++u) v[u] = __ldg(src + tid + u * TR);
+#pragma unroll
+                    for (int u = 0; u < VPT; ++u) put(dst, tid + u * TR, v[u]);
+                };
+                {
+                    double2 v[VPT];
+#pragma unroll
+                    for (int u = 0; u < VPT; ++u) v[u] = gy[tid + u * TR];
+#pragma unroll
+                    for (int u = 0; u < VPT; ++u) put(sY, tid + u * TR, v[u]);
                 }
-            }
-            if (a.gram_z != nullptr) {
-                const double2* gz = reinterpret_cast<const double2*>(a.gram_z + (size_t)r0 * B);
-                for (int idx = tid; idx < nvec; idx += TR) {
-                    const double2 v = __ldg(gz + idx);
-                    const int r = idx / (B / 2), c = (idx % (B / 2)) * 2;
-                    sZ[r * P + c] = v.x;
-                    sZ[r * P + c + 1] = v.y;
-                }
+                if (a.x1 != nullptr) stage(sX, gx);
+                if (a.gram_z != nullptr) stage(sZ, gz);
+            } else {
+                for (int idx = tid; idx < nvec; idx += TR) put(sY, idx, gy[idx]);
+                if (a.x1 != nullptr)
+                    for (int idx = tid; idx < nvec; idx += TR) put(sX, idx, __ldg(gx + idx));
+                if (a.gram_z != nullptr)
+                    for (int idx = tid; idx < nvec; idx += TR) put(sZ, idx, __ldg(gz + idx));
             }
         }
         __syncthreads();
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(RowOpCfg<B>::TR) rowop_kernel(RowOpArgs a) {
 int rowop_grid(int B, int64_t n) {
     int TR = (B == 32) ? 64 : 128;
     int64_t ntiles = (n + TR - 1) / TR;
-    int64_t cap = (int64_t)num_sms() * (B == 32 ? 3 : 3);
+    int64_t cap = (int64_t)num_sms() * (B == 32 ? 3 : 4);
     return (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, cap));
 }
 

@@ -8,4 +8,7 @@ python tools/profile_solve.py --cap 4096 > gpurun_out/plain_cap.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:reorth_gram_h -s 120 -c 1 -o gpurun_out/prof_gram_h -f python tools/profile_solve.py --cap 4096 > gpurun_out/ncu_gram.log 2>&1
 python tools/profile_solve.py --cap 4096 > gpurun_out/plain_cap2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:reorth_update_h -s 120 -c 1 -o gpurun_out/prof_update_h -f python tools/profile_solve.py --cap 4096 > gpurun_out/ncu_update.log 2>&1
-cat gpurun_out/plain_full.log gpurun_out/ncu_full.log
+
+python tools/profile_solve.py --cap 4096 > gpurun_out/plain_cap3.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:ritz_h_kernel -c 1 -o gpurun_out/prof_ritz_h -f python tools/profile_solve.py --cap 4096 > gpurun_out/ncu_ritz.log 2>&1
+cat gpurun_out/plain_full.log; tail -3 gpurun_out/ncu_full.log gpurun_out/ncu_gram.log gpurun_out/ncu_update.log gpurun_out/ncu_ritz.log
