@@ -662,7 +662,7 @@ struct RitzH {
     static constexpr int KS = B / 16;
     static constexpr int PA = B;
     static constexpr int NCOL = NT * 8;
-    static constexpr int PC = NCOL + 8;          // == 8 or 24 mod 32: conflict-free B-fragment loads
+    static constexpr int PC = NCOL + ((NCOL % 16 == 8) ? 16 : 8);  // == 8 or 24 mod 32: conflict-free B-fragment loads
     static constexpr int JC = (B == 16) ? 8 : 4;
     static constexpr int NST = 4;
     static constexpr int STAGE = 16 * PA;

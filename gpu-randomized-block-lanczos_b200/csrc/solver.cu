@@ -874,9 +874,9 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         }
         const double tr1 = now_s();
         c.tm.mark(PH_RITZ);
-        DevBuf<unsigned> ritz_words;
+        DevBuf<unsigned>& ritz_words = h->ws_ref().ritz_words;
         if (c.split_scale != 0.f) {
-            ritz_words.alloc(ritz_h_scratch_words(B, mfin, kpad));
+            ritz_words.ensure(ritz_h_scratch_words(B, mfin, kpad));
             launch_ritz_h(B, c.nloc, mfin, (int)k, kpad, c.buf.p, c.bstride, dS.p, Vdev, c.nloc, opt.v_fp32, c.split_scale,
                           ritz_words.p, c.st);
             ++c.launches;

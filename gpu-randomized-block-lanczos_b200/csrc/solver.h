@@ -92,6 +92,7 @@ struct Workspace {
     DevBuf<float> tc_scratch;
     DevBuf<double> sendbuf;
     DevBuf<unsigned char> ritzS, ritzV;   // Ritz coefficient matrix and (host-output solves) the device copy of V
+    DevBuf<unsigned> ritz_words;          // f16 hi/lo words of S for the tensor-core Ritz kernel
     DevBuf<double> omega;
     PinnedBuf<double> hA, hB;
     PinnedBuf<QrState> hqr;

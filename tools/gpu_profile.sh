@@ -11,4 +11,4 @@ ncu --set full --clock-control none --import-source on -k regex:reorth_update_h 
 
 python tools/profile_solve.py --cap 4096 > gpurun_out/plain_cap3.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:ritz_h_kernel -c 1 -o gpurun_out/prof_ritz_h -f python tools/profile_solve.py --cap 4096 > gpurun_out/ncu_ritz.log 2>&1
-cat gpurun_out/plain_full.log; tail -3 gpurun_out/ncu_full.log gpurun_out/ncu_gram.log gpurun_out/ncu_update.log gpurun_out/ncu_ritz.log
+cat gpurun_out/plain_full.log; for f in ncu_full ncu_gram ncu_update ncu_ritz; do tail -n 3 gpurun_out/$f.log; done
