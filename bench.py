@@ -66,6 +66,7 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.first = 0
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -83,13 +84,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Start of the timed region: only samples taken after this call are reported."""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -258,11 +263,18 @@ def main():
     om_dev = torch.from_numpy(np.ascontiguousarray(Om_loc.T)).to(dev)          # (b, nloc) row-major == nloc x b column-major
     v_dev = torch.empty((K_WANTED, nloc), dtype=torch.float64, device=dev)    # nloc x k column-major
     stats = None
-    for _ in range(args.warmup):
-        D, stats = solver.solve_device(K_WANTED, BLOCK, om_dev.data_ptr(), v_dev.data_ptr())
+    # the nvidia-smi poller is started before the last warm-up solve: its start-up (NVML initialisation, device
+    # enumeration) was measured to stall the first solve after it by 0.2-0.6 s; it keeps sampling every 200 ms
+    # through the timed region and only those samples are reported.  Rank 0 samples its own GPU.
     sampler = ClockSampler(local_rank)
+    for w in range(args.warmup):
+        if w == args.warmup - 1 and rank == 0:
+            sampler.start()
+        D, stats = solver.solve_device(K_WANTED, BLOCK, om_dev.data_ptr(), v_dev.data_ptr())
+    if args.warmup == 0 and rank == 0:
+        sampler.start()
     barrier()
-    sampler.start()
+    sampler.mark()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -648,11 +648,12 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     // flow and use the same Ritz basis.
     const bool is_root = (h->rank == 0);
     const bool multi = h->comm.active();
-    DevBuf<double> d_ctrl;
-    PinnedBuf<double> h_ctrl;
+    // kept in the workspace: with peer access enabled by NCCL every cudaMalloc / cudaFree / cudaFreeHost is expensive
+    DevBuf<double>& d_ctrl = h->ws_ref().ctrl;
+    PinnedBuf<double>& h_ctrl = h->ws_ref().h_ctrl;
     if (multi) {
-        d_ctrl.alloc(2);
-        h_ctrl.alloc(2);
+        d_ctrl.ensure(2);
+        h_ctrl.ensure(2);
     }
     auto agree_flag = [&](bool local) -> bool {
         if (!multi) return local;
@@ -671,8 +672,8 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             std::copy(r.d.begin(), r.d.begin() + k, hbuf.begin());
             std::copy(r.s.begin(), r.s.begin() + (size_t)Nrows * k, hbuf.begin() + k);
         }
-        DevBuf<double> dbuf;
-        dbuf.alloc(cnt);
+        DevBuf<double>& dbuf = h->ws_ref().share;
+        dbuf.ensure(cnt);
         RBL_CUDA(cudaMemcpyAsync(dbuf.p, hbuf.data(), cnt * 8, cudaMemcpyHostToDevice, c.st));
         c.allreduce(dbuf.p, cnt);
         RBL_CUDA(cudaMemcpyAsync(hbuf.data(), dbuf.p, cnt * 8, cudaMemcpyDeviceToHost, c.st));

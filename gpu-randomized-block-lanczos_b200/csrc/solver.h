@@ -94,6 +94,8 @@ struct Workspace {
     DevBuf<unsigned char> ritzS, ritzV;   // Ritz coefficient matrix and (host-output solves) the device copy of V
     DevBuf<unsigned> ritz_words;          // f16 hi/lo words of S for the tensor-core Ritz kernel
     DevBuf<double> omega;
+    DevBuf<double> ctrl, share;           // row-sharded runs: decision flag and the shared (D, S) of the accepting check
+    PinnedBuf<double> h_ctrl;
     PinnedBuf<double> hA, hB;
     PinnedBuf<QrState> hqr;
 };
