@@ -15,6 +15,7 @@
 #include <condition_variable>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include <cstring>
 #include <future>
@@ -849,6 +850,18 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     for (auto e : step_event)
         if (e) cudaEventDestroy(e);
 
+    if (const char* dump = std::getenv("RBL_DUMP_T")) {
+        // debugging aid: the A_i / B_i blocks of T (what the host checks saw), for tools/replay_dump.py
+        if (is_root && dump[0]) {
+            if (FILE* f = std::fopen(dump, "wb")) {
+                const int64_t hdr[4] = {iterations_run, (int64_t)B, (int64_t)b, final_i};
+                std::fwrite(hdr, sizeof(int64_t), 4, f);
+                std::fwrite(c.hA.p, sizeof(double), (size_t)iterations_run * B * B, f);
+                std::fwrite(c.hB.p, sizeof(double), (size_t)iterations_run * B * B, f);
+                std::fclose(f);
+            }
+        }
+    }
     const double t_final_done = now_s();
     // ---- Ritz vectors V = Qbuf * S                                              RBL_gpu.jl:106-132,219 ----
     const int64_t mfin = final_i;
