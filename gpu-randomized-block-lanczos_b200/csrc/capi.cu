@@ -164,7 +164,7 @@ int rbl_spmm(rbl_handle* h, int64_t b, const double* q, double* u) {
         dq.alloc(qp.size());
         du.alloc(up.size());
         RBL_CUDA(cudaMemcpy(dq.p, qp.data(), qp.size() * 8, cudaMemcpyHostToDevice));
-        launch_spmm(B, n, h->d_rowptr.p, h->d_colidx.p, h->d_vals.p, dq.p, du.p, h->opt.op, h->opt.sigma, h->stream);
+        launch_spmm(B, n, h->wsp->d_rowptr.p, h->wsp->d_colidx.p, h->wsp->d_vals.p, dq.p, du.p, h->opt.op, h->opt.sigma, h->stream);
         RBL_CUDA(cudaStreamSynchronize(h->stream));
         RBL_CUDA(cudaMemcpy(up.data(), du.p, up.size() * 8, cudaMemcpyDeviceToHost));
         for (int64_t r = 0; r < n; ++r)

@@ -73,11 +73,11 @@ void slab_cache_release_all() {
 
 rbl_handle::~rbl_handle() {
     cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
     rbl::workspace_park(device, wsp);
     wsp = nullptr;
-    for (auto e : event_pool) cudaEventDestroy(e);
     comm.destroy();
-    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
 }
 
 namespace rbl {
@@ -123,7 +123,8 @@ rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, co
     h->device = dev;
     RBL_CUDA(cudaSetDevice(dev));
     h->wsp = workspace_take(dev);
-    RBL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (!h->wsp->stream) RBL_CUDA(cudaStreamCreateWithFlags(&h->wsp->stream, cudaStreamNonBlocking));
+    h->stream = h->wsp->stream;
     h->n = n; h->row0 = row0; h->nloc = nloc; h->nnz = nnz; h->rank = rank; h->world = world;
     const double t0 = now_s();
 
@@ -206,16 +207,16 @@ rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, co
             if (lr < 0 || lr >= nloc) throw Error(RBL_INVALID, "halo plan: peer requested a row this rank does not own");
             send_rows[s] = (int)lr;
         }
-        h->d_send_rows.alloc(std::max<int64_t>(1, nsend));
-        if (nsend) RBL_CUDA(cudaMemcpy(h->d_send_rows.p, send_rows.data(), nsend * sizeof(int), cudaMemcpyHostToDevice));
+        h->wsp->d_send_rows.ensure(std::max<int64_t>(1, nsend));
+        if (nsend) RBL_CUDA(cudaMemcpy(h->wsp->d_send_rows.p, send_rows.data(), nsend * sizeof(int), cudaMemcpyHostToDevice));
     }
-    h->d_rowptr.alloc((size_t)nloc + 1);
-    h->d_colidx.alloc(std::max<int64_t>(1, nnz));
-    h->d_vals.alloc(std::max<int64_t>(1, nnz));
-    RBL_CUDA(cudaMemcpy(h->d_rowptr.p, rp.data(), ((size_t)nloc + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    h->wsp->d_rowptr.ensure((size_t)nloc + 1);
+    h->wsp->d_colidx.ensure(std::max<int64_t>(1, nnz));
+    h->wsp->d_vals.ensure(std::max<int64_t>(1, nnz));
+    RBL_CUDA(cudaMemcpy(h->wsp->d_rowptr.p, rp.data(), ((size_t)nloc + 1) * sizeof(int), cudaMemcpyHostToDevice));
     if (nnz) {
-        RBL_CUDA(cudaMemcpy(h->d_colidx.p, ci.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice));
-        RBL_CUDA(cudaMemcpy(h->d_vals.p, vals, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice));
+        RBL_CUDA(cudaMemcpy(h->wsp->d_colidx.p, ci.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice));
+        RBL_CUDA(cudaMemcpy(h->wsp->d_vals.p, vals, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice));
     }
     h->t_h2d_create = now_s() - t0;
     return h.release();
@@ -234,12 +235,12 @@ struct PhaseTimer {
     bool enabled = true;
     void mark(int phase) {
         if (!enabled) return;
-        if (used == h->event_pool.size()) {
+        if (used == h->wsp->event_pool.size()) {
             cudaEvent_t e;
             RBL_CUDA(cudaEventCreate(&e));
-            h->event_pool.push_back(e);
+            h->wsp->event_pool.push_back(e);
         }
-        RBL_CUDA(cudaEventRecord(h->event_pool[used], st));
+        RBL_CUDA(cudaEventRecord(h->wsp->event_pool[used], st));
         marks.emplace_back(phase, (int)used);
         ++used;
     }
@@ -248,7 +249,7 @@ struct PhaseTimer {
         for (size_t i = 0; i + 1 < marks.size(); ++i) {
             if (marks[i].first == PH_NONE) continue;
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, h->event_pool[marks[i].second], h->event_pool[marks[i + 1].second]) == cudaSuccess)
+            if (cudaEventElapsedTime(&ms, h->wsp->event_pool[marks[i].second], h->wsp->event_pool[marks[i + 1].second]) == cudaSuccess)
                 sec[marks[i].first] += ms * 1e-3;
         }
     }
@@ -313,7 +314,7 @@ struct Ctx {
         if (!h->comm.active()) return;
         std::string err;
         const int64_t nsend = h->send_ptr[h->world];
-        launch_gather_rows(B, nsend, h->d_send_rows.p, Xblk, sendbuf.p, st);
+        launch_gather_rows(B, nsend, h->wsp->d_send_rows.p, Xblk, sendbuf.p, st);
         ++launches;
         nccl(h->comm.group_start(err), err);
         for (int p = 0; p < h->world; ++p) {
@@ -327,7 +328,7 @@ struct Ctx {
     }
     void spmm(double* Q, double* U) {
         halo(Q);
-        launch_spmm(B, nloc, h->d_rowptr.p, h->d_colidx.p, h->d_vals.p, Q, U, h->opt.op, h->opt.sigma, st);
+        launch_spmm(B, nloc, h->wsp->d_rowptr.p, h->wsp->d_colidx.p, h->wsp->d_vals.p, Q, U, h->opt.op, h->opt.sigma, st);
         ++launches;
         ++n_spmm;
         bytes_spmm += 12.0 * (double)h->nnz + 4.0 * (double)(nloc + 1) + 16.0 * (double)nloc * B;

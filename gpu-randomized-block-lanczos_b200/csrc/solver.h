@@ -98,6 +98,16 @@ struct Workspace {
     PinnedBuf<double> h_ctrl;
     PinnedBuf<double> hA, hB;
     PinnedBuf<QrState> hqr;
+    // what a handle needs besides the solve buffers: parked with the workspace so that a create / destroy cycle does
+    // no cudaFree / cudaStreamDestroy / cudaEventDestroy (measured: sporadic 0.4-1.8 s stalls in rbl_destroy)
+    DevBuf<int> d_rowptr, d_colidx, d_send_rows;
+    DevBuf<double> d_vals;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> event_pool;
+    ~Workspace() {
+        for (auto e : event_pool) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
 };
 // process-wide cache of whole workspaces (one per device): a destroyed handle parks its workspace, the next
 // handle on that device adopts it
@@ -117,15 +127,12 @@ struct rbl_handle {
     int64_t nnz = 0;    // local nonzeros
     int64_t n_halo = 0;
     int rank = 0, world = 1;
-    rbl::DevBuf<int> d_rowptr, d_colidx;
-    rbl::DevBuf<double> d_vals;
+    // CSR arrays, send lists, stream and timing events live in the workspace (wsp->d_rowptr, ...)
     // halo exchange plan
     std::vector<int64_t> halo_owner_ptr;  // world+1: halo rows received from each owner
     std::vector<int64_t> send_ptr;        // world+1: rows sent to each peer
-    rbl::DevBuf<int> d_send_rows;         // local row indices, grouped by peer
     rbl::Comm comm;
-    cudaStream_t stream = nullptr;
-    std::vector<cudaEvent_t> event_pool;
+    cudaStream_t stream = nullptr;        // == wsp->stream
     double t_h2d_create = 0.0;
     ~rbl_handle();
 };

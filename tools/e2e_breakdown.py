@@ -19,7 +19,7 @@ om_pin = torch.from_numpy(np.asfortranarray(Om).T.copy()).pin_memory()
 v_pin = torch.empty((bench.K_WANTED, n), dtype=torch.float64).pin_memory()
 opts = dict(max_kryl_sz=bench.MAX_KRYL, precision=B.PRECISION_MIXED, op=B.OP_SHIFT_MINUS_A, sigma=bench.SIGMA, device=0,
             async_check=1, verbose=int(os.environ.get("RBL_VERBOSE", "0")))
-for it in range(4):
+for it in range(int(os.environ.get("CALLS", "4"))):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     s = B.Solver(L, options=B.default_options(**opts))
