@@ -354,9 +354,21 @@ def main():
     d_t, d_b, d_n = (g_t, g_b, g_n) if dom == "reorth_gram" else (u_t, u_b, u_n)
     achieved = d_b / d_t / 1e9 if d_t > 0 else 0.0
     peak = float(peaks["hbm_gbs"])
+    # DRAM bytes of the dominant kernel from the committed ncu --set full capture: the captured launch's
+    # (read + write) / algorithmic ratio applied to this run's average launch
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        cap = tj[dom]
+        ratio = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["algorithmic_bytes"]
+        traffic = ratio * d_b / d_n
+        traffic_src = f"ncu capture of one launch (m={cap['m']}): DRAM read+write = {ratio:.4f} x algorithmic bytes, scaled to the average launch"
+    except Exception:
+        pass
     roof = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "peak_source": peak_src, "traffic": None,
+        "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
         "avg_launch_ms": d_t / d_n * 1e3, "algorithmic_bytes_per_launch": d_b / d_n, "launches": int(d_n),
         "share_of_step": d_t / (sec_per_solve * steps),
         "others": {
