@@ -431,7 +431,7 @@ void extract_cluster(const BandSym& T, Work& wk, double mu, int m, const std::ve
 
 // Orthonormal eigenvector bases for (nearly) degenerate eigenvalues: vectors of eigenvalues closer than a few
 // ctol are orthonormalised and rotated to Ritz vectors (a duplicate is regenerated inside the cluster), and
-// independently converged vectors of eigenvalues closer than 1e-5 ||T|| get their eps/gap cross-components
+// independently converged vectors of eigenvalues closer than 1e-3 ||T|| get their eps/gap cross-components
 // removed (like LAPACK dstein's ortol).  *dup is set when a vector of the loose pass vanishes (two inputs were
 // the same eigenvector).
 void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, bool* dup) {
@@ -492,8 +492,9 @@ void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, boo
         g0 = g1;
     }
     // loose pass (like LAPACK dstein's ortol): independently converged vectors of eigenvalues closer than
-    // 1e-5 ||T|| carry an eps/gap component of each other; remove it by Gram-Schmidt in eigenvalue order
-    const double otol = 1e-5 * tn;
+    // 1e-3 ||T|| carry a residual/gap component of each other (refined seeds are accepted at residuals up to
+    // 1e-12 ||T||); remove it by Gram-Schmidt in eigenvalue order
+    const double otol = 1e-3 * tn;
     for (size_t j = 1; j < out.size(); ++j) {
         bool touched = false;
         for (size_t i = j; i-- > 0;) {
@@ -556,9 +557,20 @@ struct Interval {
 
 // All eigenpairs with eigenvalue in (lo,hi): recursive bisection on Sturm counts until an interval
 // holds one eigenvalue (finished by inverse iteration + RQI) or a tight cluster.
-void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, std::vector<Pair>& out, int64_t& nfac) {
+// `known` (optional): eigenpairs of T that are already available (refined seeds).  An interval whose Sturm count equals
+// the number of known eigenvalues strictly inside it is complete - its pairs are taken from `known` and the
+// bisection below it is skipped, so the factorisations go only where eigenvalues are actually missing.
+void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, std::vector<Pair>& out, int64_t& nfac,
+           const std::vector<Pair>* known = nullptr, int64_t* reused = nullptr) {
     const double tn = std::max(T.norm_inf, 1e-300);
     const double ctol = 2e-11 * tn;
+    std::vector<std::pair<double, size_t>> kn;  // (theta, index into *known), ascending
+    if (known) {
+        for (size_t i = 0; i < known->size(); ++i) kn.push_back({(*known)[i].theta, i});
+        std::sort(kn.begin(), kn.end());
+    }
+    const double kmargin = 1e-9 * tn;
+    std::atomic<int64_t> n_reused{0};
     std::mutex mu;
     std::condition_variable cv;
     std::deque<Interval> queue;
@@ -586,7 +598,22 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
             std::vector<Interval> push;
             const int64_t m = iv.chi - iv.clo;
             const double mid = 0.5 * (iv.lo + iv.hi);
-            if (m >= 2 && (iv.hi - iv.lo) <= ctol) {
+            bool complete = false;
+            if (!kn.empty() && iv.hi - iv.lo > 2 * kmargin) {
+                auto lo_it = std::upper_bound(kn.begin(), kn.end(), std::make_pair(iv.lo + kmargin, (size_t)-1));
+                auto hi_it = std::lower_bound(kn.begin(), kn.end(), std::make_pair(iv.hi - kmargin, (size_t)0));
+                // nothing known may sit in the margins (it could belong to either side of the count)
+                auto lo_edge = std::lower_bound(kn.begin(), kn.end(), std::make_pair(iv.lo - kmargin, (size_t)0));
+                auto hi_edge = std::upper_bound(kn.begin(), kn.end(), std::make_pair(iv.hi + kmargin, (size_t)-1));
+                if (hi_it >= lo_it && (int64_t)(hi_it - lo_it) == m && lo_edge == lo_it && hi_edge == hi_it) {
+                    for (auto it = lo_it; it != hi_it; ++it) local.push_back((*known)[it->second]);
+                    n_reused += m;
+                    complete = true;
+                }
+            }
+            if (complete) {
+                // nothing to do below this interval
+            } else if (m >= 2 && (iv.hi - iv.lo) <= ctol) {
                 std::lock_guard<std::mutex> lk(mu);
                 clusters.push_back(iv);
             } else {
@@ -713,6 +740,7 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
         fac += nf2;
     }
     nfac += fac.load();
+    if (reused) *reused = n_reused.load();
 }
 
 // residual bound ||B_i s[N-b..N)||, B_i row-major upper triangular b x b
@@ -743,6 +771,15 @@ void BandTopK::set_seeds(const std::vector<double>& d, const std::vector<double>
 }
 
 // All k seed pairs refined for the current T by inverse iteration (zero-padded start vectors), in parallel.
+static double seed_min_frac() {
+    static const double f = [] {
+        const char* e = std::getenv("RBL_SEED_MIN_FRAC");
+        const double v = e ? std::atof(e) : 0.0;
+        return (v > 0.0 && v <= 1.0) ? v : 0.70;
+    }();
+    return f;
+}
+
 bool BandTopK::refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pairs, int64_t& nfac) {
     const int64_t N = T.N;
     const double tn = std::max(T.norm_inf, 1e-300);
@@ -1051,9 +1088,10 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     ++full_checks;
     stage_now = 2;
     std::vector<Pair> pairs;
+    std::vector<Pair> known_pairs;
     bool from_seeds = false;
     if ((int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N &&
-        (int64_t)seeds_[0].v.size() * 20 >= N * 17) {  // seeds of a T at least 85% as large (staler ones rarely survive)
+        (double)seeds_[0].v.size() >= seed_min_frac() * (double)N) {  // staler seeds rarely survive the refinement
         // Fast path: the k pairs of an earlier full solve are refined in parallel (seeds that do not converge or that
         // collapse onto the same eigenvector are dropped).  Sturm counts then say exactly how many eigenvalues are
         // missing and where - above the smallest value found (Ritz values that entered the wanted set), inside its
@@ -1223,7 +1261,14 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
             }
         }
         from_seeds = good;
-        if (!from_seeds) pairs.clear();
+        if (!from_seeds) {
+            // the refined seeds are still eigenpairs of T: the slicing below only has to find what is missing
+            known_pairs.clear();
+            if (refined)  // (deduplicated by refine_seeds)
+                for (auto& p : pairs)
+                    if ((int64_t)p.v.size() == N && p.res <= 1.01e-11 * tn) known_pairs.push_back(std::move(p));
+            pairs.clear();
+        }
         if (verbose > 0)
             std::fprintf(stderr, "[rbl] full check N=%lld from seeds (N_seed=%lld): %s%s%s, %lld repaired\n", (long long)N,
                          (long long)nseed, from_seeds ? "ok" : "rejected", from_seeds ? "" : ": ", why, (long long)n_extra);
@@ -1250,9 +1295,12 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         }
     }
     if (!from_seeds) {
-        int64_t nf = 0;
-        slice(T, roots, threads, pairs, nf);
+        int64_t nf = 0, reused = 0;
+        slice(T, roots, threads, pairs, nf, known_pairs.empty() ? nullptr : &known_pairs, &reused);
         wk.nfac += (int)nf;
+        if (verbose > 0 && !known_pairs.empty())
+            std::fprintf(stderr, "[rbl] full check N=%lld: slicing reused %lld of %lld refined seeds (%lld factorisations)\n",
+                         (long long)N, (long long)reused, (long long)known_pairs.size(), (long long)nf);
     }
     // sort_eig_abs: k largest |lambda|, returned by descending |lambda|
     std::stable_sort(pairs.begin(), pairs.end(),

@@ -232,3 +232,32 @@ def test_stale_seeds_are_refined_repaired_or_rejected(rbl, grid, k, b):
         assert np.max(np.abs(r["D"] - Dr[::-1])) < 1e-11 * 12
         S = r["S"]
         assert np.max(np.abs(S.T @ S - np.eye(k))) < 1e-8
+
+
+def test_rejected_seeds_assist_the_slicing(rbl):
+    """In the middle of a run many Ritz values enter the wanted set between two full solves: the refined seeds fail the
+    count validation, but they are still eigenpairs of T and the slicing only has to find what is missing.  The result
+    must be dsbev's at every stage (eigenvalues, orthonormal vectors, small residuals)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from tools.replay_checks import capture
+    grid, k, b = 20, 60, 16
+    A = matrices.shifted(matrices.laplacian_3d(grid), 12.0)
+    Om = np.random.default_rng(0).standard_normal((grid ** 3, b))
+    Ts, Bs, oks = capture(A, k, b, Om)
+    ck = rbl.Checker(threads=2)
+    L = len(Ts)
+    picks = sorted({max(1, int(f * L)) for f in (0.3, 0.4, 0.5, 0.62, 0.75, 0.9)} | {L - 1})
+    for i in picks:
+        T = Ts[i]
+        if T.shape[1] < 2 * k:
+            continue
+        r = ck.check(T, k, Bs[i], force_full=True)
+        assert r["have_all"]
+        w, z = rbl_oracle.dsbev(T)
+        Dr, _ = rbl_oracle.sort_eig_abs(w, z, k)
+        assert np.max(np.abs(r["D"] - Dr[::-1])) < 1e-11 * 12, i
+        S = r["S"]
+        assert np.max(np.abs(S.T @ S - np.eye(k))) < 1e-8, i
+        M = rbl_oracle.dense_band_from_T(T)
+        assert np.max(np.linalg.norm(M @ S - S * r["D"][None, :], axis=0)) < 1e-10 * 12, i
