@@ -516,40 +516,6 @@ void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, boo
     nfac += wk2.nfac;
 }
 
-// One eigenpair with eigenvalue in (lo,hi) that is NOT in span(against): Rayleigh-quotient iteration started at the
-// middle of the interval, with the given (accurate) eigenvectors projected out of every iterate.
-bool deflated_rqi(const BandSym& T, Work& wk, double lo, double hi, const std::vector<const std::vector<double>*>& against,
-                  Pair& out) {
-    const int64_t N = T.N;
-    const double tn = std::max(T.norm_inf, 1e-300);
-    std::vector<std::vector<double>> X(1);
-    wk.random_unit(X[0], N);
-    mgs(X, 0, against, N);
-    double mu = 0.5 * (lo + hi);
-    double th = mu, rs = 1e300;
-    for (int round = 0; round < 10; ++round) {
-        wk.lu.factor(T, mu);
-        ++wk.nfac;
-        for (int it = 0; it < 2; ++it) {
-            wk.lu.solve(X[0].data());
-            const double nn = nrm2(X[0].data(), N);
-            if (!(nn > 0) || !std::isfinite(nn)) { wk.random_unit(X[0], N); }
-            else scal(X[0].data(), 1.0 / nn, N);
-            mgs(X, 0, against, N);
-        }
-        rayleigh(T, X[0], wk.t, th, rs);
-        if (getenv("RBL_DEBUG_RQI")) std::fprintf(stderr, "    drqi round %d mu=%.15g th=%.15g rs=%.2e (lo=%.15g hi=%.15g, against %zu)\n", round, mu, th, rs, lo, hi, against.size());
-        if (rs <= 2e-13 * tn) break;
-        // stay inside the interval: a Ritz value outside means the iterate is still dominated by other directions
-        mu = (th > lo && th < hi) ? th : 0.5 * (lo + hi) + (round + 1) * 0.07 * (hi - lo) * ((round & 1) ? 1.0 : -1.0);
-    }
-    if (!(rs <= 1e-11 * tn) || !(th > lo && th < hi)) return false;
-    out.theta = th;
-    out.res = rs;
-    out.v = X[0];
-    return true;
-}
-
 struct Interval {
     double lo, hi;
     int64_t clo, chi;  // eigenvalues below lo / below hi
@@ -1100,7 +1066,6 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         const int64_t nseed = (int64_t)seeds_[0].v.size();
         const bool refined = refine_seeds(T, k, pairs, nf);
         wk.nfac += (int)nf;
-        int64_t n_extra = 0;
         const char* why = refined ? "" : "too few seeds survived";
         bool good = refined;
         auto by_mag = [](const Pair& a, const Pair& b2) { return std::fabs(a.theta) > std::fabs(b2.theta); };
@@ -1119,7 +1084,6 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
             } else {
                 std::vector<double> f(kf);
                 for (int64_t j = 0; j < kf; ++j) f[j] = pairs[j].theta;
-                std::vector<Pair> extra;
                 auto above = [&](double x) -> int64_t {  // #{lambda > x}
                     if (x > T.gersh_hi) return 0;
                     wk.lu.factor(T, x);
@@ -1132,121 +1096,21 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
                         if (f[i] > x) ++c;
                     return c;
                 };
-                // number of eigenvalues above x that are neither found nor already extracted
-                auto miss = [&](double x) -> int64_t {
-                    int64_t ex = 0;
-                    for (auto& e : extra)
-                        if (e.theta > x) ++ex;
-                    return above(x) - found_above(x) - ex;
-                };
-                auto try_one = [&](double lo, double hi) -> bool {
-                    const double pad = std::max(hi - lo, 1e-6 * tn);
-                    std::vector<const std::vector<double>*> against;
-                    for (int64_t i = 0; i < kf; ++i)
-                        if (f[i] > lo - pad && f[i] < hi + pad) against.push_back(&pairs[i].v);
-                    for (auto& e : extra)
-                        if (e.theta > lo - pad && e.theta < hi + pad) against.push_back(&e.v);
-                    Pair np;
-                    if (!deflated_rqi(T, wk, lo, hi, against, np)) return false;
-                    extra.push_back(std::move(np));
-                    return true;
-                };
-                // `count` eigenpairs inside (lo,hi) that are not among the found/extra ones: bisect on the missing
-                // counts until a deflated iteration started in the interval locks onto the missing eigenvalue
-                std::function<bool(double, double, int64_t, int64_t, int)> fill_rec =
-                    [&](double lo, double hi, int64_t m_lo, int64_t m_hi, int depth) -> bool {
-                    const int64_t c = m_lo - m_hi;  // missing inside (lo,hi)
-                    if (c <= 0) return c == 0;
-                    if (!(hi > lo)) return false;
-                    if (c == 1 && try_one(lo, hi)) return true;
-                    if (hi - lo <= 1e-9 * tn || depth > 40) {  // a cluster of missing values: one after the other
-                        for (int64_t q = 0; q < c; ++q)
-                            if (!try_one(lo, hi)) return false;
-                        return true;
-                    }
-                    const double mid = 0.5 * (lo + hi);
-                    const int64_t m_mid = miss(mid);
-                    if (m_mid > m_lo || m_mid < m_hi) return false;
-                    return fill_rec(mid, hi, m_mid, m_hi, depth + 1) && fill_rec(lo, mid, m_lo, m_mid, depth + 1);
-                };
-                auto fill = [&](double lo, double hi, int64_t count) -> bool {
-                    if (count <= 0) return true;
-                    if (!(hi > lo)) return false;
-                    const int64_t m_hi = miss(hi);
-                    return fill_rec(lo, hi, m_hi + count, m_hi, 0);
-                };
-                const int64_t c_hi = above(tk + delta), c_lo = above(std::max(0.0, tk - delta));
+                // Sturm counts against the refined set: anything missing (Ritz values that entered the wanted set since
+                // the seeds were computed) sends the check to the seed-assisted slicing below, which finds the missing
+                // pairs in parallel and keeps the refined ones
+                const int64_t c_hi = above(tk + delta);
                 const int64_t fa_hi = found_above(tk + delta);
-                const int64_t miss_above = c_hi - fa_hi;                      // entrants above the smallest found value
-                const int64_t miss_clu = (c_lo - c_hi) - (kf - fa_hi);        // missing members of its cluster
-                if (miss_above < 0 || miss_clu < 0 || miss_above > 6) {
+                if (c_hi != fa_hi) {
                     good = false;
-                    why = "counts inconsistent with the refined set";
-                }
-                if (good && miss_above > 0) {
-                    // a_j = #{lambda > f_j + delta} - #{found > f_j + delta} is non-decreasing in j: bisect over j for the
-                    // gaps where it increases
-                    struct Gap { int64_t j; int64_t count; };
-                    std::vector<Gap> gaps;
-                    std::vector<std::array<int64_t, 4>> stack;
-                    const int64_t a0 = above(f[0] + delta) - found_above(f[0] + delta);
-                    if (a0 > 0) gaps.push_back(Gap{-1, a0});
-                    stack.push_back({0, kf - 1, a0, miss_above});
-                    while (!stack.empty() && good) {
-                        auto cur = stack.back();
-                        stack.pop_back();
-                        const int64_t jl = cur[0], jh = cur[1], al = cur[2], ah = cur[3];
-                        if (ah < al) { good = false; why = "non-monotone missing counts"; break; }
-                        if (ah == al) continue;
-                        if (jh - jl <= 1) { gaps.push_back(Gap{jl, ah - al}); continue; }
-                        const int64_t jm = (jl + jh) / 2;
-                        const int64_t am = above(f[jm] + delta) - found_above(f[jm] + delta);
-                        stack.push_back({jl, jm, al, am});
-                        stack.push_back({jm, jh, am, ah});
-                    }
-                    for (size_t gi = 0; gi < gaps.size() && good; ++gi) {
-                        const int64_t j = gaps[gi].j;
-                        const double hi_x = (j < 0) ? g : f[j] - delta;
-                        const double lo_x = (j < 0) ? f[0] + delta : f[j + 1] + delta;
-                        if (!fill(lo_x, hi_x, gaps[gi].count)) { good = false; why = "could not extract an entrant"; }
-                    }
-                }
-                int64_t have = kf + (int64_t)extra.size();
-                if (good && have < k && miss_clu > 0) {  // only as many cluster members as are needed to reach k
-                    const int64_t need = std::min<int64_t>(miss_clu, k - have);
-                    if (!fill(std::max(0.0, tk - 2 * delta), tk + 2 * delta, need)) {
-                        good = false;
-                        why = "could not complete the boundary cluster";
-                    }
-                    have = kf + (int64_t)extra.size();
-                }
-                if (good && have < k) {
-                    // still short: take everything between the smallest found value and the first x with >= k above it
-                    double xl = std::max(0.0, tk - delta), step = std::max(1e-6 * tn, 4 * delta);
-                    int64_t cx = c_lo;
-                    for (int it = 0; it < 60 && cx < k; ++it) {
-                        xl = std::max(0.0, xl - step);
-                        cx = above(xl);
-                        step *= 2.0;
-                        if (xl == 0.0) break;
-                    }
-                    if (cx < k || cx - c_lo > 32) { good = false; why = "too many pairs missing below the refined set"; }
-                    else if (!fill(xl, std::max(0.0, tk - delta), cx - c_lo)) { good = false; why = "could not extract the pairs below the refined set"; }
-                }
-                if (good) {
-                    n_extra = (int64_t)extra.size();
-                    for (auto& e : extra) pairs.push_back(std::move(e));
-                    if (n_extra > 0) {
-                        int64_t nf3 = 0;
-                        bool dup = false;
-                        finalize_pairs(T, pairs, nf3, &dup);
-                        wk.nfac += (int)nf3;
-                        if (dup) { good = false; why = "duplicate after repair"; }
-                    }
+                    why = "eigenvalues missing above the smallest refined one";
+                } else if (kf < k) {
+                    good = false;
+                    why = "fewer than k refined pairs";
                 }
                 if (good) {
                     std::stable_sort(pairs.begin(), pairs.end(), by_mag);
-                    if ((int64_t)pairs.size() < k) { good = false; why = "fewer than k pairs after repair"; }
+                    if ((int64_t)pairs.size() < k) { good = false; why = "fewer than k refined pairs"; }
                 }
                 if (good) {
                     pairs.resize(k);
@@ -1270,8 +1134,8 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
             pairs.clear();
         }
         if (verbose > 0)
-            std::fprintf(stderr, "[rbl] full check N=%lld from seeds (N_seed=%lld): %s%s%s, %lld repaired\n", (long long)N,
-                         (long long)nseed, from_seeds ? "ok" : "rejected", from_seeds ? "" : ": ", why, (long long)n_extra);
+            std::fprintf(stderr, "[rbl] full check N=%lld from seeds (N_seed=%lld): %s%s%s\n", (long long)N,
+                         (long long)nseed, from_seeds ? "ok" : "rejected", from_seeds ? "" : ": ", why);
     }
     // bracket the k-th largest |lambda|: largest x_lo with #{|lambda| > x_lo} >= k (within a modest surplus)
     double x_lo = 0.0, x_hi = g;
