@@ -291,11 +291,8 @@ void launch_rowop(int B, const RowOpArgs& a, int grid, cudaStream_t st) {
     dispatch_B(B, [&](auto bc) {
         constexpr int BB = decltype(bc)::value;
         using C = RowOpCfg<BB>;
-        static bool configured = false;
-        if (!configured) {
-            cudaFuncSetAttribute(rowop_kernel<BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
-            configured = true;
-        }
+        static PerDeviceOnce once;
+        if (once.first()) cudaFuncSetAttribute(rowop_kernel<BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
         rowop_kernel<BB><<<grid, C::TR, C::smem_bytes, st>>>(a);
     });
 }
@@ -781,11 +778,8 @@ static void update_launch_t(const ReorthPlan& p, const void* buf, int64_t bstrid
                             double* w1, void* store_w1, cudaStream_t st) {
     using C = UpdCfg<B, S>;
     const size_t smem = (size_t)C::JC * C::BLK * sizeof(S);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(reorth_update_kernel<B, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(reorth_update_kernel<B, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     unsigned grid = (unsigned)((p.n + C::ROWS_CTA - 1) / C::ROWS_CTA);
     reorth_update_kernel<B, S><<<grid, 256, smem, st>>>(p.n, p.m, (const S*)buf, bstride, (const S*)Cmat, w0, w1,
                                                          (S*)store_w1);

@@ -5,9 +5,24 @@
 // buffer is a slab of `m` such blocks, stored as float (mixed precision) or double.
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <cstdint>
 
 namespace rbl {
+
+// Kernel attributes (cudaFuncSetAttribute) are per device: one of these per call site remembers which devices
+// of the process have been configured.
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool first() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long bit = 1ull << (d & 63);
+        return !(mask.fetch_or(bit) & bit);
+    }
+};
+
 
 inline int padded_block(int b) { return b <= 4 ? 4 : (b <= 8 ? 8 : (b <= 16 ? 16 : 32)); }
 

@@ -321,11 +321,8 @@ void launch_reorth_gram_d(const ReorthPlan& p, const void* buf, int64_t bstride,
                           void* partials, void* Cmat, cudaStream_t st) {
     constexpr int B = 16;
     using G = GramD<B>;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(reorth_gram_d_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(reorth_gram_d_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
     int64_t rpr = (p.n + p.ranges - 1) / p.ranges;
     rpr = (rpr + G::RW - 1) / G::RW * G::RW;
     dim3 grid((unsigned)((p.m + G::JT - 1) / G::JT), p.ranges);
@@ -340,11 +337,8 @@ void launch_reorth_update_d(const ReorthPlan& p, const void* buf, int64_t bstrid
                             double* w1, void* store_w1, cudaStream_t st) {
     constexpr int B = 16;
     using U = UpdD<B>;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(reorth_update_d_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::smem_bytes);
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(reorth_update_d_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::smem_bytes);
     const unsigned grid = (unsigned)((p.n + U::ROWS_CTA - 1) / U::ROWS_CTA);
     reorth_update_d_kernel<B><<<grid, U::NW * 32, U::smem_bytes, st>>>(p.n, p.m, (const double*)buf, bstride,
                                                                        (const double*)Cmat, w0, w1, (double*)store_w1);

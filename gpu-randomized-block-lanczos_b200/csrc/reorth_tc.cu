@@ -380,11 +380,8 @@ void launch_reorth_gram_tc(const ReorthPlan& p, const void* buf, int64_t bstride
     float* wlo = whi + (size_t)p.n * 2 * B;
     float* chi = wlo + (size_t)p.n * 2 * B;
     float* clo = chi + (size_t)m_cap * B * 2 * B;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(reorth_gram_tc_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(reorth_gram_tc_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
     int sms = 148;
     {
         int dev = 0;
@@ -427,11 +424,8 @@ void launch_reorth_update_tc(const ReorthPlan& p, const void* buf, int64_t bstri
     using U = UpdTc<B>;
     float* chi = scratch + 2 * (size_t)p.n * 2 * B;
     float* clo = chi + (size_t)m_cap * B * 2 * B;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(reorth_update_tc_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::smem_bytes);
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(reorth_update_tc_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::smem_bytes);
     const unsigned grid = (unsigned)((p.n + U::ROWS_CTA - 1) / U::ROWS_CTA);
     reorth_update_tc_kernel<B><<<grid, 256, U::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, chi, clo, w0, w1,
                                                                   (float*)store_w1);

@@ -562,11 +562,8 @@ static void gram_h_launch(const ReorthPlan& p, int64_t n_global, const void* buf
                           const double* w1, void* partials, void* Cmat, float* scratch, int64_t m_cap, cudaStream_t st) {
     using G = GramH<B>;
     HScratch s = h_layout(scratch, B, p.n, m_cap);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(reorth_gram_h_kernel<B, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(reorth_gram_h_kernel<B, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes);
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -628,11 +625,8 @@ static void update_h_launch(const ReorthPlan& p, int64_t n_global, const void* b
                             double* w1, void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st) {
     using U = UpdH<B, PS>;
     HScratch s = h_layout(scratch, B, p.n, m_cap);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(reorth_update_h_kernel<B, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::smem_bytes);
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(reorth_update_h_kernel<B, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::smem_bytes);
     const unsigned grid = (unsigned)((p.n + U::ROWS_CTA - 1) / U::ROWS_CTA);
     reorth_update_h_kernel<B, PS><<<grid, U::NW * 32, U::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.ch, s.cl,
                                                                  pick_scale(n_global), s.scale_c, w0, w1, (float*)store_w1);
