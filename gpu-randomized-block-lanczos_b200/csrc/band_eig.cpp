@@ -1053,6 +1053,9 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     // ---- stage 3: all k pairs of largest |lambda| --------------------------------------------------------
     ++full_checks;
     stage_now = 2;
+    auto since_start = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() * 1e3; };
+    const double ms_stage3_begin = since_start();
+    double ms_refined = 0, ms_validated = 0;
     std::vector<Pair> pairs;
     std::vector<Pair> known_pairs;
     bool from_seeds = false;
@@ -1066,6 +1069,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         const int64_t nseed = (int64_t)seeds_[0].v.size();
         const bool refined = refine_seeds(T, k, pairs, nf);
         wk.nfac += (int)nf;
+        ms_refined = since_start();
         const char* why = refined ? "" : "too few seeds survived";
         bool good = refined;
         auto by_mag = [](const Pair& a, const Pair& b2) { return std::fabs(a.theta) > std::fabs(b2.theta); };
@@ -1125,6 +1129,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
             }
         }
         from_seeds = good;
+        ms_validated = since_start();
         if (!from_seeds) {
             // the refined seeds are still eigenpairs of T: the slicing below only has to find what is missing
             known_pairs.clear();
@@ -1202,6 +1207,9 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         if (stepA_ <= 0) stepA_ = 1e-5 * tn;
         if (stepB_ <= 0) stepB_ = 1e-5 * tn;
     }
+    if (verbose > 1)
+        std::fprintf(stderr, "[rbl]   timeline of this check [ms]: stages 1-2 %.1f, seeds refined at %.1f, validated at %.1f, done at %.1f\n",
+                     ms_stage3_begin, ms_refined, ms_validated, since_start());
     if (verbose > 0)
         std::fprintf(stderr, "[rbl] full check N=%lld (%s) found=%lld worst rho=%.3e conv=%d (nfac=%d)\n", (long long)N,
                      from_seeds ? "seeds refined" : (hinted ? "hinted slicing" : "slicing"),
