@@ -261,3 +261,57 @@ def test_rejected_seeds_assist_the_slicing(rbl):
         assert np.max(np.abs(S.T @ S - np.eye(k))) < 1e-8, i
         M = rbl_oracle.dense_band_from_T(T)
         assert np.max(np.linalg.norm(M @ S - S * r["D"][None, :], axis=0)) < 1e-10 * 12, i
+
+
+def _random_band(rng, N, kd, kind):
+    """kind 0: plain random band (two-sided spectrum); 1: decaying off-diagonals; 2: decoupled identical blocks (exact
+    multiplicities, half of them scaled by 0.9) plus a small diagonal tail."""
+    M = np.zeros((N, N))
+    for d in range(kd + 1):
+        v = rng.standard_normal(N - d) * (0.3 ** d if kind else 1.0)
+        M += np.diag(v, -d)
+        if d:
+            M += np.diag(v, d)
+    if kind == 2:
+        w = kd * 3
+        blk = M[:w, :w].copy()
+        M[:, :] = 0
+        nb = N // w
+        for q in range(nb):
+            M[q * w:(q + 1) * w, q * w:(q + 1) * w] = blk if q % 2 == 0 else blk * 0.9
+        for i in range(nb * w, N):
+            M[i, i] = 0.01 * i
+    return M
+
+
+def _band_of(M, kd):
+    N = M.shape[0]
+    ab = np.zeros((kd + 1, N))
+    for d in range(kd + 1):
+        ab[d, :N - d] = np.diag(M, -d)
+    return ab
+
+
+@pytest.mark.parametrize("trial", range(15))
+def test_seeded_paths_on_random_bands(rbl, trial):
+    """A full solve of a leading principal submatrix provides the seeds for the full solve of the whole band matrix
+    (refined, rejected or assisting the slicing - whatever the counts say): always the k eigenvalues of largest
+    magnitude of a dense eigh, orthonormal vectors, small residuals."""
+    rng = np.random.default_rng(1000 + trial)
+    kd = int(rng.integers(2, 9))
+    N2 = int(rng.integers(150, 420))
+    N1 = int(N2 * rng.uniform(0.7, 0.97))
+    k = int(rng.integers(5, 40))
+    M2 = _random_band(rng, N2, kd, trial % 3)
+    ck = rbl.Checker(threads=2)
+    Bi = np.triu(rng.standard_normal((kd, kd)))
+    assert ck.check(_band_of(M2[:N1, :N1], kd), k, Bi, force_full=True)["have_all"]
+    r = ck.check(_band_of(M2, kd), k, Bi, force_full=True)
+    assert r["have_all"]
+    w = np.linalg.eigvalsh(M2)
+    tn = np.max(np.abs(w))
+    ref = np.sort(np.abs(w))[::-1][:k]
+    assert np.max(np.abs(np.sort(np.abs(r["D"]))[::-1] - ref)) < 1e-10 * tn
+    S = r["S"]
+    assert np.max(np.abs(S.T @ S - np.eye(k))) < 1e-8
+    assert np.max(np.linalg.norm(M2 @ S - S * r["D"][None, :], axis=0)) < 1e-9 * tn
