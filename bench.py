@@ -2,19 +2,26 @@
 """bench.py - time-to-k-eigenpairs of the RBL hot path on BASELINE.json configs[1].
 
 Workload (N=1 and N>1, "strong" scaling): 3-D 7-point Laplacian 100^3 (n = 10^6, nnz = 6.94e6), the 100 lowest
-eigenpairs as the 100 largest of 12*I - A, block size b = 16, fp64 SpMM / 3-term / QR with an fp32 Krylov buffer
-and fp32 re-orthogonalisation ("mixed", the reference's README.md:69 split).  One "step" is one complete solve
-(random start block -> Lanczos iteration with all convergence checks -> Ritz vectors).
+eigenpairs as the 100 largest of 12*I - A, block size b = 16, fp64 SpMM / 3-term / QR with a 4-byte Krylov buffer
+and fp32-accumulate re-orthogonalisation ("mixed", the reference's README.md:69 split).  One "step" is one complete
+solve (random start block -> Lanczos iteration with all convergence checks -> Ritz vectors), with the reference's own
+algorithm (plain operator, no restart): `value`.
 
     value   seconds per solve with A, Omega and V resident in HBM          (rbl_solve_device)
-    e2e     seconds per solve through the reference-facing call RBL_gpu(A,k,b) with HOST buffers: upload of A
-            (CSR) and Omega, download of V inside the timed region         (rbl_create + rbl_solve + rbl_destroy)
+    e2e     seconds per solve through the reference-facing call RBL_gpu(A,k,b) with PAGEABLE HOST buffers (what a
+            Julia Matrix is): upload of A (CSR) and Omega, download of V inside the timed region
+            (rbl_create + rbl_solve + rbl_destroy); `e2e.pinned_value` is the same with pinned buffers
     roofline   the dominant kernel family (re-orthogonalisation Gram / update against the Krylov buffer):
             algorithmic HBM bytes / CUDA-event time inside the library's stream, against MEASURED_PEAKS.json
-    cpu_baseline   the oracle restatement of RBL.jl on the box's host cores: a bounded sample (first block
-            steps of the same problem) extrapolated with the measured per-phase costs - a reported baseline.
+    solve   the three north-star gates measured on THIS run's full-size result: eigenvalues vs the analytic spectrum,
+            max ||A v - lambda v|| / ||A|| and ||V'V - I|| on the n = 1e6 V, orthogonality loss of the device Krylov basis
+    variants   the same problem in all-fp64 mode (the reference as shipped) and with the Chebyshev-filtered operator (N1)
+    cpu_baseline   the oracle restatement of RBL.jl on the box's host cores.  The full CPU solve takes hours, so the
+            config-2 number is an EXTRAPOLATION from a bounded sample and says so (`extrapolated`, `measured_steps`,
+            `of`); `anchor_config1` is the fully MEASURED companion: BASELINE configs[0] (n = 1e4, k = 10, b = 4) solved
+            end to end on both arms.
 
-`--impl reference` times only that CPU restatement (the reference itself is Julia and cannot run here).
+`--impl reference` times only the CPU restatement (the reference itself is Julia and cannot run here).
 """
 from __future__ import annotations
 
@@ -38,6 +45,8 @@ SIGMA = 12.0
 MAX_KRYL = 9600
 SEED = 20260
 METRIC = "time_to_k_eigenpairs"
+DTYPE_MIXED = ("f64 (SpMM, 3-term, QR, T) + 4-byte split16 Krylov buffer (2 x f16 terms, ~22 significant bits) "
+               "with fp32-accumulate tensor-core reorth / Ritz products")
 
 
 def problem():
@@ -47,8 +56,8 @@ def problem():
     return L
 
 
-def omega(n, b):
-    return np.random.default_rng(SEED).standard_normal((n, b))
+def omega(n, b, seed=SEED):
+    return np.random.default_rng(seed).standard_normal((n, b))
 
 
 def measured_peaks():
@@ -112,65 +121,133 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
 # block steps the fixed workload (seeded Omega) needs to converge: measured by the GPU arm (oracle-identical iteration
-# rule); the reference arm cannot afford to run the CPU solve to the end (~2e4 s) to find out
+# rule); the reference arm cannot afford to run the CPU solve to the end (hours) to find out
 KNOWN_BLOCK_STEPS = 492
+ANCHOR = dict(grid=100, k=10, b=4, sigma=8.0, seed=1234, cap=1400)   # BASELINE configs[0] at full size
 
 
-def cpu_reference(iterations_needed: int | None, budget_steps: int = 20):
+def anchor_problem():
+    from oracle import matrices
+    L = matrices.laplacian_2d(ANCHOR["grid"]).tocsr()
+    L.sort_indices()
+    return L, omega(L.shape[0], ANCHOR["b"], ANCHOR["seed"])
+
+
+def cpu_anchor_config1():
+    """BASELINE configs[0], fully MEASURED: the oracle restatement of RBL.jl, whole solve, all host cores."""
+    from oracle import matrices, rbl_oracle
+    L, Om = anchor_problem()
+    A = matrices.shifted(L, ANCHOR["sigma"])
+    t0 = time.perf_counter()
+    D, V, det = rbl_oracle.RBL(A, ANCHOR["k"], ANCHOR["b"], Om, max_kryl_sz=ANCHOR["cap"], return_details=True)
+    t = time.perf_counter() - t0
+    exact = ANCHOR["sigma"] - matrices.laplacian_eigs(ANCHOR["grid"], 2, ANCHOR["k"])
+    return {"cpu_s": t, "cpu_block_steps": int(det["stats"].iterations), "cpu_phase_s": dict(det["stats"].seconds),
+            "cpu_max_rel_eig_err_vs_analytic": float(np.max(np.abs(D - exact) / exact)), "D": D}
+
+
+def cpu_reference(iterations_needed: int | None, budget_steps: int = 10, one_thread_steps: int = 4, dsbev_n: int = 2000):
     """Oracle restatement of RBL.jl (fp64 as shipped) on the host cores: first `budget_steps` block steps of the
     same problem, then extrapolation to `iterations_needed` steps with the measured per-phase costs."""
     from oracle import matrices, rbl_oracle
     from scipy.linalg import lapack
+    from threadpoolctl import threadpool_limits
     L = problem()
     A = matrices.shifted(L, SIGMA)
     n = A.shape[0]
     Om = omega(n, BLOCK)
     cores = os.cpu_count() or 1
-    t0 = time.perf_counter()
-    _, _, det = rbl_oracle.RBL(A, K_WANTED, BLOCK, Om, max_kryl_sz=MAX_KRYL, max_iterations=budget_steps,
-                               return_details=True)
-    t_sample = time.perf_counter() - t0
-    st = det["stats"]
+
+    def sample(steps):
+        t0 = time.perf_counter()
+        _, _, det = rbl_oracle.RBL(A, K_WANTED, BLOCK, Om, max_kryl_sz=MAX_KRYL, max_iterations=steps, return_details=True)
+        return time.perf_counter() - t0, det["stats"]
+
+    t_sample, st = sample(budget_steps)
     m0 = st.iterations
     sec = st.seconds
-    # dsbev('V') cost model c*N^3, measured at N=640 (bandwidth 16), RBL.jl:107 / common.jl:36-48
-    N_e = 640
+    # dsbev('V') cost model c*N^3 (RBL.jl:107 / common.jl:36-48), anchored on a measurement at N = dsbev_n (bandwidth 16)
     rng = np.random.default_rng(0)
-    ab = rng.standard_normal((BLOCK + 1, N_e))
+    ab = rng.standard_normal((BLOCK + 1, dsbev_n))
     te = time.perf_counter()
     lapack.dsbev(np.asfortranarray(ab), compute_v=1, lower=1)
-    c_eig = (time.perf_counter() - te) / N_e ** 3
+    t_dsbev = time.perf_counter() - te
+    c_eig = t_dsbev / dsbev_n ** 3
+    # Ritz GEMM rate: measured dgemm of the recover_eigvec shape (n x 16) * (16 x 100)
+    Qb = rng.standard_normal((n, BLOCK)); Sb = rng.standard_normal((BLOCK, K_WANTED))
+    tg = time.perf_counter()
+    for _ in range(3):
+        Qb @ Sb
+    gemm_rate = 3 * 2.0 * n * BLOCK * K_WANTED / (time.perf_counter() - tg)
     m = iterations_needed or KNOWN_BLOCK_STEPS
-    per_step = (sec["A*Q"] + sec["3-term"] + sec["QR"] + sec["Loc reorth"]) / m0
-    blocks0 = sum(i - 2 for i in range(2, m0 + 1, 2))
-    c_reorth = sec["Part reorth"] / max(blocks0, 1)
-    blocks = sum(i - 2 for i in range(2, m + 1, 2))
+
+    def extrapolate(sec, m0):
+        per_step = (sec["A*Q"] + sec["3-term"] + sec["QR"] + sec["Loc reorth"]) / m0
+        blocks0 = sum(i - 2 for i in range(2, m0 + 1, 2))
+        c_reorth = sec["Part reorth"] / max(blocks0, 1)
+        blocks = sum(i - 2 for i in range(2, m + 1, 2))
+        return m * per_step + c_reorth * blocks, per_step, c_reorth
+
+    est_iter, per_step, c_reorth = extrapolate(sec, m0)
     t_eig = sum(c_eig * (i * BLOCK) ** 3 for i in range(4, m + 1, 4) if i * BLOCK > K_WANTED)
-    t_ritz = 2.0 * n * m * BLOCK * K_WANTED / 5e10  # dgemm at ~50 GFLOP/s
-    est_no_eig = m * per_step + c_reorth * blocks + t_ritz
+    t_ritz = 2.0 * n * m * BLOCK * K_WANTED / gemm_rate
+    est_no_eig = est_iter + t_ritz
     est = est_no_eig + t_eig
+    # the benchmark.jl:49 row: BLAS.set_num_threads(1)
+    one = None
+    if one_thread_steps > 0:
+        with threadpool_limits(limits=1, user_api="blas"):
+            t1, st1 = sample(one_thread_steps)
+            te = time.perf_counter()
+            lapack.dsbev(np.asfortranarray(ab[:, :640]), compute_v=1, lower=1)
+            c_eig1 = (time.perf_counter() - te) / 640 ** 3
+        e1, ps1, cr1 = extrapolate(st1.seconds, st1.iterations)
+        t_eig1 = sum(c_eig1 * (i * BLOCK) ** 3 for i in range(4, m + 1, 4) if i * BLOCK > K_WANTED)
+        one = {"value": e1 + t_ritz * cores + t_eig1, "unit": "s", "cores": 1, "extrapolated": True,
+               "measured_steps": int(st1.iterations), "of": int(m), "measured_sample_s": t1,
+               "note": "OPENBLAS threads = 1 (benchmark.jl:49 BLAS.set_num_threads(1)); dsbev measured at N=640 single-threaded"}
     return {
         "value": est, "unit": "s", "cores": cores, "kind": "port",
-        "sample": (f"oracle restatement of RBL.jl (NumPy/SciPy-OpenBLAS, fp64 as shipped, {cores} threads): first {m0} block "
-                   f"steps of the same problem measured ({t_sample:.1f} s: per-step {per_step:.3f} s, part-reorth "
-                   f"{c_reorth * 1e3:.1f} ms per stored block), dsbev('V') measured at N={N_e} ({c_eig * N_e ** 3:.2f} s, "
-                   f"cubic model); extrapolated to the {m} block steps the solve needs: "
-                   f"{est_no_eig:.0f} s without the host eigensolves + {t_eig:.0f} s of dsbev"),
+        "extrapolated": True, "measured_steps": int(m0), "of": int(m),
+        "sample": (f"oracle restatement of RBL.jl (NumPy/SciPy-OpenBLAS, fp64 as shipped, {cores} threads): first {m0} of {m} block "
+                   f"steps of the same problem MEASURED ({t_sample:.1f} s: per-step {per_step:.3f} s, part-reorth "
+                   f"{c_reorth * 1e3:.1f} ms per stored block), dsbev('V') MEASURED at N={dsbev_n} ({t_dsbev:.1f} s) and scaled "
+                   f"as N^3, Ritz GEMM at the measured {gemm_rate / 1e9:.0f} GFLOP/s; EXTRAPOLATED to {m} block steps: "
+                   f"{est_no_eig:.0f} s without the host eigensolves + {t_eig:.0f} s of dsbev.  Not a measurement of a full solve: "
+                   f"see anchor_config1 for a fully measured pair"),
         "measured_sample_s": t_sample, "estimate_without_dsbev_s": est_no_eig, "estimate_dsbev_s": t_eig,
-        "block_steps_extrapolated_to": m,
+        "dsbev_measured": {"N": dsbev_n, "seconds": t_dsbev},
+        "block_steps_extrapolated_to": m, "one_thread": one,
     }
+
+
+def library_replica():
+    """The reference's GPU call sequence replayed with library kernels (tools/library_replica.py), builder-measured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_library_replica_config2.json")) as f:
+            j = json.load(f)
+        return {"device_side_estimate_s": j["device_side_estimate_s"], "source": "profiles/r01_library_replica_config2.json "
+                "(cuSPARSE/cuBLAS/cuSOLVER through PyTorch in the reference's call pattern, host dsbev excluded; builder-run)"}
+    except Exception:
+        return None
 
 
 def run_reference(args, rank, out=sys.stdout):
     if rank != 0:
         return
-    cb = cpu_reference(None, budget_steps=args.ref_steps)
+    cb = cpu_reference(None, budget_steps=args.ref_steps, one_thread_steps=0 if args.quick else 4)
+    anchor = None if args.quick else cpu_anchor_config1()
+    if anchor:
+        anchor.pop("D")
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["value"] * 1e3, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "extrapolated": True, "measured_steps": cb["measured_steps"], "of": cb["of"],
         "config": config_dict(args.gpus),
         "cpu_baseline": cb,
+        "anchor_config1": anchor,
+        "library_replica": library_replica(),
         "e2e": {"value": cb["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -180,7 +257,8 @@ def run_reference(args, rank, out=sys.stdout):
 
 def config_dict(ngpu):
     return {"workload": f"configs[1]: 3D 7-point Laplacian {GRID}^3 (n=1e6, nnz=6.94e6), {K_WANTED} lowest eigenpairs via "
-                        f"{SIGMA:g}I-A, b={BLOCK}, fp64 SpMM/QR + fp32 Krylov buffer/reorth (mixed), tol=1e-7, full solve",
+                        f"{SIGMA:g}I-A, b={BLOCK}, fp64 SpMM/QR + 4-byte Krylov buffer/fp32-accumulate reorth (mixed), tol=1e-7, "
+                        f"full solve, plain operator (reference algorithm)",
             "n": GRID ** 3, "k": K_WANTED, "b": BLOCK, "precision": "mixed", "max_kryl_sz": MAX_KRYL,
             "row_shards": ngpu, "l2": "working set (Krylov buffer, tens of GB) >> 126 MB L2; no flush needed"}
 
@@ -194,7 +272,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--ref-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the variants, the anchor and the 1-thread CPU row")
     ap.add_argument("--precision", default="mixed")
+    ap.add_argument("--filter-degree", type=int, default=0, help="make the filtered operator the timed `value` (default: plain)")
     ap.add_argument("--verbose", type=int, default=0)
     args = ap.parse_args()
     # keep stdout to the ONE JSON line: libraries (NCCL prints its version banner) write to fd 1, so point fd 1
@@ -209,9 +289,11 @@ def main():
         run_reference(args, rank, real_stdout)
         return
 
+    import ctypes as C
     import torch
     import rbl_b200
     from rbl_b200 import binding as B
+    from oracle import matrices
     if not torch.cuda.is_available() or rbl_b200.lib().rbl_device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: rbl_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -226,34 +308,40 @@ def main():
     Om = omega(n, BLOCK)
     cores = os.cpu_count() or 1
     host_threads = cores  # only rank 0 evaluates the host eigen-checks, so it may use every core of the box
-    opt_kw = dict(max_kryl_sz=MAX_KRYL, precision=B.PRECISION_MIXED if args.precision == "mixed" else B.PRECISION_FP64,
+
+    def options(**over):
+        kw = dict(max_kryl_sz=MAX_KRYL, precision=B.PRECISION_MIXED if args.precision == "mixed" else B.PRECISION_FP64,
                   op=B.OP_SHIFT_MINUS_A, sigma=SIGMA, device=local_rank, async_check=1, host_threads=host_threads,
-                  verbose=args.verbose)
+                  verbose=args.verbose, filter_degree=args.filter_degree)
+        kw.update(over)
+        return B.default_options(**kw)
 
     if world > 1:
         rs = rbl_b200.partition_rows(n, world)
         r0, r1 = int(rs[rank]), int(rs[rank + 1])
-        def fresh_uid():
-            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-            if rank == 0:
-                import ctypes
-                buf = ctypes.create_string_buffer(128)
-                assert rbl_b200.lib().rbl_nccl_unique_id(buf) == 0, rbl_b200.lib().rbl_last_error()
-                uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
-            dist.broadcast(uid, 0)
-            return bytes(uid.cpu().numpy().tobytes())
+        # ONE NCCL unique id for the whole run: every handle of this group presents it, so the library reuses the
+        # communicator it parked when the previous handle was destroyed (comm.cpp)
+        uid_t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            assert rbl_b200.lib().rbl_nccl_unique_id(buf) == 0, rbl_b200.lib().rbl_last_error()
+            uid_t.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(uid_t, 0)
+        uid = bytes(uid_t.cpu().numpy().tobytes())
         Lloc = L[r0:r1, :]
         Lloc.sort_indices()
 
-        def make_solver():
-            return B.Solver(options=B.default_options(**opt_kw),
+        def make_solver(**over):
+            return B.Solver(options=options(**over),
                             shard=dict(n=n, row0=r0, rowptr=Lloc.indptr.astype(np.int64), colidx=Lloc.indices.astype(np.int64),
-                                       vals=Lloc.data, rank=rank, world=world, uid=fresh_uid()))
+                                       vals=Lloc.data, rank=rank, world=world, uid=uid))
         Om_loc = np.asfortranarray(Om[r0:r1])
         nloc = r1 - r0
     else:
-        def make_solver():
-            return B.Solver(L, options=B.default_options(**opt_kw))
+        r0 = 0
+
+        def make_solver(**over):
+            return B.Solver(L, options=options(**over))
         Om_loc = np.asfortranarray(Om)
         nloc = n
 
@@ -262,6 +350,13 @@ def main():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
 
     # ---- value: everything resident in HBM ------------------------------------------------------------
     solver = make_solver()
@@ -294,44 +389,47 @@ def main():
     e1.record()
     barrier()
     clocks = sampler.stop()
-    t_dev = e0.elapsed_time(e1) * 1e-3
-    if dist is not None:
-        tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev = float(tt.item())
-    sec_per_solve = t_dev / args.steps
+    sec_per_solve = max_over_ranks(e0.elapsed_time(e1) * 1e-3) / args.steps
+    # orthogonality loss of the Krylov basis the last solve left in the slab (north-star gate 3), measured on the device
+    ortho_max, ortho_fro = solver.orthogonality()
     solver.close()
 
     # ---- e2e: the reference-facing call with host buffers ------------------------------------------------
-    om_pin = torch.from_numpy(np.asfortranarray(Om_loc).T.copy()).pin_memory()   # pinned host Omega (column-major view)
-    v_pin = torch.empty((K_WANTED, nloc), dtype=torch.float64).pin_memory()
-    import ctypes as C
+    def e2e_run(pinned: bool):
+        if pinned:
+            om_h = torch.from_numpy(np.asfortranarray(Om_loc).T.copy()).pin_memory()
+            v_h = torch.empty((K_WANTED, nloc), dtype=torch.float64).pin_memory()
+            om_ptr, v_ptr = om_h.data_ptr(), v_h.data_ptr()
+        else:   # pageable, like the Matrix{Float64} a Julia caller passes (julia/RBL_b200.jl)
+            om_h = np.asfortranarray(Om_loc)
+            v_h = np.zeros((nloc, K_WANTED), order="F")
+            om_ptr, v_ptr = om_h.ctypes.data, v_h.ctypes.data
 
-    def e2e_once():
-        s = make_solver()                                                        # uploads A (rbl_create)
-        Dh = np.zeros(K_WANTED)
-        st = B.RblStats()
-        rc = rbl_b200.lib().rbl_solve(s._h, K_WANTED, BLOCK, C.cast(om_pin.data_ptr(), C.POINTER(C.c_double)),
-                                      Dh.ctypes.data_as(C.POINTER(C.c_double)), C.c_void_p(v_pin.data_ptr()), C.byref(st))
-        if rc != 0:
-            raise RuntimeError(rbl_b200.lib().rbl_last_error().decode())
-        s.close()
-        return Dh, st
-    for _ in range(max(1, args.warmup)):     # same warm-up count as the device-resident arm (first calls grow the workspace)
-        e2e_once()
-    barrier()
-    f0 = torch.cuda.Event(enable_timing=True)
-    f1 = torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        Dh, st_e2e = e2e_once()
-    f1.record()
-    barrier()
-    t_e2e = f0.elapsed_time(f1) * 1e-3
-    if dist is not None:
-        tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_e2e = float(tt.item())
+        def once():
+            s = make_solver()                                                        # uploads A (rbl_create)
+            Dh = np.zeros(K_WANTED)
+            st = B.RblStats()
+            rc = rbl_b200.lib().rbl_solve(s._h, K_WANTED, BLOCK, C.cast(om_ptr, C.POINTER(C.c_double)),
+                                          Dh.ctypes.data_as(C.POINTER(C.c_double)), C.c_void_p(v_ptr), C.byref(st))
+            if rc != 0:
+                raise RuntimeError(rbl_b200.lib().rbl_last_error().decode())
+            s.close()
+            return Dh, st
+        for _ in range(max(1, args.warmup)):     # same warm-up count as the device-resident arm
+            once()
+        barrier()
+        f0 = torch.cuda.Event(enable_timing=True)
+        f1 = torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            Dh, st = once()
+        f1.record()
+        barrier()
+        t = max_over_ranks(f0.elapsed_time(f1) * 1e-3) / args.steps
+        Vh = v_h.numpy().T if pinned else v_h
+        return t, Dh, np.asarray(Vh), st
+    t_e2e, Dh, Vh, st_e2e = e2e_run(pinned=False)
+    t_e2e_pinned = None if args.quick else e2e_run(pinned=True)[0]
     nnz_loc = (Lloc.nnz if world > 1 else L.nnz)
     h2d = 4 * (nloc + 1) + 12 * nnz_loc + 8 * nloc * BLOCK
     d2h = 8 * nloc * K_WANTED
@@ -340,10 +438,81 @@ def main():
         dist.all_reduce(hb)
         h2d, d2h = int(hb[0].item()), int(hb[1].item())
 
-    # ---- checks on the result (eigenvalues against the analytic spectrum) -----------------------------------
-    from oracle import matrices
+    # ---- the north-star gates on THIS run's full-size result --------------------------------------------------
     exact = SIGMA - matrices.laplacian_eigs(GRID, 3, K_WANTED)
     eig_err = float(np.max(np.abs(D - exact) / exact))
+    # Ritz residuals and orthonormality of the n = 1e6 V that came back through the host-buffer call
+    if dist is not None:
+        parts = [torch.empty((int(rs[p + 1] - rs[p]), K_WANTED), dtype=torch.float64, device=dev) for p in range(world)]
+        dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(Vh)).to(dev))
+        Vfull = torch.cat(parts).cpu().numpy() if rank == 0 else None
+    else:
+        Vfull = Vh
+    gates = {}
+    if rank == 0:
+        A = matrices.shifted(L, SIGMA)
+        R = A @ Vfull - Vfull * Dh[None, :]
+        gates["max_ritz_residual_over_normA"] = float(np.max(np.linalg.norm(R, axis=0)) / SIGMA)
+        G = Vfull.T @ Vfull
+        gates["v_orthonormality_maxabs"] = float(np.max(np.abs(G - np.eye(K_WANTED))))
+        gates["v_orthonormality_2norm"] = float(np.linalg.norm(G - np.eye(K_WANTED), 2))
+        gates["max_rel_eig_err_vs_analytic_e2e"] = float(np.max(np.abs(Dh - exact) / exact))
+    gates["krylov_basis_QtQ_minus_I_maxabs"] = ortho_max
+    gates["krylov_basis_QtQ_minus_I_fro"] = ortho_fro
+
+    # ---- variants (single GPU, not part of `value`): all-fp64 mode, Chebyshev-filtered operator -------------------
+    variants = {}
+    if world == 1 and not args.quick:
+        def timed_variant(name, solves=2, **over):
+            s = make_solver(**over)
+            Dv, stv = s.solve_device(K_WANTED, BLOCK, om_dev.data_ptr(), v_dev.data_ptr())        # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(solves):
+                Dv, stv = s.solve_device(K_WANTED, BLOCK, om_dev.data_ptr(), v_dev.data_ptr())
+            torch.cuda.synchronize()
+            t = (time.perf_counter() - t0) / solves
+            Vv = v_dev.cpu().numpy().T
+            Rv = matrices.shifted(L, SIGMA) @ Vv - Vv * Dv[None, :]
+            variants[name] = {"s_per_solve": t, "block_steps": int(stv.iterations), "spmm_launches": int(stv.launches_spmm),
+                              "max_rel_eig_err_vs_analytic": float(np.max(np.abs(Dv - exact) / exact)),
+                              "max_ritz_residual_over_normA": float(np.max(np.linalg.norm(Rv, axis=0)) / SIGMA),
+                              "filter_degree": int(stv.filter_degree), "converged": bool(stv.converged)}
+            s.close()
+        if args.precision == "mixed":
+            timed_variant("fp64_mode", solves=1, precision=B.PRECISION_FP64)
+        for d in (4, 8):
+            timed_variant(f"chebyshev_filter_degree_{d}", filter_degree=d)
+
+    # ---- N > 1: the sharded result must equal the single-GPU result ---------------------------------------------
+    vs_1gpu = None
+    if world > 1:
+        if rank == 0:
+            with B.Solver(L, options=options()) as s1:
+                D1, _, st1 = s1.solve(K_WANTED, BLOCK, np.asfortranarray(Om))
+            vs_1gpu = {"max_rel_eig_diff": float(np.max(np.abs(D1 - D) / np.abs(D1))), "block_steps_1gpu": int(st1.iterations)}
+            assert vs_1gpu["max_rel_eig_diff"] < 1e-8, vs_1gpu
+        dist.barrier()
+
+    # ---- anchor: BASELINE configs[0] at full size, fully measured on the GPU arm -------------------------------------
+    anchor = None
+    if world == 1 and not args.quick:
+        La, Oma = anchor_problem()
+        oa = B.default_options(max_kryl_sz=ANCHOR["cap"], precision=B.PRECISION_FP64, op=B.OP_SHIFT_MINUS_A, sigma=ANCHOR["sigma"],
+                               device=local_rank, host_threads=host_threads)
+
+        def anchor_once():
+            with B.Solver(La, options=oa) as sa:
+                return sa.solve(ANCHOR["k"], ANCHOR["b"], Oma)
+        anchor_once()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            Da, Va, sta = anchor_once()
+        t_anchor = (time.perf_counter() - t0) / 3
+        exa = ANCHOR["sigma"] - matrices.laplacian_eigs(ANCHOR["grid"], 2, ANCHOR["k"])
+        anchor = {"workload": "BASELINE configs[0] at full size: 2D 5-point Laplacian 100x100 (n=1e4), 10 lowest pairs via 8I-A, b=4, fp64",
+                  "gpu_e2e_s": t_anchor, "gpu_block_steps": int(sta.iterations),
+                  "gpu_max_rel_eig_err_vs_analytic": float(np.max(np.abs(Da - exa) / exa))}
 
     if rank != 0:
         if dist is not None:
@@ -362,15 +531,17 @@ def main():
     # DRAM bytes of the dominant kernel from the committed ncu --set full capture: the captured launch's
     # (read + write) / algorithmic ratio applied to this run's average launch
     traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tj = json.load(f)
-        cap = tj[dom]
-        ratio = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["algorithmic_bytes"]
-        traffic = ratio * d_b / d_n
-        traffic_src = f"ncu capture of one launch (m={cap['m']}): DRAM read+write = {ratio:.4f} x algorithmic bytes, scaled to the average launch"
-    except Exception:
-        pass
+    for tf in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", tf)) as f:
+                tj = json.load(f)
+            cap = tj[dom]
+            ratio = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["algorithmic_bytes"]
+            traffic = ratio * d_b / d_n
+            traffic_src = f"profiles/{tf}: ncu capture of one launch (m={cap['m']}): DRAM read+write = {ratio:.4f} x algorithmic bytes, scaled to the average launch"
+            break
+        except Exception:
+            continue
     roof = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
@@ -385,24 +556,35 @@ def main():
                      "s_per_solve": agg["t_ritz_kernel"] / steps},
             "3term_s_per_solve": agg["t_3term"] / steps, "qr_s_per_solve": agg["t_qr"] / steps,
             "loc_reorth_s_per_solve": agg["t_loc_reorth"] / steps,
-            "host_eig_s_per_solve": agg["t_eig"] / steps, "host_eig_wait_s_per_solve": agg["t_eig_wait"] / steps,
+            "host_eig_s_per_solve": agg["t_eig"] / steps,
+            "device_idle_waiting_for_checks_s_per_solve": agg["t_eig_wait"] / steps,
+            "host_thread_blocked_s_per_solve": agg["t_host_blocked"] / steps,
         },
     }
     iterations = int(round(agg["iterations"] / steps))
     if args.no_cpu_baseline or world > 1:
         cb = {"value": None, "unit": "s", "cores": cores, "kind": "port", "sample": "skipped (N>1 or --no-cpu-baseline)"}
     else:
-        cb = cpu_reference(iterations, budget_steps=args.ref_steps)
+        cb = cpu_reference(iterations, budget_steps=args.ref_steps, one_thread_steps=0 if args.quick else 4)
+        if anchor is not None:
+            ca = cpu_anchor_config1()
+            Dc = ca.pop("D")
+            anchor.update(ca)
+            anchor["cpu_over_gpu"] = ca["cpu_s"] / anchor["gpu_e2e_s"]
+            anchor["max_rel_eig_diff_gpu_vs_cpu"] = float(np.max(np.abs(Da - Dc) / np.abs(Dc)))
+            anchor["note"] = "both arms fully measured (no extrapolation): whole solve, host buffers, same Omega"
     line = {
         "metric": METRIC, "value": sec_per_solve, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec_per_solve * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64" if args.precision != "mixed" else "f64+f32", "data": "synthetic", "config": config_dict(world),
-        "e2e": {"value": t_e2e / steps, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "dtype": "f64" if args.precision != "mixed" else DTYPE_MIXED, "data": "synthetic", "config": config_dict(world),
+        "e2e": {"value": t_e2e, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "host_buffers": "pageable", "pinned_value": t_e2e_pinned},
         "gpu_launches": int(agg["kernel_launches"]),
         "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
-        "solve": {"block_steps": iterations, "kryl_sz": iterations * BLOCK, "block_steps_run": int(round(agg["iterations_run"] / steps)),
-                  "checks": int(round(agg["checks"] / steps)), "full_checks": int(round(agg["full_checks"] / steps)),
-                  "max_rel_eig_err_vs_analytic": eig_err, "host_cores": cores},
+        "solve": dict({"block_steps": iterations, "kryl_sz": iterations * BLOCK, "block_steps_run": int(round(agg["iterations_run"] / steps)),
+                       "checks": int(round(agg["checks"] / steps)), "full_checks": int(round(agg["full_checks"] / steps)),
+                       "max_rel_eig_err_vs_analytic": eig_err, "host_cores": cores, "filter_degree": args.filter_degree}, **gates),
+        "variants": variants, "anchor_config1": anchor, "vs_1gpu": vs_1gpu, "library_replica": library_replica(),
     }
     real_stdout.write(json.dumps(line) + "\n")
     real_stdout.flush()

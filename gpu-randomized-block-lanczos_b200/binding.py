@@ -25,7 +25,9 @@ class RblOptions(C.Structure):
     _fields_ = [("max_kryl_sz", C.c_int64), ("tol", C.c_double), ("reorth_period", C.c_int32),
                 ("check_period", C.c_int32), ("precision", C.c_int32), ("op", C.c_int32), ("sigma", C.c_double),
                 ("device", C.c_int32), ("async_check", C.c_int32), ("host_threads", C.c_int32), ("v_fp32", C.c_int32),
-                ("verbose", C.c_int32), ("reorth_impl", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("verbose", C.c_int32), ("reorth_impl", C.c_int32), ("seed", C.c_int32), ("ngpus", C.c_int32),
+                ("filter_degree", C.c_int32), ("restart", C.c_int32), ("spill", C.c_int32), ("probe_steps", C.c_int32),
+                ("mem_limit_mb", C.c_int32)]
 
 
 class RblStats(C.Structure):
@@ -39,7 +41,9 @@ class RblStats(C.Structure):
                 ("bytes_reorth_update", C.c_double), ("launches_reorth_gram", C.c_int64),
                 ("launches_reorth_update", C.c_int64), ("launches_spmm", C.c_int64), ("t_ritz_kernel", C.c_double),
                 ("bytes_ritz", C.c_double), ("flops_ritz", C.c_double), ("host_factorizations", C.c_int64),
-                ("reserved", C.c_double * 8)]
+                ("restarts", C.c_int64), ("locked", C.c_int64), ("spilled_blocks", C.c_int64), ("buffer_blocks", C.c_int64),
+                ("max_residual", C.c_double), ("t_host_blocked", C.c_double), ("filter_cut", C.c_double),
+                ("filter_degree", C.c_int32), ("filter_two_sided", C.c_int32)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_ if f != "reserved"}
@@ -59,6 +63,7 @@ SIGNATURES = {
     "rbl_version": (C.c_char_p, []),
     "rbl_device_count": (C.c_int, []),
     "rbl_options_default": (C.c_int, [C.POINTER(RblOptions)]),
+    "rbl_struct_sizes": (C.c_int, [_P64, _P64]),
     "rbl_create": (C.c_int, [C.c_int64, C.c_int64, _P64, _P64, _PD, C.c_int, C.POINTER(RblOptions), C.POINTER(C.c_void_p)]),
     "rbl_create_dense": (C.c_int, [C.c_int64, _PD, C.POINTER(RblOptions), C.POINTER(C.c_void_p)]),
     "rbl_nccl_unique_id": (C.c_int, [C.c_void_p]),
@@ -69,6 +74,10 @@ SIGNATURES = {
     "rbl_solve": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _PD, _PD, C.c_void_p, C.POINTER(RblStats)]),
     "rbl_solve_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, _PD, C.c_void_p, C.POINTER(RblStats)]),
     "rbl_buffer_blocks": (C.c_int, [C.c_void_p, C.c_int64, _P64]),
+    "rbl_plan_blocks": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _P64]),
+    "rbl_krylov_info": (C.c_int, [C.c_void_p, _P64, _P64]),
+    "rbl_krylov_block": (C.c_int, [C.c_void_p, C.c_int64, _PD]),
+    "rbl_orthogonality": (C.c_int, [C.c_void_p, _PD, _PD]),
     "rbl_query_memory": (C.c_int, [C.c_int, _P64, _P64]),
     "rbl_spmm": (C.c_int, [C.c_void_p, C.c_int64, _PD, _PD]),
     "rbl_gram": (C.c_int, [C.c_int64, C.c_int64, _PD, _PD, _PD]),
@@ -135,15 +144,19 @@ def default_options(**kw) -> RblOptions:
 
 
 class Solver:
-    """Owns an rbl_handle (device-resident A).  `A` is any SciPy sparse matrix or a dense ndarray (symmetric)."""
+    """Owns an rbl_handle (device-resident A).  `A` is any SciPy sparse matrix or a dense ndarray (symmetric).
 
-    def __init__(self, A=None, *, options: RblOptions | None = None, shard=None, **opt_kw):
+    index_base=1 hands the library Julia's SparseMatrixCSC arrays exactly as `julia/RBL_b200.jl` does (Int64, 1-based
+    colptr / rowval); ngpus > 1 (option) makes it a single-process multi-GPU group handle."""
+
+    def __init__(self, A=None, *, options: RblOptions | None = None, shard=None, index_base: int = 0, **opt_kw):
         import scipy.sparse as sp
         self._h = C.c_void_p()
         self.options = options if options is not None else default_options(**opt_kw)
         L = lib()
         if shard is not None:
-            # shard = dict(n, row0, rowptr, colidx, vals, rank, world, uid)
+            # shard = dict(n, row0, rowptr, colidx, vals, rank, world, uid[, index_base])
+            base = int(shard.get("index_base", 0))
             rp = np.ascontiguousarray(shard["rowptr"], dtype=np.int64)
             ci = np.ascontiguousarray(shard["colidx"], dtype=np.int64)
             va = np.ascontiguousarray(shard["vals"], dtype=np.float64)
@@ -151,20 +164,21 @@ class Solver:
             self.nloc = len(rp) - 1
             uid = shard.get("uid")
             uid_buf = C.create_string_buffer(bytes(uid), 128) if uid is not None else None
-            _check(L.rbl_create_sharded(self.n, int(shard["row0"]), self.nloc, len(ci), _p64(rp), _p64(ci), _pd(va), 0,
+            _check(L.rbl_create_sharded(self.n, int(shard["row0"]), self.nloc, len(ci), _p64(rp), _p64(ci), _pd(va), base,
                                         int(shard["rank"]), int(shard["world"]), uid_buf, C.byref(self.options),
                                         C.byref(self._h)))
             return
         if sp.issparse(A):
-            # a symmetric matrix: CSC of A is CSR of A; Julia hands colptr/rowval/nzval (1-based) - here 0-based
+            # a symmetric matrix: CSC of A is CSR of A; Julia hands colptr/rowval/nzval 1-based (index_base=1)
             M = sp.csr_matrix(A)
             M.sort_indices()
             self.n = M.shape[0]
             self.nloc = self.n
-            rp = M.indptr.astype(np.int64)
-            ci = M.indices.astype(np.int64)
+            rp = M.indptr.astype(np.int64) + index_base
+            ci = M.indices.astype(np.int64) + index_base
             va = np.ascontiguousarray(M.data, dtype=np.float64)
-            _check(L.rbl_create(self.n, len(ci), _p64(rp), _p64(ci), _pd(va), 0, C.byref(self.options), C.byref(self._h)))
+            _check(L.rbl_create(self.n, len(ci), _p64(rp), _p64(ci), _pd(va), index_base, C.byref(self.options),
+                                C.byref(self._h)))
         else:
             D = np.asfortranarray(A, dtype=np.float64)
             self.n = D.shape[0]
@@ -221,6 +235,28 @@ class Solver:
         out = C.c_int64()
         _check(lib().rbl_buffer_blocks(self._h, b, C.byref(out)))
         return out.value
+
+    def plan_blocks(self, k: int, b: int) -> int:
+        out = C.c_int64()
+        _check(lib().rbl_plan_blocks(self._h, k, b, C.byref(out)))
+        return out.value
+
+    def krylov_basis(self):
+        """The Krylov basis the last solve left in the slab, decoded to fp64: n x (blocks*b) (locked vectors first)."""
+        nb, b = C.c_int64(), C.c_int64()
+        _check(lib().rbl_krylov_info(self._h, C.byref(nb), C.byref(b)))
+        Q = np.zeros((self.nloc, nb.value * b.value), order="F")
+        blk = np.zeros((self.nloc, b.value), order="F")
+        for j in range(nb.value):
+            _check(lib().rbl_krylov_block(self._h, j, _pd(blk)))
+            Q[:, j * b.value:(j + 1) * b.value] = blk
+        return Q
+
+    def orthogonality(self):
+        """(max |Q'Q - I|, ||Q'Q - I||_F) of the stored basis, computed on the device."""
+        mx, fro = C.c_double(), C.c_double()
+        _check(lib().rbl_orthogonality(self._h, C.byref(mx), C.byref(fro)))
+        return mx.value, fro.value
 
 
 # ---- kernel-level wrappers (parity tests) -------------------------------------------------------------

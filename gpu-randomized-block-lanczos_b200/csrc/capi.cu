@@ -1,8 +1,11 @@
 // extern "C" entry points declared in include/rbl_b200.h.
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "partition.h"
@@ -34,6 +37,130 @@ static void need_device() {
         throw Error(RBL_NO_DEVICE, "no CUDA device visible: rbl_b200 has no CPU fallback");
 }
 
+// ---- single-process multi-GPU (opts.ngpus > 1): one per-device handle + one host thread per device -------------
+// `RBL_gpu(A,k,b; ngpus=8)` from ONE caller (Julia is one process).  The group handle owns N
+// row-sharded handles on devices [device, device+N); NCCL ranks are the host threads of this process.
+namespace {
+std::mutex g_group_mu;
+std::map<std::pair<int, int>, std::vector<char>> g_group_uid;   // (first device, N) -> unique id of that group
+
+template <typename F>
+void run_parts(int N, std::vector<std::string>& errs, std::vector<int>& codes, F&& f) {
+    errs.assign(N, std::string());
+    codes.assign(N, RBL_OK);
+    std::vector<std::thread> th;
+    for (int p = 0; p < N; ++p)
+        th.emplace_back([&, p] {
+            try {
+                codes[p] = f(p);
+            } catch (const Error& e) {
+                errs[p] = e.what();
+                codes[p] = e.status;
+            } catch (const std::exception& e) {
+                errs[p] = e.what();
+                codes[p] = RBL_INVALID;
+            }
+        });
+    for (auto& t : th) t.join();
+}
+
+rbl_handle* create_group(int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                         int index_base, const rbl_options* opts) {
+    const int N = opts->ngpus;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        throw Error(RBL_NO_DEVICE, "no CUDA device visible: rbl_b200 has no CPU fallback");
+    int dev0 = opts->device;
+    if (dev0 < 0) dev0 = 0;
+    if (dev0 + N > ndev) throw Error(RBL_INVALID, "rbl_create: opts.ngpus exceeds the visible devices");
+    if (n <= 0 || nnz < 0 || !colptr || (nnz > 0 && (!rowval || !nzval))) throw Error(RBL_INVALID, "rbl_create: bad arguments");
+    if (n < N) throw Error(RBL_INVALID, "rbl_create: fewer rows than GPUs");
+    if (colptr[n] - colptr[0] != nnz) throw Error(RBL_INVALID, "rbl_create: rowptr[n]-rowptr[0] != nnz");
+    std::unique_ptr<rbl_handle> g(new rbl_handle());
+    g->opt = *opts;
+    g->n = n; g->nloc = n; g->nnz = nnz; g->world = N; g->device = dev0;
+    g->part_rows.resize((size_t)N + 1);
+    partition_rows(n, N, g->part_rows.data());
+    std::vector<char> uid(128);
+    {
+        std::lock_guard<std::mutex> lk(g_group_mu);
+        auto it = g_group_uid.find({dev0, N});
+        if (it == g_group_uid.end()) {
+            std::string err;
+            if (!Comm::unique_id(uid.data(), err)) throw Error(RBL_NCCL_ERROR, err);
+            g_group_uid[{dev0, N}] = uid;
+        } else {
+            uid = it->second;
+        }
+    }
+    g->parts.assign(N, nullptr);
+    std::vector<std::string> errs;
+    std::vector<int> codes;
+    run_parts(N, errs, codes, [&](int p) {
+        rbl_options o = *opts;
+        o.device = dev0 + p;
+        o.ngpus = 1;
+        if (p != 0) o.verbose = 0;
+        const int64_t r0 = g->part_rows[p], r1 = g->part_rows[p + 1];
+        const int64_t e0 = colptr[r0] - colptr[0], e1 = colptr[r1] - colptr[0];
+        g->parts[p] = handle_create(n, r0, r1 - r0, e1 - e0, colptr + r0, rowval + e0, nzval + e0, index_base, p, N,
+                                    uid.data(), &o);
+        return (int)RBL_OK;
+    });
+    for (int p = 0; p < N; ++p)
+        if (codes[p] != RBL_OK) {
+            {   // the group id may be half-used: never reuse it
+                std::lock_guard<std::mutex> lk(g_group_mu);
+                g_group_uid.erase({dev0, N});
+            }
+            throw Error(codes[p], "rbl_create (device " + std::to_string(dev0 + p) + "): " + errs[p]);
+        }
+    g->gersh_lo = g->parts[0]->gersh_lo;
+    g->gersh_hi = g->parts[0]->gersh_hi;
+    return g.release();
+}
+
+int solve_group(rbl_handle* g, int64_t k, int64_t b, const double* omega, double* d_out, void* v_out, rbl_stats* stats) {
+    const int N = (int)g->parts.size();
+    if (!d_out || !v_out) throw Error(RBL_INVALID, "rbl_solve: null output");
+    const size_t vsz = g->opt.v_fp32 ? 4 : 8;
+    std::vector<std::vector<double>> dpart(N, std::vector<double>((size_t)std::max<int64_t>(k, 1)));
+    std::vector<rbl_stats> st(N);
+    std::vector<std::string> errs;
+    std::vector<int> codes;
+    run_parts(N, errs, codes, [&](int p) {
+        SolveIO io;
+        const int64_t r0 = g->part_rows[p];
+        io.omega = omega ? omega + r0 : nullptr;
+        io.ld_omega = g->n;
+        io.v = (char*)v_out + (size_t)r0 * vsz;
+        io.ldv = g->n;
+        return solve(g->parts[p], k, b, io, dpart[p].data(), &st[p]);
+    });
+    for (int p = 0; p < N; ++p)
+        if (codes[p] != RBL_OK && codes[p] != RBL_NOT_CONVERGED)
+            throw Error(codes[p], "rbl_solve (device " + std::to_string(g->device + p) + "): " + errs[p]);
+    for (int64_t t = 0; t < k; ++t) d_out[t] = dpart[0][t];
+    if (stats) {
+        *stats = st[0];
+        for (int p = 1; p < N; ++p) {   // device phases: the slowest rank; launches: all ranks
+            stats->t_spmm = std::max(stats->t_spmm, st[p].t_spmm);
+            stats->t_3term = std::max(stats->t_3term, st[p].t_3term);
+            stats->t_qr = std::max(stats->t_qr, st[p].t_qr);
+            stats->t_part_reorth = std::max(stats->t_part_reorth, st[p].t_part_reorth);
+            stats->t_loc_reorth = std::max(stats->t_loc_reorth, st[p].t_loc_reorth);
+            stats->t_ritz = std::max(stats->t_ritz, st[p].t_ritz);
+            stats->t_total = std::max(stats->t_total, st[p].t_total);
+            stats->kernel_launches += st[p].kernel_launches;
+            stats->bytes_part_reorth += st[p].bytes_part_reorth;
+            stats->bytes_spmm += st[p].bytes_spmm;
+            stats->max_residual = std::max(stats->max_residual, st[p].max_residual);
+        }
+    }
+    return codes[0];
+}
+}  // namespace
+
 extern "C" {
 
 const char* rbl_last_error(void) { return g_err.c_str(); }
@@ -42,6 +169,11 @@ int rbl_device_count(void) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess) return 0;
     return ndev;
+}
+int rbl_struct_sizes(int64_t* options_bytes, int64_t* stats_bytes) {
+    if (options_bytes) *options_bytes = (int64_t)sizeof(rbl_options);
+    if (stats_bytes) *stats_bytes = (int64_t)sizeof(rbl_stats);
+    return RBL_OK;
 }
 int rbl_options_default(rbl_options* opts) {
     if (!opts) return RBL_INVALID;
@@ -53,7 +185,12 @@ int rbl_create(int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* row
                int index_base, const rbl_options* opts, rbl_handle** out) {
     return guarded([&] {
         if (!out) throw Error(RBL_INVALID, "rbl_create: out is null");
-        *out = handle_create(n, 0, n, nnz, colptr, rowval, nzval, index_base, 0, 1, nullptr, opts);
+        if (opts && opts->ngpus > 1) {
+            if (index_base != 0 && index_base != 1) throw Error(RBL_INVALID, "rbl_create: index_base must be 0 or 1");
+            *out = create_group(n, nnz, colptr, rowval, nzval, index_base, opts);
+        } else {
+            *out = handle_create(n, 0, n, nnz, colptr, rowval, nzval, index_base, 0, 1, nullptr, opts);
+        }
         return (int)RBL_OK;
     });
 }
@@ -98,6 +235,8 @@ int rbl_create_sharded(int64_t n, int64_t row0, int64_t nloc, int64_t nnz_loc, c
 int rbl_release_cached_memory(void) {
     slab_cache_release_all();
     Comm::release_cached();
+    std::lock_guard<std::mutex> lk(g_group_mu);
+    g_group_uid.clear();   // the parked communicators of the group ids are gone
     return RBL_OK;
 }
 
@@ -109,7 +248,10 @@ int rbl_destroy(rbl_handle* h) {
 int rbl_solve(rbl_handle* h, int64_t k, int64_t b, const double* omega, double* d_out, void* v_out, rbl_stats* stats) {
     return guarded([&] {
         if (!h) throw Error(RBL_INVALID, "rbl_solve: null handle");
-        return solve(h, k, b, omega, false, d_out, v_out, false, stats);
+        if (!h->parts.empty()) return solve_group(h, k, b, omega, d_out, v_out, stats);
+        SolveIO io;
+        io.omega = omega; io.ld_omega = h->nloc; io.v = v_out; io.ldv = h->nloc;
+        return solve(h, k, b, io, d_out, stats);
     });
 }
 
@@ -117,7 +259,11 @@ int rbl_solve_device(rbl_handle* h, int64_t k, int64_t b, const void* omega_dev,
                      rbl_stats* stats) {
     return guarded([&] {
         if (!h) throw Error(RBL_INVALID, "rbl_solve_device: null handle");
-        return solve(h, k, b, (const double*)omega_dev, true, d_out, v_dev, true, stats);
+        if (!h->parts.empty()) throw Error(RBL_INVALID, "rbl_solve_device: not available on multi-GPU group handles (use rbl_solve)");
+        SolveIO io;
+        io.omega = (const double*)omega_dev; io.ld_omega = h->nloc; io.omega_on_device = true;
+        io.v = v_dev; io.ldv = h->nloc; io.v_on_device = true;
+        return solve(h, k, b, io, d_out, stats);
     });
 }
 
@@ -133,18 +279,40 @@ int rbl_query_memory(int device, int64_t* free_bytes, int64_t* total_bytes) {
     });
 }
 
-int rbl_buffer_blocks(rbl_handle* h, int64_t b, int64_t* blocks_out) {
+int rbl_plan_blocks(rbl_handle* h, int64_t k, int64_t b, int64_t* blocks_out) {
     return guarded([&] {
-        if (!h || !blocks_out || b < 1 || b > 32) throw Error(RBL_INVALID, "rbl_buffer_blocks: bad arguments");
-        RBL_CUDA(cudaSetDevice(h->device));
-        size_t f = 0, t = 0;
-        RBL_CUDA(cudaMemGetInfo(&f, &t));
-        const int B = padded_block((int)b);
-        const size_t ssz = h->opt.precision == RBL_PRECISION_MIXED ? 4 : 8;
-        const double fixed = 3.0 * (double)(h->nloc + h->n_halo) * B * 8 + (double)((size_t)64 << 20);
-        const double per_block = (double)h->nloc * B * ssz + (double)B * 2 * B * ssz;
-        double fit = (0.92 * (double)f - fixed) / per_block;
-        *blocks_out = fit > 0 ? (int64_t)fit : 0;
+        if (!h || !blocks_out || b < 1 || b > 32 || k < 0) throw Error(RBL_INVALID, "rbl_plan_blocks: bad arguments");
+        rbl_handle* hh = h->parts.empty() ? h : h->parts[0];
+        RBL_CUDA(cudaSetDevice(hh->device));
+        MemPlan p = plan_memory(hh, k, (int)b, hh->n / b + 1);   // a Krylov basis never exceeds n columns
+        *blocks_out = p.m_fit > 0 ? p.m_fit : 0;
+        return (int)RBL_OK;
+    });
+}
+int rbl_buffer_blocks(rbl_handle* h, int64_t b, int64_t* blocks_out) { return rbl_plan_blocks(h, 0, b, blocks_out); }
+
+int rbl_krylov_info(rbl_handle* h, int64_t* blocks_out, int64_t* b_out) {
+    return guarded([&] {
+        if (!h) throw Error(RBL_INVALID, "rbl_krylov_info: null handle");
+        if (!h->parts.empty()) throw Error(RBL_INVALID, "rbl_krylov_info: single-GPU handles only");
+        if (blocks_out) *blocks_out = h->last.blocks;
+        if (b_out) *b_out = h->last.b;
+        return (int)RBL_OK;
+    });
+}
+int rbl_krylov_block(rbl_handle* h, int64_t j, double* out_colmajor) {
+    return guarded([&] {
+        if (!h || !out_colmajor) throw Error(RBL_INVALID, "rbl_krylov_block: bad arguments");
+        if (!h->parts.empty() || h->world != 1) throw Error(RBL_INVALID, "rbl_krylov_block: single-GPU handles only");
+        krylov_block(h, j, out_colmajor);
+        return (int)RBL_OK;
+    });
+}
+int rbl_orthogonality(rbl_handle* h, double* max_abs_out, double* fro_out) {
+    return guarded([&] {
+        if (!h) throw Error(RBL_INVALID, "rbl_orthogonality: null handle");
+        if (!h->parts.empty()) throw Error(RBL_INVALID, "rbl_orthogonality: per-rank handles only");
+        orthogonality(h, max_abs_out, fro_out);
         return (int)RBL_OK;
     });
 }
@@ -153,7 +321,7 @@ int rbl_buffer_blocks(rbl_handle* h, int64_t b, int64_t* blocks_out) {
 int rbl_spmm(rbl_handle* h, int64_t b, const double* q, double* u) {
     return guarded([&] {
         if (!h || !q || !u || b < 1 || b > 32) throw Error(RBL_INVALID, "rbl_spmm: bad arguments");
-        if (h->world != 1) throw Error(RBL_INVALID, "rbl_spmm: single-GPU handles only");
+        if (h->world != 1 || !h->parts.empty()) throw Error(RBL_INVALID, "rbl_spmm: single-GPU handles only");
         RBL_CUDA(cudaSetDevice(h->device));
         const int B = padded_block((int)b);
         const int64_t n = h->nloc;
@@ -164,7 +332,8 @@ int rbl_spmm(rbl_handle* h, int64_t b, const double* q, double* u) {
         dq.alloc(qp.size());
         du.alloc(up.size());
         RBL_CUDA(cudaMemcpy(dq.p, qp.data(), qp.size() * 8, cudaMemcpyHostToDevice));
-        launch_spmm(B, n, h->wsp->d_rowptr.p, h->wsp->d_colidx.p, h->wsp->d_vals.p, dq.p, du.p, h->opt.op, h->opt.sigma, h->stream);
+        const SpmmCoef cf = (h->opt.op == RBL_OP_SHIFT_MINUS_A) ? SpmmCoef{-1.0, h->opt.sigma, 0.0} : SpmmCoef{1.0, 0.0, 0.0};
+        launch_spmm(B, n, h->wsp->d_rowptr.p, h->wsp->d_colidx.p, h->wsp->d_vals.p, dq.p, du.p, cf, nullptr, h->stream);
         RBL_CUDA(cudaStreamSynchronize(h->stream));
         RBL_CUDA(cudaMemcpy(up.data(), du.p, up.size() * 8, cudaMemcpyDeviceToHost));
         for (int64_t r = 0; r < n; ++r)
@@ -261,9 +430,9 @@ int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qb
         need_device();
         if (!qbuf || !w0 || !w1 || b < 1 || b > 32 || n < 1 || m < 1) throw Error(RBL_INVALID, "rbl_reorth: bad arguments");
         const int B = padded_block((int)b);
-        const bool tc = impl != 1 && reorth_tc_supported(B, storage_fp32);
-        const bool hs = impl != 1 && impl != 2 && reorth_h_supported(B, storage_fp32);
-        if ((impl == 2 && !tc) || (impl >= 3 && !hs)) throw Error(RBL_INVALID, "rbl_reorth: tensor-core path needs fp32 storage and padded block size 16");
+        const bool hs = impl != 1 && reorth_h_supported(B, storage_fp32);
+        if (impl == 2) throw Error(RBL_INVALID, "rbl_reorth: impl 2 (3xTF32) was removed");
+        if (impl >= 3 && !hs) throw Error(RBL_INVALID, "rbl_reorth: tensor-core path needs fp32 storage and padded block size 16 or 32");
         const size_t ssz = storage_fp32 ? 4 : 8;
         // pad the stored blocks
         std::vector<unsigned char> hb((size_t)m * n * B * ssz, 0);
@@ -301,12 +470,6 @@ int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qb
             launch_reorth_gram_h(p, n, slab, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, scratch.p, m, presplit, 0);
             launch_reorth_coeff_h(p, dC.p, scratch.p, m, 0, 0);
             launch_reorth_update_h(p, n, slab, n * B, W0.dev.p, W1.dev.p, nullptr, scratch.p, m, presplit, 0);
-            RBL_CUDA(cudaDeviceSynchronize());
-        } else if (tc) {
-            DevBuf<float> scratch;
-            scratch.alloc(reorth_tc_scratch_floats(B, n, m));
-            launch_reorth_gram_tc(p, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, scratch.p, m, 0);
-            launch_reorth_update_tc(p, dbuf.p, n * B, W0.dev.p, W1.dev.p, nullptr, scratch.p, m, 0);
             RBL_CUDA(cudaDeviceSynchronize());
         } else {
             launch_reorth_gram(p, dbuf.p, n * B, W0.dev.p, W1.dev.p, dpart.p, dC.p, 0);

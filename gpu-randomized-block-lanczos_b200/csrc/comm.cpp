@@ -85,9 +85,11 @@ bool Comm::unique_id(void* uid128, std::string& err) {
 
 namespace {
 // Communicators are expensive to create (ncclCommInitRank is a collective of ~1 s); a destroyed handle parks
-// its communicator here and the next handle with the same (device, rank, world) reuses it.  Every rank of a
-// job takes the same decision because every rank created and parked the same communicators in the same order.
-struct Parked { int device, rank, world; void* comm; };
+// its communicator here and a later handle reuses it ONLY when it presents the same 128-byte unique id (and
+// device, rank, world): the id names the group, so a different group - or a group re-formed after a peer
+// restarted, which must come with a fresh id - never picks up a stale communicator.  Callers that want the
+// reuse keep one id per group (bench.py, the single-process group handles in capi.cu).
+struct Parked { int device, rank, world; char uid[128]; void* comm; };
 std::mutex g_comm_mu;
 std::vector<Parked> g_parked;
 }  // namespace
@@ -97,13 +99,17 @@ bool Comm::init(const void* uid128, int rank_, int world_, std::string& err) {
     world = world_;
     if (world <= 1) return true;
     if (!ready(err)) return false;
+    if (!uid128) { err = "null NCCL unique id"; return false; }
     int dev = 0;
     cudaGetDevice(&dev);
     device_ = dev;
+    std::memcpy(uid_, uid128, 128);
+    failed_ = false;
     {
         std::lock_guard<std::mutex> lk(g_comm_mu);
         for (size_t i = 0; i < g_parked.size(); ++i)
-            if (g_parked[i].device == dev && g_parked[i].rank == rank && g_parked[i].world == world) {
+            if (g_parked[i].device == dev && g_parked[i].rank == rank && g_parked[i].world == world &&
+                std::memcmp(g_parked[i].uid, uid_, 128) == 0) {
                 comm_ = g_parked[i].comm;
                 g_parked.erase(g_parked.begin() + i);
                 return true;
@@ -111,13 +117,25 @@ bool Comm::init(const void* uid128, int rank_, int world_, std::string& err) {
     }
     nccl_uid_t id;
     std::memcpy(&id, uid128, sizeof(id));
-    return ok(api().CommInitRank(&comm_, world, id, rank), "CommInitRank", err);
+    return check(api().CommInitRank(&comm_, world, id, rank), "CommInitRank", err);
+}
+
+bool Comm::check(int rc, const char* what, std::string& err) {
+    if (ok(rc, what, err)) return true;
+    failed_ = true;
+    return false;
 }
 
 void Comm::destroy() {
     if (comm_) {
-        std::lock_guard<std::mutex> lk(g_comm_mu);
-        g_parked.push_back(Parked{device_, rank, world, comm_});
+        if (failed_) {
+            api().CommDestroy(comm_);   // never re-park a communicator that reported an error
+        } else {
+            std::lock_guard<std::mutex> lk(g_comm_mu);
+            Parked p{device_, rank, world, {0}, comm_};
+            std::memcpy(p.uid, uid_, 128);
+            g_parked.push_back(p);
+        }
     }
     comm_ = nullptr;
 }
@@ -130,25 +148,25 @@ void Comm::release_cached() {
 
 bool Comm::allreduce_f64(double* buf, size_t count, cudaStream_t st, std::string& err) {
     if (!active() || count == 0) return true;
-    return ok(api().AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, comm_, st), "AllReduce", err);
+    return check(api().AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, comm_, st), "AllReduce", err);
 }
 bool Comm::allreduce_f32(float* buf, size_t count, cudaStream_t st, std::string& err) {
     if (!active() || count == 0) return true;
-    return ok(api().AllReduce(buf, buf, count, kNcclFloat32, kNcclSum, comm_, st), "AllReduce", err);
+    return check(api().AllReduce(buf, buf, count, kNcclFloat32, kNcclSum, comm_, st), "AllReduce", err);
 }
 bool Comm::allgather_i64(const int64_t* send, int64_t* recv, size_t count_per_rank, cudaStream_t st, std::string& err) {
     if (!active()) return true;
-    return ok(api().AllGather(send, recv, count_per_rank, kNcclInt64, comm_, st), "AllGather", err);
+    return check(api().AllGather(send, recv, count_per_rank, kNcclInt64, comm_, st), "AllGather", err);
 }
-bool Comm::group_start(std::string& err) { return !active() || ok(api().GroupStart(), "GroupStart", err); }
-bool Comm::group_end(std::string& err) { return !active() || ok(api().GroupEnd(), "GroupEnd", err); }
+bool Comm::group_start(std::string& err) { return !active() || check(api().GroupStart(), "GroupStart", err); }
+bool Comm::group_end(std::string& err) { return !active() || check(api().GroupEnd(), "GroupEnd", err); }
 bool Comm::send_bytes(const void* buf, size_t bytes, int peer, cudaStream_t st, std::string& err) {
     if (!active() || bytes == 0) return true;
-    return ok(api().Send(buf, bytes, kNcclInt8, peer, comm_, st), "Send", err);
+    return check(api().Send(buf, bytes, kNcclInt8, peer, comm_, st), "Send", err);
 }
 bool Comm::recv_bytes(void* buf, size_t bytes, int peer, cudaStream_t st, std::string& err) {
     if (!active() || bytes == 0) return true;
-    return ok(api().Recv(buf, bytes, kNcclInt8, peer, comm_, st), "Recv", err);
+    return check(api().Recv(buf, bytes, kNcclInt8, peer, comm_, st), "Recv", err);
 }
 
 }  // namespace rbl

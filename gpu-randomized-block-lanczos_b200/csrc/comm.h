@@ -27,8 +27,11 @@ public:
     bool recv_bytes(void* buf, size_t bytes, int peer, cudaStream_t st, std::string& err);
 
 private:
+    bool check(int rc, const char* what, std::string& err);
     void* comm_ = nullptr;
     int device_ = 0;
+    char uid_[128] = {0};
+    bool failed_ = false;
 };
 
 }  // namespace rbl

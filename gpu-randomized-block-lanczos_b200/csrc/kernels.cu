@@ -46,8 +46,8 @@ static void dispatch_B(int B, F&& f) {
 template <int B>
 __global__ void __launch_bounds__(256) spmm_kernel(int64_t nrows, const int* __restrict__ rowptr,
                                                    const int* __restrict__ colidx, const double* __restrict__ vals,
-                                                   const double* __restrict__ Q, double* __restrict__ U, int op,
-                                                   double sigma) {
+                                                   const double* __restrict__ Q, double* U, SpmmCoef cf,
+                                                   const double* Z) {
     constexpr int LPR = B / 2;
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31;
@@ -80,17 +80,24 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t nrows, const int* __r
             const double2 q0 = __ldg(Q2 + (size_t)c0 * LPR + sub);
             acc.x = fma(v0, q0.x, acc.x); acc.y = fma(v0, q0.y, acc.y);
         }
-        if (op == 1) {
+        acc.x *= cf.alpha;
+        acc.y *= cf.alpha;
+        if (cf.beta != 0.0) {
             const double2 q = __ldg(Q2 + (size_t)row * LPR + sub);
-            acc.x = fma(sigma, q.x, -acc.x);
-            acc.y = fma(sigma, q.y, -acc.y);
+            acc.x = fma(cf.beta, q.x, acc.x);
+            acc.y = fma(cf.beta, q.y, acc.y);
+        }
+        if (cf.gamma != 0.0) {
+            const double2 z = reinterpret_cast<const double2*>(Z)[(size_t)row * LPR + sub];
+            acc.x = fma(cf.gamma, z.x, acc.x);
+            acc.y = fma(cf.gamma, z.y, acc.y);
         }
         reinterpret_cast<double2*>(U)[(size_t)row * LPR + sub] = acc;
     }
 }
 
 void launch_spmm(int B, int64_t nrows, const int* rowptr, const int* colidx, const double* vals, const double* Q,
-                 double* U, int op, double sigma, cudaStream_t st) {
+                 double* U, SpmmCoef cf, const double* Z, cudaStream_t st) {
     if (nrows <= 0) return;
     dispatch_B(B, [&](auto bc) {
         constexpr int BB = decltype(bc)::value;
@@ -98,7 +105,7 @@ void launch_spmm(int B, int64_t nrows, const int* rowptr, const int* colidx, con
         int64_t rows_per_cta = (int64_t)RPW * 8;
         int64_t want = (nrows + rows_per_cta - 1) / rows_per_cta;
         int grid = (int)std::min<int64_t>(want, (int64_t)num_sms() * 16);
-        spmm_kernel<BB><<<grid, 256, 0, st>>>(nrows, rowptr, colidx, vals, Q, U, op, sigma);
+        spmm_kernel<BB><<<grid, 256, 0, st>>>(nrows, rowptr, colidx, vals, Q, U, cf, Z);
     });
 }
 
@@ -598,6 +605,11 @@ ReorthPlan reorth_plan(int B, int fp32, int64_t n, int64_t m) {
     int64_t target_ctas = (int64_t)num_sms() * 16;  // >= 8 waves of 1-CTA/SM kernels: short tail
     int64_t ranges = (target_ctas + p.chunks - 1) / p.chunks;
     int64_t max_ranges = std::max<int64_t>(1, n / 256);
+    static const int64_t rows_override = [] { const char* e = std::getenv("RBL_GRAM_ROWS"); return e ? std::atoll(e) : 0ll; }();
+    if (rows_override > 0) {   // experiment knob: rows per range (accumulation chain length of the Gram kernels)
+        ranges = (n + rows_override - 1) / rows_override;
+        max_ranges = std::max<int64_t>(1, n / 64);
+    }
     ranges = std::max<int64_t>(1, std::min<int64_t>(ranges, max_ranges));
     ranges = std::min<int64_t>(ranges, 65535);
     p.ranges = (int)ranges;
@@ -1012,6 +1024,105 @@ void launch_load_block(int B, int64_t n, const void* src, int fp32, double* dst,
     int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)num_sms() * 16);
     if (fp32) widen_kernel<float><<<grid, 256, 0, st>>>(count, (const float*)src, dst);
     else widen_kernel<double><<<grid, 256, 0, st>>>(count, (const double*)src, dst);
+}
+
+__global__ void decode_split_kernel(int B, int64_t rows, const unsigned* __restrict__ src, double* __restrict__ dst,
+                                    float inv_scale) {
+    const int hb = B / 2;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one column pair per thread
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < rows * hb; i += stride) {
+        const int64_t r = i / hb;
+        const int p = (int)(i % hb);
+        const float2 x = join_h2(src[r * B + p], src[r * B + hb + p], inv_scale);
+        dst[r * B + 2 * p] = (double)x.x;
+        dst[r * B + 2 * p + 1] = (double)x.y;
+    }
+}
+void launch_decode_block(int B, int64_t n, const void* src, int fp32, float split_scale, double* dst, cudaStream_t st) {
+    if (n <= 0) return;
+    if (fp32 && split_scale != 0.f) {
+        int grid = (int)std::min<int64_t>((n * (B / 2) + 255) / 256, (int64_t)num_sms() * 16);
+        decode_split_kernel<<<grid, 256, 0, st>>>(B, n, (const unsigned*)src, dst, 1.0f / split_scale);
+        return;
+    }
+    launch_load_block(B, n, src, fp32, dst, st);
+}
+
+// orthogonality loss accumulation (see kernels.h); one thread per coefficient
+template <typename S>
+__global__ void ortho_accumulate_kernel(int B, int64_t m, int64_t j0, int ntargets, const S* __restrict__ C,
+                                        double* __restrict__ out) {
+    const int64_t total = m * B * 2 * B;
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double mx = 0.0, ss = 0.0;
+    for (; e < total; e += stride) {
+        const int64_t row = e / (2 * B);
+        const int t = (int)(e % (2 * B));
+        if (t / B >= ntargets) continue;
+        double v = (double)C[e];
+        if (row == (j0 + t / B) * B + (t % B)) {
+            // diagonal: a deflated / padded column is exactly zero in the slab (q'q == 0): not part of the basis
+            if (v == 0.0) continue;
+            v -= 1.0;
+        }
+        mx = fmax(mx, fabs(v));
+        ss += v * v;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out + 1, ss);
+        // non-negative doubles order like their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(mx));
+    }
+}
+void launch_ortho_accumulate(int B, int64_t m, int64_t j0, int ntargets, int fp32, const void* C, double* out,
+                             cudaStream_t st) {
+    if (m <= 0) return;
+    const int64_t total = m * B * 2 * B;
+    int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 8);
+    if (fp32) ortho_accumulate_kernel<float><<<grid, 256, 0, st>>>(B, m, j0, ntargets, (const float*)C, out);
+    else ortho_accumulate_kernel<double><<<grid, 256, 0, st>>>(B, m, j0, ntargets, (const double*)C, out);
+}
+
+// per-column dots of column-major matrices: grid.y = column, grid.x strides over rows
+__global__ void col_dots_kernel(int64_t n, int k, const double* __restrict__ V, const double* __restrict__ W, int64_t ld,
+                                double* __restrict__ out) {
+    const int c = blockIdx.y;
+    const double* v = V + (size_t)c * ld;
+    const double* w = W + (size_t)c * ld;
+    double vv = 0.0, vw = 0.0, ww = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const double a = v[r], b = w[r];
+        vv = fma(a, a, vv);
+        vw = fma(a, b, vw);
+        ww = fma(b, b, ww);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        vv += __shfl_xor_sync(0xffffffffu, vv, off);
+        vw += __shfl_xor_sync(0xffffffffu, vw, off);
+        ww += __shfl_xor_sync(0xffffffffu, ww, off);
+    }
+    __shared__ double red[3][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = vv; red[1][warp] = vw; red[2][warp] = ww; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[threadIdx.x][i];
+        atomicAdd(out + (size_t)threadIdx.x * k + c, s);
+    }
+}
+void launch_col_dots(int64_t n, int k, const double* V, const double* W, int64_t ld, double* out3k, cudaStream_t st) {
+    if (n <= 0 || k <= 0) return;
+    dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 64), (unsigned)k);
+    col_dots_kernel<<<grid, 256, 0, st>>>(n, k, V, W, ld, out3k);
 }
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {

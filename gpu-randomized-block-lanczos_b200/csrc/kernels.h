@@ -27,10 +27,16 @@ struct PerDeviceOnce {
 inline int padded_block(int b) { return b <= 4 ? 4 : (b <= 8 ? 8 : (b <= 16 ? 16 : 32)); }
 
 // ---- K1 block SpMM ------------------------------------------------------------------------------
-// U[r,:] = sum_p vals[p] * Q[colidx[p],:]   (op 0)      replaces mul!(U,Ag,Qg_d)  RBL_gpu.jl:152,176
-// U[r,:] = sigma*Q[r,:] - (that sum)        (op 1)
+// U[r,:] = alpha * sum_p vals[p] * Q[colidx[p],:] + beta * Q[r,:] + gamma * Z[r,:]
+//   alpha = 1, beta = gamma = 0          replaces mul!(U,Ag,Qg_d)  RBL_gpu.jl:152,176
+//   alpha = -1, beta = sigma             the shifted operator sigma*I - A
+//   general                              one step of the Chebyshev three-term recurrence of the filtered operator
+// Z may alias U (it is read and written row by row by the same thread); Z == nullptr when gamma == 0.
+struct SpmmCoef {
+    double alpha = 1.0, beta = 0.0, gamma = 0.0;
+};
 void launch_spmm(int B, int64_t nrows, const int* rowptr, const int* colidx, const double* vals, const double* Q,
-                 double* U, int op, double sigma, cudaStream_t st);
+                 double* U, SpmmCoef cf, const double* Z, cudaStream_t st);
 
 // ---- K2/K3/K4 fused row-wise block operations on fp64 blocks --------------------------------------
 // For every row r of Y (n x B, fp64):
@@ -97,17 +103,6 @@ void launch_reorth_gram_reduce(const ReorthPlan& p, const void* partials, void* 
 void launch_reorth_update(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, const void* C, double* w0,
                           double* w1, void* store_w1, cudaStream_t st);
 
-// tensor-core (3xTF32 mma.sync + cp.async pipelines) variants of K5, fp32 buffer, B = 16 (reorth_tc.cu).
-// `scratch` holds the tf32 hi/lo parts of the targets and of the coefficients (reorth_tc_scratch_floats).
-bool reorth_tc_supported(int B, int fp32);
-size_t reorth_tc_scratch_floats(int B, int64_t n, int64_t m_cap);
-void launch_reorth_gram_tc(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, const double* w0,
-                           const double* w1, void* partials, void* C, float* scratch, int64_t m_cap, cudaStream_t st);
-// after an all-reduce of C: recompute the coefficient hi/lo parts from C (ranges must be 1, partials = C)
-void launch_reorth_gram_tc_resplit(const ReorthPlan& p, void* C, float* scratch, int64_t m_cap, cudaStream_t st);
-void launch_reorth_update_tc(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, double* w0, double* w1,
-                             void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st);
-
 // scaled two-term FP16 split on mma.sync m16n8k16 (reorth_tc16.cu): same interface, half the tensor-pipe time.
 // `n_global` fixes the power-of-two operand scale (orthonormal columns of global length n_global).
 bool reorth_h_supported(int B, int fp32);   // fp32 buffer, B = 16 or 32
@@ -150,6 +145,17 @@ void launch_store_block(int B, int64_t n, const double* src, void* dst, int fp32
 // fp32 rows -> split16 rows (out of place)
 void launch_encode_split(int B, int64_t rows, const float* src, void* dst, float scale, cudaStream_t st);
 void launch_load_block(int B, int64_t n, const void* src, int fp32, double* dst, cudaStream_t st);
+// slab block (fp64 / fp32 / split16 when split_scale != 0) -> fp64 row-major block
+void launch_decode_block(int B, int64_t n, const void* src, int fp32, float split_scale, double* dst, cudaStream_t st);
+// Orthogonality loss of the Krylov basis: C is the (m*B) x 2B coefficient matrix of a Gram pass whose targets are the
+// decoded stored blocks j0 and j0+1 (ntargets = 1: only j0), so the exact answer is delta = 1 at
+// (row (j0 + t/B)*B + t%B, column t).  Accumulates out[0] = max |C - delta|, out[1] = sum (C - delta)^2 over calls
+// (zero `out` first).  Rows / columns of padded or deflated (all-zero) columns are skipped via `skip` (m*B flags).
+void launch_ortho_accumulate(int B, int64_t m, int64_t j0, int ntargets, int fp32, const void* C, double* out,
+                             cudaStream_t st);
+// per-column dot products of two column-major n x k matrices (ld): out[c] = v_c'v_c, out[k+c] = v_c'w_c,
+// out[2k+c] = w_c'w_c (accumulated with atomics: zero `out` first).  Rayleigh quotients / residuals of Ritz vectors.
+void launch_col_dots(int64_t n, int k, const double* V, const double* W, int64_t ld, double* out3k, cudaStream_t st);
 void launch_randn(int64_t count, uint64_t seed, uint64_t offset, double* dst, cudaStream_t st);
 void launch_convert_s(int64_t count, const double* src, void* dst, int fp32, cudaStream_t st);
 void launch_gather_rows(int B, int64_t nrows, const int* rows, const double* src, double* dst, cudaStream_t st);

@@ -61,6 +61,37 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], const unsigned (&a)[4], c
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+
+// ---- tensor memory (TMEM) as the second accumulation level of the Gram kernel --------------------------------
+// mma.sync accumulates in fp32 with truncation, so the error of an accumulator grows linearly with the length of its
+// chain (measured, tools/reorth_accuracy.py: 256-row chains 1.4x, 1024-row chains 4.9x the error of an fp32 sgemm).
+// Every GRAM_FLUSH k-steps each warp therefore adds its MMA accumulators, with round-to-nearest FADDs, to running sums
+// and restarts the chain from zero.  The sums live in TMEM (256 KB per SM, otherwise unused by this kernel): neither the
+// register file (106 of 128 registers in use) nor shared memory (180 KB of stages) has room for a second accumulator set.
+// A warp reaches lanes [32 (warp % 4), +32) of TMEM; the four warps that share a lane quarter use different columns.
+__device__ __forceinline__ void tmem_alloc(unsigned* smem_dst, unsigned ncols) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(d), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, unsigned (&r)[8]) {   // issue only: tmem_wait_ld() before use
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const unsigned (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
 }  // namespace
 
 // ---- targets: row-pair interleaved f16x2 words  Wp[(r/2) * 2B + t] = (W[r][t], W[r+1][t]) ----------------
@@ -107,6 +138,9 @@ struct GramH {
     static constexpr int WBUF = (RW / 2) * PW;   // words per target buffer (hi or lo)
     static constexpr int NCP = (WB * RS * (B / 4)) / 32;  // cp.async per lane per stage
     static constexpr size_t smem_bytes = (size_t)(NW * NST * STAGE + 4 * WBUF) * sizeof(float);
+    static constexpr int NACC = WB * MT * NT * 4;   // fp32 accumulators per thread
+    static constexpr int TCOLS = 4 * NACC;          // TMEM columns: four warps per lane quarter
+    static constexpr int FLUSH = 8;                 // k-steps (of RS rows) per tensor-core accumulation chain
 };
 
 // Shared-memory slot of element (row r of a 16-row stage, column c) of a stored block, in floats.
@@ -150,6 +184,50 @@ __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
             for (int x = 0; x < NT; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y) acc[b][a][x][y] = 0.f;
+
+    // second-level sums in tensor memory (see tmem_* above)
+    constexpr int NACC = C::NACC;
+    static_assert(NACC % 16 == 0 && (C::TCOLS & (C::TCOLS - 1)) == 0 && C::TCOLS >= 32 && C::TCOLS <= 512, "TMEM slice shape");
+    __shared__ unsigned tmem_base_sh;
+    if (warp == 0) tmem_alloc(&tmem_base_sh, C::TCOLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const unsigned tsum = tmem_base_sh + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * NACC;
+    {
+        const unsigned z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int c0 = 0; c0 < NACC; c0 += 8) tmem_st8(tsum + c0, z);
+        tmem_wait_st();
+    }
+    // sums += acc (round to nearest); acc = 0, or (last) acc = sums.  16 sums are in flight per TMEM round trip.
+    auto flush = [&](bool last) {
+        float* af = &acc[0][0][0][0];
+#pragma unroll
+        for (int c0 = 0; c0 < NACC; c0 += 16) {
+            unsigned sa[8], sb[8];
+            tmem_ld8(tsum + c0, sa);
+            tmem_ld8(tsum + c0 + 8, sb);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                sa[e] = __float_as_uint(__uint_as_float(sa[e]) + af[c0 + e]);
+                sb[e] = __float_as_uint(__uint_as_float(sb[e]) + af[c0 + 8 + e]);
+            }
+            if (last) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    af[c0 + e] = __uint_as_float(sa[e]);
+                    af[c0 + 8 + e] = __uint_as_float(sb[e]);
+                }
+            } else {
+                tmem_st8(tsum + c0, sa);
+                tmem_st8(tsum + c0 + 8, sb);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) af[c0 + e] = 0.f;
+            }
+        }
+    };
 
     if (nrows > 0) {
         const int nks = (int)((nrows + RS - 1) / RS);
@@ -265,9 +343,19 @@ __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
                     }
                 }
             }
+            // the warps flush in turn (two per k-step): the TMEM round trips of one warp hide behind the MMAs of the others
+            if ((ks + 1 + warp) % C::FLUSH == 0 && ks + 1 < nks) {
+                tmem_wait_st();   // the stores of this warp's previous flush (issued FLUSH k-steps ago)
+                flush(false);
+            }
         }
         cp_async_wait<0>();
+        tmem_wait_st();
+        flush(true);
     }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_sh, C::TCOLS);
 #pragma unroll
     for (int b = 0; b < WB; ++b) {
         const int64_t j = jbase + b;

@@ -1,26 +1,37 @@
 // Device-resident RBL driver.  Reference restated by structure, not by call sequence:
 //   handle_create   <- Ag = adapt(CuArray, A)                         RBL_gpu.jl:209
 //   solve           <- RBL_gpu body + lanczos_iteration               RBL_gpu.jl:134-203, 211-220
-//   ritz            <- recover_eigvec                                 RBL_gpu.jl:106-132
+//   Run::ritz       <- recover_eigvec                                 RBL_gpu.jl:106-132
+//   Run::restart    <- RBL_gpu_restarted / lanczos_iteration_res      restarted.jl:23-146 (generalised, see below)
 // Differences by design: no per-statement synchronisation (the only host waits
 // are the convergence checks), Krylov buffer is one slab written by kernel epilogues (no F<->D copy
 // kernels, no per-block host mirror), full re-orthogonalisation is two streaming passes (block CGS)
 // over the slab instead of 4 small GEMMs + a sync per stored block, block QR is shifted CholQR with
 // re-orthogonalisation instead of Householder geqrf/orgqr, and the host eigen-check computes only the
 // k wanted Ritz pairs and may overlap the device iteration.
+//
+// Restart / filter (CPU twin: oracle/rbl_restart_oracle.py):
+//   * the slab holds [locked Ritz vectors (whole blocks) | Krylov blocks of the current cycle]; the K5 kernels
+//     stream both, so every reorth pass also enforces orthogonality against the locked vectors
+//     (restart_reorth_gpu!, restarted.jl:1-21,:40,:58-59);
+//   * when the cap is reached: every wanted pair whose residual bound passed is locked (restarted.jl:122-131),
+//     the best b others form the restart block (:133-135);
+//   * with opts.filter_degree the cycles iterate with p(op(A)) = rho T_d((op(A) - c)/e); eigenvalues are
+//     recovered as Rayleigh quotients with op(A) and the true residuals are measured on the device.
 #include "solver.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
-#include <condition_variable>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
-#include <atomic>
 #include <cstring>
 #include <future>
 #include <memory>
 #include <mutex>
+#include <numeric>
 #include <thread>
 
 #include "partition.h"
@@ -31,9 +42,14 @@ namespace rbl {
 namespace {
 std::mutex g_ws_mu;
 std::vector<std::pair<int, Workspace*>> g_parked_ws;  // (device, workspace)
-size_t ws_bytes(const Workspace& w) {
+size_t solve_bytes(const Workspace& w) {
+    size_t x = 0;
+    for (int i = 0; i < 4; ++i) x += w.X[i].count;
     return w.buf.count + w.ritzV.count + w.ritzS.count + w.Cmat.count + w.rpart.count + w.tc_scratch.count * 4 +
-           (w.X[0].count + w.X[1].count + w.X[2].count + w.omega.count + w.part.count + w.sendbuf.count) * 8;
+           w.ritz_words.count * 4 + (x + w.omega.count + w.part.count + w.small.count + w.sendbuf.count + w.Vacc.count) * 8;
+}
+size_t ws_bytes(const Workspace& w) {
+    return solve_bytes(w) + (w.d_rowptr.count + w.d_colidx.count + w.d_send_rows.count) * 4 + w.d_vals.count * 8;
 }
 }  // namespace
 Workspace* workspace_take(int device) {
@@ -72,6 +88,9 @@ void slab_cache_release_all() {
 }  // namespace rbl
 
 rbl_handle::~rbl_handle() {
+    for (rbl_handle* p : parts) delete p;
+    parts.clear();
+    if (!wsp) return;
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     rbl::workspace_park(device, wsp);
@@ -101,6 +120,13 @@ void default_options(rbl_options* o) {
     o->v_fp32 = 0;
     o->verbose = 0;
     o->reorth_impl = 0;
+    o->seed = 0;
+    o->ngpus = 1;
+    o->filter_degree = 0;   // the reference iterates with the operator itself
+    o->restart = 0;         // RBL_gpu gives up at the cap (RBL_gpu.jl:162); restarted.jl is a separate entry
+    o->spill = 0;
+    o->probe_steps = 0;
+    o->mem_limit_mb = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ create
@@ -136,6 +162,19 @@ rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, co
         rp[r] = (int)v;
     }
     const int64_t* cidx = colidx;  // entries of the first local row start at colidx[0]
+    // Gershgorin interval of A (rigorous spectrum bounds; places the damped interval of the Chebyshev filter)
+    double glo = 1e300, ghi = -1e300;
+    for (int64_t r = 0; r < nloc; ++r) {
+        double d = 0.0, off = 0.0;
+        const int64_t gr = row0 + r;
+        for (int p = rp[r]; p < rp[r + 1]; ++p) {
+            const int64_t c = cidx[p] - index_base;
+            if (c == gr) d += vals[p]; else off += std::fabs(vals[p]);
+        }
+        glo = std::min(glo, d - off);
+        ghi = std::max(ghi, d + off);
+    }
+    if (nloc == 0) { glo = 0.0; ghi = 0.0; }
     if (world <= 1) {
         for (int64_t p = 0; p < nnz; ++p) {
             int64_t c = cidx[p] - index_base;
@@ -147,22 +186,28 @@ rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, co
         std::string err;
         if (!h->comm.init(nccl_uid, rank, world, err)) throw Error(RBL_NCCL_ERROR, err);
         std::vector<int64_t> starts((size_t)world + 1);
-        // all ranks must use the same partition: gather every rank's row0 via NCCL
+        // all ranks must use the same partition: gather every rank's row0 (and Gershgorin bounds) via NCCL
         DevBuf<int64_t> d_send, d_recv;
-        d_send.alloc(2);
-        d_recv.alloc((size_t)2 * world);
-        int64_t mine[2] = {row0, nloc};
+        d_send.alloc(4);
+        d_recv.alloc((size_t)4 * world);
+        int64_t mine[4] = {row0, nloc, 0, 0};
+        std::memcpy(&mine[2], &glo, 8);
+        std::memcpy(&mine[3], &ghi, 8);
         RBL_CUDA(cudaMemcpyAsync(d_send.p, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
-        if (!h->comm.allgather_i64(d_send.p, d_recv.p, 2, h->stream, err)) throw Error(RBL_NCCL_ERROR, err);
-        std::vector<int64_t> all((size_t)2 * world);
+        if (!h->comm.allgather_i64(d_send.p, d_recv.p, 4, h->stream, err)) throw Error(RBL_NCCL_ERROR, err);
+        std::vector<int64_t> all((size_t)4 * world);
         RBL_CUDA(cudaMemcpyAsync(all.data(), d_recv.p, all.size() * 8, cudaMemcpyDeviceToHost, h->stream));
         RBL_CUDA(cudaStreamSynchronize(h->stream));
         for (int p = 0; p < world; ++p) {
-            starts[p] = all[2 * p];
-            if (p > 0 && starts[p] != all[2 * (p - 1)] + all[2 * (p - 1) + 1])
+            starts[p] = all[4 * p];
+            if (p > 0 && starts[p] != all[4 * (p - 1)] + all[4 * (p - 1) + 1])
                 throw Error(RBL_INVALID, "rbl_create_sharded: row ranges are not contiguous in rank order");
+            double lo, hi;
+            std::memcpy(&lo, &all[4 * p + 2], 8);
+            std::memcpy(&hi, &all[4 * p + 3], 8);
+            if (all[4 * p + 1] > 0) { glo = std::min(glo, lo); ghi = std::max(ghi, hi); }
         }
-        starts[world] = all[2 * (world - 1)] + all[2 * (world - 1) + 1];
+        starts[world] = all[4 * (world - 1)] + all[4 * (world - 1) + 1];
         if (starts[0] != 0 || starts[world] != n) throw Error(RBL_INVALID, "rbl_create_sharded: ranges do not cover [0,n)");
         HaloPlan plan;
         if (!halo_plan(n, world, starts.data(), rank, nloc, nnz, rowptr, colidx, index_base, plan))
@@ -210,6 +255,8 @@ rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, co
         h->wsp->d_send_rows.ensure(std::max<int64_t>(1, nsend));
         if (nsend) RBL_CUDA(cudaMemcpy(h->wsp->d_send_rows.p, send_rows.data(), nsend * sizeof(int), cudaMemcpyHostToDevice));
     }
+    h->gersh_lo = glo;
+    h->gersh_hi = ghi;
     h->wsp->d_rowptr.ensure((size_t)nloc + 1);
     h->wsp->d_colidx.ensure(std::max<int64_t>(1, nnz));
     h->wsp->d_vals.ensure(std::max<int64_t>(1, nnz));
@@ -220,6 +267,51 @@ rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, co
     }
     h->t_h2d_create = now_s() - t0;
     return h.release();
+}
+
+// ------------------------------------------------------------------------------------------------ memory plan
+// gpu_buffer_size (RBL_gpu.jl:95-104): how many Krylov blocks of width b fit, given everything else a solve of k
+// pairs allocates.  One function for rbl_solve and for rbl_plan_blocks / rbl_buffer_blocks.
+MemPlan plan_memory(rbl_handle* h, int64_t k, int b, int64_t m_req) {
+    MemPlan p;
+    const rbl_options& opt = h->opt;
+    const int B = padded_block(b);
+    const bool fp32 = opt.precision == RBL_PRECISION_MIXED;
+    const size_t ssz = fp32 ? 4 : 8;
+    const int64_t nloc = h->nloc, next = h->nloc + h->n_halo;
+    size_t free_b = 0, total_b = 0;
+    RBL_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    free_b += solve_bytes(h->ws_ref());  // memory already held by this handle's workspace is available to the solve
+    double budget = 0.92 * (double)free_b;
+    if (opt.mem_limit_mb > 0) budget = std::min(budget, (double)opt.mem_limit_mb * 1048576.0);
+    const bool extra = opt.restart || opt.filter_degree != 0;
+    const int nX = 3 + (opt.filter_degree != 0 ? 1 : 0);
+    const int rgrid = rowop_grid(B, nloc);
+    const size_t vsz = opt.v_fp32 ? 4 : 8;
+    size_t fixed = (size_t)nX * next * B * 8                    // active blocks
+                   + (size_t)nloc * 4 * B * 4                    // packed target words of the tensor-core reorth
+                   + (size_t)rgrid * B * B * 8                   // Gram partials
+                   + (size_t)nloc * b * 8                        // Omega
+                   + (size_t)nloc * (size_t)std::max<int64_t>(k, 0) * vsz   // device copy of V
+                   + ((size_t)16 << 20);
+    if (extra) fixed += (size_t)nloc * (size_t)(2 * k + b) * 8;  // fp64 accumulation of locked + final vectors, restart scratch
+    const size_t per_block = (size_t)nloc * B * ssz + (size_t)B * 2 * B * (ssz + 8);
+    p.budget = budget;
+    p.per_block = (double)per_block;
+    // the Gram partials grow with the number of stored blocks too (piecewise): largest m <= m_req that fits
+    auto need = [&](int64_t m) { return (double)fixed + (double)reorth_max_partial_elems(B, fp32, nloc, std::max<int64_t>(m, 1)) * ssz + (double)m * per_block; };
+    int64_t lo = 0, hi = std::max<int64_t>(m_req, 1);
+    if (need(hi) <= budget) {
+        lo = hi;
+    } else {
+        while (hi - lo > 1) {
+            const int64_t mid = lo + (hi - lo) / 2;
+            if (need(mid) <= budget) lo = mid; else hi = mid;
+        }
+    }
+    p.m_fit = lo;
+    p.fixed = need(lo) - (double)lo * per_block;
+    return p;
 }
 
 // ------------------------------------------------------------------------------------------------ solve
@@ -255,42 +347,68 @@ struct PhaseTimer {
     }
 };
 
-struct Ctx {
-    rbl_handle* h = nullptr;
-    cudaStream_t st = nullptr;
+// p(x) = rho * T_d((x - c)/e): damps [a, b], grows outside (oracle/rbl_restart_oracle.py ChebFilter)
+struct FilterPlan {
+    int degree = 0;
+    double a = 0, b = 0, rho = 1;
+    bool two_sided = false;
+    double c() const { return 0.5 * (a + b); }
+    double e() const { return 0.5 * (b - a); }
+    double eval(double lam) const {
+        if (degree == 0) return lam;
+        const double x = (lam - c()) / e(), ax = std::fabs(x);
+        double t = ax <= 1.0 ? std::cos(degree * std::acos(std::max(-1.0, std::min(1.0, x))))
+                             : std::cosh(degree * std::acosh(ax)) * ((x < 0 && (degree & 1)) ? -1.0 : 1.0);
+        return rho * t;
+    }
+};
+
+struct CycleOut {
+    bool converged = false;
+    int64_t final_i = 0;         // blocks of this cycle that span the accepted / final Ritz pairs
+    int64_t iterations_run = 0;  // block steps the device ran in this cycle
+    TopKResult res;
+};
+
+struct Run {
+    rbl_handle* h;
+    const rbl_options& opt;
+    cudaStream_t st;
+    Workspace& w;
     int b = 0, B = 0;
     int64_t k = 0;
     bool fp32 = false;
     size_t ssz = 8;
-    int64_t nloc = 0, next = 0, m_cap = 0, bstride = 0;
-    Workspace& w;
-    DevBuf<double> (&X)[3];
-    DevBuf<unsigned char>& buf;
-    DevBuf<double>&part, &small;  // rowop partials; small: G, Ai, Bp, Gloc (4 * B*B)
-    DevBuf<QrState>& qr;
-    DevBuf<unsigned char>&Cmat, &rpart;
-    DevBuf<float>& tc_scratch;
-    DevBuf<double>& sendbuf;
-    PinnedBuf<double>&hA, &hB;
-    PinnedBuf<QrState>& hqr;
-    explicit Ctx(Workspace& ws)
-        : w(ws), X(ws.X), buf(ws.buf), part(ws.part), small(ws.small), qr(ws.qr), Cmat(ws.Cmat), rpart(ws.rpart),
-          tc_scratch(ws.tc_scratch), sendbuf(ws.sendbuf), hA(ws.hA), hB(ws.hB), hqr(ws.hqr) {}
-    bool use_tc = false;
-    bool use_h = false;   // FP16-split tensor-core kernels (default when supported); else TF32x3
+    int64_t nloc = 0, next = 0, m_cap = 0, bstride = 0, kryl_sz = 0;
+    bool use_h = false, use_d = false;
     float split_scale = 0.f;  // != 0: the Krylov slab holds split16 rows (split16.h) written with this scale
-    bool use_d = false;   // all-fp64 mode: FP64 tensor-core kernels
     int rgrid = 1;
+    int reorth_period = 2, check_period = 4;
+    bool async_ok = false, multi = false, is_root = true;
     int64_t launches = 0;
     PhaseTimer tm;
     double bytes_rgram = 0, bytes_rupd = 0, bytes_spmm = 0;
     int64_t n_rgram = 0, n_rupd = 0, n_spmm = 0;
+    double *cur = nullptr, *prev = nullptr, *U = nullptr, *P1 = nullptr;
+    SpmmCoef base;       // op(A) q = base.alpha * A q + base.beta * q
+    FilterPlan flt;
+    // host bookkeeping over the whole solve
+    int checks = 0, full_checks = 0;
+    int64_t host_factorizations = 0;
+    double t_eig = 0.0, t_blocked = 0.0, t_idle = 0.0;
+    int64_t total_steps = 0, total_steps_run = 0;
+    cudaEvent_t tail_event = nullptr;
 
-    double* G() { return small.p; }
-    double* Ai() { return small.p + (size_t)B * B; }
-    double* Bp() { return small.p + 2 * (size_t)B * B; }
-    double* Gloc() { return small.p + 3 * (size_t)B * B; }
-    void* slot(int64_t j) { return buf.p + (size_t)j * bstride * ssz; }
+    Run(rbl_handle* hh) : h(hh), opt(hh->opt), st(hh->stream), w(hh->ws_ref()) {}
+    ~Run() {
+        if (tail_event) cudaEventDestroy(tail_event);
+    }
+
+    double* G() { return w.small.p; }
+    double* Ai() { return w.small.p + (size_t)B * B; }
+    double* Bp() { return w.small.p + 2 * (size_t)B * B; }
+    double* Gloc() { return w.small.p + 3 * (size_t)B * B; }
+    void* slot(int64_t j) { return w.buf.p + (size_t)j * bstride * ssz; }
 
     void nccl(bool ok, const std::string& err) {
         if (!ok) throw Error(RBL_NCCL_ERROR, err);
@@ -302,7 +420,7 @@ struct Ctx {
     }
     // sum the per-CTA Gram partials into `out` (B*B) and across ranks
     void finish_gram(double* out) {
-        launch_reduce_partials(part.p, rgrid, B * B, out, st);
+        launch_reduce_partials(w.part.p, rgrid, B * B, out, st);
         ++launches;
         allreduce(out, (size_t)B * B);
     }
@@ -314,180 +432,168 @@ struct Ctx {
         if (!h->comm.active()) return;
         std::string err;
         const int64_t nsend = h->send_ptr[h->world];
-        launch_gather_rows(B, nsend, h->wsp->d_send_rows.p, Xblk, sendbuf.p, st);
+        launch_gather_rows(B, nsend, w.d_send_rows.p, Xblk, w.sendbuf.p, st);
         ++launches;
         nccl(h->comm.group_start(err), err);
         for (int p = 0; p < h->world; ++p) {
             if (p == h->rank) continue;
             const size_t sb = (size_t)(h->send_ptr[p + 1] - h->send_ptr[p]) * B * sizeof(double);
             const size_t rb = (size_t)(h->halo_owner_ptr[p + 1] - h->halo_owner_ptr[p]) * B * sizeof(double);
-            nccl(h->comm.send_bytes(sendbuf.p + (size_t)h->send_ptr[p] * B, sb, p, st, err), err);
+            nccl(h->comm.send_bytes(w.sendbuf.p + (size_t)h->send_ptr[p] * B, sb, p, st, err), err);
             nccl(h->comm.recv_bytes(Xblk + (size_t)(nloc + h->halo_owner_ptr[p]) * B, rb, p, st, err), err);
         }
         nccl(h->comm.group_end(err), err);
     }
-    void spmm(double* Q, double* U) {
+    // U = cf.alpha * A Q + cf.beta * Q + cf.gamma * Z
+    void spmm(double* Q, double* Uo, SpmmCoef cf, const double* Z) {
         halo(Q);
-        launch_spmm(B, nloc, h->wsp->d_rowptr.p, h->wsp->d_colidx.p, h->wsp->d_vals.p, Q, U, h->opt.op, h->opt.sigma, st);
+        launch_spmm(B, nloc, w.d_rowptr.p, w.d_colidx.p, w.d_vals.p, Q, Uo, cf, Z, st);
         ++launches;
         ++n_spmm;
-        bytes_spmm += 12.0 * (double)h->nnz + 4.0 * (double)(nloc + 1) + 16.0 * (double)nloc * B;
+        bytes_spmm += 12.0 * (double)h->nnz + 4.0 * (double)(nloc + 1) + 16.0 * (double)nloc * B +
+                      (cf.gamma != 0.0 ? 8.0 * (double)nloc * B : 0.0);
     }
-    // thin QR of the block in `U` (in place).  The Gram U'U must already be in the rowop partials.
-    void block_qr(double* U, int reset_ref) {
+    // Uo = op(A) Q (plain) - mul!(U,Ag,Qg_d), RBL_gpu.jl:152,176
+    void apply_plain(double* Q, double* Uo) { spmm(Q, Uo, base, nullptr); }
+    // Uo = p(op(A)) Q by the Chebyshev three-term recurrence; Q is preserved, P1 is scratch.
+    void apply_op(double* Q, double* Uo) {
+        const int d = flt.degree;
+        if (d == 0) {
+            apply_plain(Q, Uo);
+            return;
+        }
+        const double c = flt.c(), e = flt.e();
+        SpmmCoef c1{base.alpha / e, (base.beta - c) / e, 0.0};
+        SpmmCoef cj{2.0 * base.alpha / e, 2.0 * (base.beta - c) / e, -1.0};
+        auto scaled = [&](SpmmCoef x) { x.alpha *= flt.rho; x.beta *= flt.rho; x.gamma *= flt.rho; return x; };
+        // t_j lands alternately in A (odd j) and Bf (even j); the last one must land in Uo
+        double* bufA = (d & 1) ? Uo : P1;
+        double* bufB = (d & 1) ? P1 : Uo;
+        spmm(Q, bufA, d == 1 ? scaled(c1) : c1, nullptr);                        // t1
+        for (int j = 2; j <= d; ++j) {
+            double* tj1 = (j & 1) ? bufB : bufA;      // t_{j-1}
+            double* out = (j & 1) ? bufA : bufB;      // t_j overwrites t_{j-2} (aliasing Z is allowed), j = 2: Z = Q
+            const double* z = (j == 2) ? Q : out;
+            spmm(tj1, out, j == d ? scaled(cj) : cj, z);
+        }
+    }
+    // thin QR of the block in `Ub` (in place).  The Gram Ub'Ub must already be in the rowop partials.
+    void block_qr(double* Ub, int reset_ref) {
         const double defl_rel = 1e-12;
         finish_gram(G());
-        launch_chol(B, G(), qr.p, 1, h->n, reset_ref, defl_rel, st);
+        launch_chol(B, G(), w.qr.p, 1, h->n, reset_ref, defl_rel, st);
         ++launches;
         RowOpArgs a;
-        a.n = nloc; a.y = U; a.rinv = qr.p->Rinv; a.write_y = 1; a.do_gram = 1; a.partials = part.p;
+        a.n = nloc; a.y = Ub; a.rinv = w.qr.p->Rinv; a.write_y = 1; a.do_gram = 1; a.partials = w.part.p;
         rowop(a);
         finish_gram(G());
-        launch_chol(B, G(), qr.p, 2, h->n, 0, defl_rel, st);
+        launch_chol(B, G(), w.qr.p, 2, h->n, 0, defl_rel, st);
         ++launches;
         rowop(a);  // apply pass 2, Gram for the optional pass 3
         finish_gram(G());
-        launch_chol(B, G(), qr.p, 3, h->n, 0, defl_rel, st);
+        launch_chol(B, G(), w.qr.p, 3, h->n, 0, defl_rel, st);
         ++launches;
         RowOpArgs a3;
-        a3.n = nloc; a3.y = U; a3.rinv = qr.p->Rinv; a3.write_y = 1; a3.skip_flag = &qr.p->need_more;
+        a3.n = nloc; a3.y = Ub; a3.rinv = w.qr.p->Rinv; a3.write_y = 1; a3.skip_flag = &w.qr.p->need_more;
         rowop(a3);
     }
+    void gram_then_qr(double* Ub, int reset_ref) {
+        RowOpArgs a;
+        a.n = nloc; a.y = Ub; a.do_gram = 1; a.partials = w.part.p;
+        rowop(a);
+        block_qr(Ub, reset_ref);
+    }
+
+    // K5a: C = Qbuf[0..m)' * [w0 | w1] into w.Cmat (all-reduced over ranks); K5b: w -= Qbuf * C, optional refresh
+    // of one slab block with the updated w1.  hybrid_part_reorth! / part_reorth_gpu_async!, RBL_gpu.jl:59-81,29-47
+    void reorth_gram(int64_t m, double* w0, double* w1) {
+        ReorthPlan p = reorth_plan(B, fp32, nloc, m);
+        if (use_d) {
+            launch_reorth_gram_d(p, w.buf.p, bstride, w0, w1, w.rpart.p, w.Cmat.p, st);
+            launches += 2;
+            if (multi) { std::string err; nccl(h->comm.allreduce_f64((double*)w.Cmat.p, (size_t)m * B * 2 * B, st, err), err); }
+        } else if (use_h) {
+            launch_reorth_gram_h(p, h->n, w.buf.p, bstride, w0, w1, w.rpart.p, w.Cmat.p, w.tc_scratch.p, m_cap, split_scale != 0.f, st);
+            launches += 4;
+            if (multi) { std::string err; nccl(h->comm.allreduce_f32((float*)w.Cmat.p, (size_t)m * B * 2 * B, st, err), err); }
+        } else {
+            launch_reorth_gram(p, w.buf.p, bstride, w0, w1, w.rpart.p, w.Cmat.p, st);
+            launches += 2;
+            if (multi) {
+                std::string err;
+                const size_t cnt = (size_t)m * B * 2 * B;
+                nccl(fp32 ? h->comm.allreduce_f32((float*)w.Cmat.p, cnt, st, err) : h->comm.allreduce_f64((double*)w.Cmat.p, cnt, st, err), err);
+            }
+        }
+        ++n_rgram;
+        bytes_rgram += (double)ssz * (double)nloc * (double)m * B + 8.0 * (double)nloc * 2 * B;
+    }
+    void reorth_update(int64_t m, double* w0, double* w1, void* store_w1) {
+        ReorthPlan p = reorth_plan(B, fp32, nloc, m);
+        if (use_d) {
+            launch_reorth_update_d(p, w.buf.p, bstride, w.Cmat.p, w0, w1, store_w1, st);
+            ++launches;
+        } else if (use_h) {
+            launch_reorth_coeff_h(p, w.Cmat.p, w.tc_scratch.p, m_cap, multi ? 1 : 0, st);
+            launch_reorth_update_h(p, h->n, w.buf.p, bstride, w0, w1, store_w1, w.tc_scratch.p, m_cap, split_scale != 0.f, st);
+            launches += 2;
+        } else {
+            launch_reorth_update(p, w.buf.p, bstride, w.Cmat.p, w0, w1, store_w1, st);
+            ++launches;
+        }
+        ++n_rupd;
+        bytes_rupd += (double)ssz * (double)nloc * (double)m * B + 2 * 8.0 * (double)nloc * 2 * B +
+                      (store_w1 ? (double)ssz * (double)nloc * B : 0.0);
+    }
+
+    // decision shared by all ranks: 0 continue, 1 accept, 2 abort (the root's host check failed)
+    int agree(int local_code) {
+        if (!multi) return local_code;
+        DevBuf<double>& d_ctrl = w.ctrl;
+        PinnedBuf<double>& h_ctrl = w.h_ctrl;
+        h_ctrl.p[0] = is_root ? (double)local_code : 0.0;
+        RBL_CUDA(cudaMemcpyAsync(d_ctrl.p, h_ctrl.p, 8, cudaMemcpyHostToDevice, st));
+        allreduce(d_ctrl.p, 1);
+        RBL_CUDA(cudaMemcpyAsync(h_ctrl.p + 1, d_ctrl.p, 8, cudaMemcpyDeviceToHost, st));
+        RBL_CUDA(cudaStreamSynchronize(st));
+        return (int)std::lround(h_ctrl.p[1]);
+    }
+    // the root's (d, s, resid) of `cols` pairs over Nrows rows of T, made identical on every rank
+    void share_result(TopKResult& r, int64_t Nrows, int64_t cols) {
+        if (!multi) return;
+        const size_t cnt = (size_t)2 * cols + (size_t)Nrows * cols;
+        std::vector<double> hbuf(cnt, 0.0);
+        if (is_root) {
+            std::copy(r.d.begin(), r.d.begin() + cols, hbuf.begin());
+            std::copy(r.resid.begin(), r.resid.begin() + cols, hbuf.begin() + cols);
+            std::copy(r.s.begin(), r.s.begin() + (size_t)Nrows * cols, hbuf.begin() + 2 * cols);
+        }
+        DevBuf<double>& dbuf = w.share;
+        dbuf.ensure(cnt);
+        RBL_CUDA(cudaMemcpyAsync(dbuf.p, hbuf.data(), cnt * 8, cudaMemcpyHostToDevice, st));
+        allreduce(dbuf.p, cnt);
+        RBL_CUDA(cudaMemcpyAsync(hbuf.data(), dbuf.p, cnt * 8, cudaMemcpyDeviceToHost, st));
+        RBL_CUDA(cudaStreamSynchronize(st));
+        r.N = Nrows;
+        r.d.assign(hbuf.begin(), hbuf.begin() + cols);
+        r.resid.assign(hbuf.begin() + cols, hbuf.begin() + 2 * cols);
+        r.s.assign(hbuf.begin() + 2 * cols, hbuf.end());
+        r.have_all = true;
+    }
+
+    CycleOut cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int64_t max_steps);
+    void ritz(int64_t nlb, int64_t mfin, const TopKResult& res, const std::vector<int64_t>& cols, void* Vdev, int64_t ldv,
+              bool out_fp32, rbl_stats& stats);
+    void rayleigh(double* V, int64_t ncols, std::vector<double>& lam, std::vector<double>& resn);
 };
 
-void fill_stats(rbl_stats* s, Ctx& c, double* sec) {
-    s->t_spmm = sec[PH_SPMM];
-    s->t_3term = sec[PH_3TERM];
-    s->t_qr = sec[PH_QR];
-    s->t_loc_reorth = sec[PH_LOC];
-    s->t_part_reorth = sec[PH_RGRAM] + sec[PH_RUPD];
-    s->t_reorth_gram = sec[PH_RGRAM];
-    s->t_reorth_update = sec[PH_RUPD];
-    s->t_ritz = sec[PH_RITZ];
-    s->t_ritz_kernel = sec[PH_RITZ];
-    s->bytes_reorth_gram = c.bytes_rgram;
-    s->bytes_reorth_update = c.bytes_rupd;
-    s->bytes_part_reorth = c.bytes_rgram + c.bytes_rupd;
-    s->bytes_spmm = c.bytes_spmm;
-    s->launches_reorth_gram = c.n_rgram;
-    s->launches_reorth_update = c.n_rupd;
-    s->launches_spmm = c.n_spmm;
-    s->kernel_launches = c.launches;
-}
-
-}  // namespace
-
-int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omega_on_device, double* d_out, void* v_out,
-          bool v_on_device, rbl_stats* stats_out) {
-    const double t_begin = now_s();
-    rbl_stats stats;
-    std::memset(&stats, 0, sizeof(stats));
-    const rbl_options& opt = h->opt;
-    if (k <= 0 || b_in <= 0 || b_in > 32) throw Error(RBL_INVALID, "rbl_solve: need k >= 1 and 1 <= b <= 32");
-    if (k > h->n) throw Error(RBL_INVALID, "rbl_solve: k > n");
-    if (!d_out || !v_out) throw Error(RBL_INVALID, "rbl_solve: null output");
-    RBL_CUDA(cudaSetDevice(h->device));
-    Ctx c(h->ws_ref());
-    c.h = h; c.st = h->stream; c.b = (int)b_in; c.B = padded_block(c.b); c.k = k;
-    c.fp32 = opt.precision == RBL_PRECISION_MIXED;
-    c.ssz = c.fp32 ? 4 : 8;
-    c.nloc = h->nloc; c.next = h->nloc + h->n_halo;
-    c.bstride = c.nloc * c.B;
-    c.tm.h = h; c.tm.st = c.st;
-    const int b = c.b, B = c.B;
-    const int64_t kryl_sz = std::max<int64_t>(opt.max_kryl_sz, b);
-    int64_t m_cap = (kryl_sz + b - 1) / b;
-    const int reorth_period = std::max(1, opt.reorth_period), check_period = std::max(1, opt.check_period);
-    const bool async_ok = opt.async_check && (check_period % reorth_period == 0);
-
-    // ---- memory plan (gpu_buffer_size, RBL_gpu.jl:95-104: how many Krylov blocks fit) ---------------
-    size_t free_b = 0, total_b = 0;
-    RBL_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    {   // memory already held by this handle's workspace is available to this solve
-        const Workspace& w = h->ws_ref();
-        free_b += w.buf.count + w.ritzS.count + w.ritzV.count + w.omega.count * 8 + (w.X[0].count + w.X[1].count + w.X[2].count + w.part.count + w.small.count + w.sendbuf.count) * 8 +
-                  w.Cmat.count + w.rpart.count + w.tc_scratch.count * 4;
-    }
-    c.rgrid = rowop_grid(B, c.nloc);
-    const size_t fixed = 3 * (size_t)c.next * B * 8 + (size_t)c.nloc * 4 * B * 4 + (size_t)c.rgrid * B * B * 8 + (size_t)c.nloc * (size_t)(b + k) * 8 +
-                         ((size_t)64 << 20);
-    const size_t per_block = (size_t)c.bstride * c.ssz + (size_t)B * 2 * B * (c.ssz + 8);
-    if ((double)fixed + 2.0 * per_block > 0.92 * (double)free_b) throw Error(RBL_OOM, "rbl_solve: problem does not fit device memory");
-    {
-        size_t rp_elems = reorth_max_partial_elems(B, c.fp32, c.nloc, m_cap);
-        double avail = 0.92 * (double)free_b - (double)fixed - (double)rp_elems * c.ssz;
-        int64_t fit = (int64_t)std::floor(avail / (double)per_block);
-        if (fit < m_cap) {
-            m_cap = std::max<int64_t>(2, fit);
-            if (opt.verbose) std::fprintf(stderr, "[rbl] Krylov buffer capped at %lld blocks by device memory\n", (long long)m_cap);
-        }
-    }
-    c.m_cap = m_cap;
-    for (int i = 0; i < 3; ++i) c.X[i].ensure((size_t)c.next * B);
-    c.buf.ensure((size_t)m_cap * c.bstride * c.ssz);
-    c.part.ensure((size_t)c.rgrid * B * B);
-    c.small.ensure(4 * (size_t)B * B);
-    c.qr.ensure(1);
-    c.Cmat.ensure((size_t)m_cap * B * 2 * B * c.ssz);
-    c.rpart.ensure(std::max<size_t>(1, reorth_max_partial_elems(B, c.fp32, c.nloc, m_cap)) * c.ssz);
-    c.use_tc = reorth_tc_supported(B, c.fp32) && opt.reorth_impl != 1;
-    if (opt.reorth_impl == 2 && !c.use_tc)
-        throw Error(RBL_INVALID, "rbl_solve: tensor-core reorth needs precision=mixed and padded block size 16");
-    if (opt.reorth_impl >= 3 && !reorth_h_supported(B, c.fp32))
-        throw Error(RBL_INVALID, "rbl_solve: FP16-split tensor-core reorth needs precision=mixed and padded block size 16 or 32");
-    c.use_h = reorth_h_supported(B, c.fp32) && opt.reorth_impl != 1 && !(opt.reorth_impl == 2 && c.use_tc);
-    c.split_scale = (c.use_h && opt.reorth_impl != 3) ? reorth_h_scale(h->n) : 0.f;
-    c.use_d = reorth_d_supported(B, c.fp32) && opt.reorth_impl != 1;
-    if (c.use_tc || c.use_h) c.tc_scratch.ensure(std::max(reorth_tc_scratch_floats(B, c.nloc, m_cap), reorth_h_scratch_words(B, c.nloc, m_cap)));
-    if (h->comm.active()) c.sendbuf.ensure(std::max<int64_t>(1, h->send_ptr[h->world]) * (size_t)B);
-    c.hA.ensure((size_t)m_cap * B * B);
-    c.hB.ensure((size_t)m_cap * B * B);
-    c.hqr.ensure(1);
-    const double t_alloc_done = now_s();
-    RBL_CUDA(cudaMemsetAsync(c.qr.p, 0, sizeof(QrState), c.st));
-    RBL_CUDA(cudaMemsetAsync(c.small.p, 0, 4 * (size_t)B * B * 8, c.st));
-    for (int i = 0; i < 3; ++i) RBL_CUDA(cudaMemsetAsync(c.X[i].p, 0, (size_t)c.next * B * 8, c.st));
-
-    // ---- start block: Q1 = thin-Q of qr(A * Omega)                              RBL_gpu.jl:213-214 ----
-    DevBuf<double>& d_omega = h->ws_ref().omega;
-    const double* om_dev = nullptr;
-    {
-        const double t0 = now_s();
-        if (omega && omega_on_device) {
-            om_dev = omega;
-        } else {
-            d_omega.ensure((size_t)c.nloc * b);
-            if (omega) {
-                RBL_CUDA(cudaMemcpyAsync(d_omega.p, omega, (size_t)c.nloc * b * 8, cudaMemcpyHostToDevice, c.st));
-            } else {
-                for (int col = 0; col < b; ++col)
-                    launch_randn(c.nloc, 0x5eedull, (uint64_t)col * (uint64_t)h->n + (uint64_t)h->row0,
-                                 d_omega.p + (size_t)col * c.nloc, c.st);
-            }
-            om_dev = d_omega.p;
-            RBL_CUDA(cudaStreamSynchronize(c.st));
-        }
-        stats.t_h2d = (now_s() - t0) + h->t_h2d_create;
-    }
-    double *cur = c.X[1].p, *prev = c.X[0].p, *U = c.X[2].p;
-    launch_colmajor_to_block(B, c.nloc, b, om_dev, c.nloc, c.X[0].p, c.st);
-    ++c.launches;
-    c.tm.mark(PH_SPMM);
-    c.spmm(c.X[0].p, cur);
-    c.tm.mark(PH_QR);
-    {
-        RowOpArgs a;
-        a.n = c.nloc; a.y = cur; a.do_gram = 1; a.partials = c.part.p;
-        c.rowop(a);
-        c.block_qr(cur, 1);
-        // a start block of rank 0 (Omega = 0, or A*Omega = 0) spans no Krylov space: report it instead of
-        // iterating on zero columns (the reference's Householder QR would continue with arbitrary unit vectors)
-        RBL_CUDA(cudaMemcpyAsync(c.hqr.p, c.qr.p, sizeof(QrState), cudaMemcpyDeviceToHost, c.st));
-        RBL_CUDA(cudaStreamSynchronize(c.st));
-        if (c.hqr.p->bad) throw Error(RBL_INVALID, "rbl_solve: A*Omega contains non-finite values");
-        if (c.hqr.p->ndeflated >= B) throw Error(RBL_BREAKDOWN, "rbl_solve: the start block A*Omega has rank 0");
-    }
-
+// One Lanczos cycle (lanczos_iteration, RBL_gpu.jl:134-203) on the operator apply_op, starting from the orthonormal
+// block in `cur`; slab slots [0, nlb) hold locked vectors, the cycle's blocks go to slots nlb, nlb+1, ...
+//   probe      no convergence checks; run max_steps steps, then return the kk_end leading Ritz pairs of T
+//   otherwise  checks every check_period steps for k_rem pairs; when the cap is reached the result holds the
+//              kk_end leading pairs of the last T with their residual bounds
+CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int64_t max_steps) {
+    CycleOut out;
     // ---- host-side T bookkeeping (insertA!/insertB!, common.jl:9-26) ---------------------------------
     BandSym T;
     T.reset(0, b);
@@ -496,17 +602,24 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
     checker.verbose = opt.verbose;
     int64_t t_blocks = 0;  // blocks already inserted into T
     std::vector<cudaEvent_t> step_event((size_t)m_cap + 2, nullptr);
+    struct EventGuard {
+        std::vector<cudaEvent_t>& v;
+        ~EventGuard() {
+            for (auto e : v)
+                if (e) cudaEventDestroy(e);
+        }
+    } event_guard{step_event};
     auto grow_T = [&](int64_t upto_blocks) {
         // A_j for j < upto, B_j for j < upto-1 (B_i of the newest block is applied after the check, common.jl:113)
         const int W = 2 * b + 1;
         T.F.resize((size_t)upto_blocks * b * W, 0.0);
         T.N = upto_blocks * b;
         for (int64_t j = t_blocks; j < upto_blocks; ++j) {
-            const double* A = c.hA.p + (size_t)j * B * B;
+            const double* A = w.hA.p + (size_t)j * B * B;
             for (int r = 0; r < b; ++r)
                 for (int cc = 0; cc <= r; ++cc) T.set_sym(j * b + r, j * b + cc, A[r * B + cc]);
             if (j > 0) {
-                const double* Bm = c.hB.p + (size_t)(j - 1) * B * B;  // couples block j-1 and j
+                const double* Bm = w.hB.p + (size_t)(j - 1) * B * B;  // couples block j-1 and j
                 for (int cc = 0; cc < b; ++cc)
                     for (int m = 0; m <= cc; ++m) T.set_sym(j * b + m, (j - 1) * b + cc, Bm[m * B + cc]);
             }
@@ -514,7 +627,6 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         t_blocks = upto_blocks;
         T.update_norm();
     };
-    double t_eig = 0.0;
     // Shadow tracker (rank 0): from the first checks on a background thread keeps computing
     // ALL k Ritz pairs of the latest T snapshot - by slicing the first time, by refining its own previous pairs
     // afterwards (BandTopK::refine_seeds) - so that the accepting check only has to refine fresh seeds instead of
@@ -529,7 +641,8 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         TopKResult res;
     } shadow;
     const int shadow_verbose = opt.verbose;
-    auto shadow_loop = [&shadow, k, b, shadow_verbose](int nthreads) {
+    const int bb = b;
+    auto shadow_loop = [&shadow, k_rem, bb, shadow_verbose](int nthreads) {
         BandTopK tracker;
         tracker.threads = nthreads;
         for (;;) {
@@ -546,9 +659,11 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             const double ts0 = now_s();
             const int64_t f0 = tracker.total_factorizations;
             try {
-                r = tracker.check(Tc, nullptr, b, k, 0.0, true);
+                r = tracker.check(Tc, nullptr, bb, k_rem, 0.0, true);
             } catch (const Cancelled&) {
                 return;
+            } catch (...) {
+                return;  // the tracker is an accelerator only: the checks work without its seeds
             }
             if (shadow_verbose > 1)
                 std::fprintf(stderr, "[rbl] tracker N=%lld: %.1f ms, %lld factorisations, all pairs %d\n", (long long)Tc.N,
@@ -572,28 +687,28 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
             if (s.th.joinable()) s.th.join();
         }
     } shadow_join{shadow};
-    auto run_check = [&](int64_t it, bool force_full) -> TopKResult {
+    auto run_check = [&](int64_t it, bool force_full, int64_t kwant) -> TopKResult {
         cudaSetDevice(h->device);
         cudaEventSynchronize(step_event[it]);
         const double t0 = now_s();
         grow_T(it);
-        if (shadow.active) {
+        if (shadow.active && kwant == k_rem) {
             std::lock_guard<std::mutex> lk(shadow.mu);
             if (shadow.have_res) {
-                checker.set_seeds(shadow.res.d, shadow.res.s, shadow.res.N, k);
+                checker.set_seeds(shadow.res.d, shadow.res.s, shadow.res.N, k_rem);
                 shadow.have_res = false;
             }
         }
         std::vector<double> Bi((size_t)b * b);
-        const double* Bm = c.hB.p + (size_t)(it - 1) * B * B;
+        const double* Bm = w.hB.p + (size_t)(it - 1) * B * B;
         for (int r = 0; r < b; ++r)
             for (int cc = 0; cc < b; ++cc) Bi[(size_t)r * b + cc] = Bm[r * B + cc];
-        TopKResult r = checker.check(T, Bi.data(), b, k, opt.tol, force_full);
-        if (!r.converged && !shadow.active && T.N >= 2 * k) {
+        TopKResult r = checker.check(T, Bi.data(), b, std::min<int64_t>(kwant, T.N), opt.tol, force_full);
+        if (!r.converged && !shadow.active && !force_full && T.N >= 2 * k_rem) {
             shadow.active = true;
             shadow.th = std::thread(shadow_loop, std::max(1, checker.threads - 1));
         }
-        if (!r.converged && shadow.active) {
+        if (!r.converged && shadow.active && !force_full) {
             {
                 std::lock_guard<std::mutex> lk(shadow.mu);
                 shadow.req = T;  // snapshot (a few MB)
@@ -608,342 +723,711 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const double* omega, bool omeg
         return r;
     };
 
-    // ---- first step (i = 1)                                                     RBL_gpu.jl:149-161 ----
     auto record_step = [&](int64_t it) {
-        RBL_CUDA(cudaMemcpyAsync(c.hA.p + (size_t)(it - 1) * B * B, c.Ai(), (size_t)B * B * 8, cudaMemcpyDeviceToHost, c.st));
-        RBL_CUDA(cudaMemcpyAsync(c.Bp(), c.qr.p->R, (size_t)B * B * 8, cudaMemcpyDeviceToDevice, c.st));
-        RBL_CUDA(cudaMemcpyAsync(c.hB.p + (size_t)(it - 1) * B * B, c.qr.p->R, (size_t)B * B * 8, cudaMemcpyDeviceToHost, c.st));
+        RBL_CUDA(cudaMemcpyAsync(w.hA.p + (size_t)(it - 1) * B * B, Ai(), (size_t)B * B * 8, cudaMemcpyDeviceToHost, st));
+        RBL_CUDA(cudaMemcpyAsync(Bp(), w.qr.p->R, (size_t)B * B * 8, cudaMemcpyDeviceToDevice, st));
+        RBL_CUDA(cudaMemcpyAsync(w.hB.p + (size_t)(it - 1) * B * B, w.qr.p->R, (size_t)B * B * 8, cudaMemcpyDeviceToHost, st));
     };
-    c.tm.mark(PH_LOC);
-    launch_store_block(B, c.nloc, cur, c.slot(0), c.fp32, c.split_scale, c.st);
-    ++c.launches;
-    c.tm.mark(PH_SPMM);
-    c.spmm(cur, U);
-    c.tm.mark(PH_3TERM);
+    auto mark_event = [&](int64_t it) {
+        if (!step_event[it]) RBL_CUDA(cudaEventCreateWithFlags(&step_event[it], cudaEventDisableTiming));
+        RBL_CUDA(cudaEventRecord(step_event[it], st));
+    };
+
+    // ---- first step (i = 1)                                                     RBL_gpu.jl:149-161 ----
+    tm.mark(PH_LOC);
+    launch_store_block(B, nloc, cur, slot(nlb), fp32, split_scale, st);
+    ++launches;
+    tm.mark(PH_SPMM);
+    apply_op(cur, U);
+    tm.mark(PH_3TERM);
     {
         RowOpArgs a;
-        a.n = c.nloc; a.y = U; a.gram_z = cur; a.do_gram = 1; a.partials = c.part.p;
-        c.rowop(a);
-        c.finish_gram(c.Ai());
+        a.n = nloc; a.y = U; a.gram_z = cur; a.do_gram = 1; a.partials = w.part.p;
+        rowop(a);
+        finish_gram(Ai());
         RowOpArgs a2;
-        a2.n = c.nloc; a2.y = U; a2.x1 = cur; a2.m1 = c.Ai(); a2.write_y = 1; a2.do_gram = 1; a2.partials = c.part.p;
-        c.rowop(a2);
+        a2.n = nloc; a2.y = U; a2.x1 = cur; a2.m1 = Ai(); a2.write_y = 1; a2.do_gram = 1; a2.partials = w.part.p;
+        rowop(a2);
     }
-    c.tm.mark(PH_QR);
-    c.block_qr(U, 1);
+    tm.mark(PH_QR);
+    block_qr(U, 1);
     record_step(1);
-    c.tm.mark(PH_NONE);
+    tm.mark(PH_NONE);
     { double* t = prev; prev = cur; cur = U; U = t; }
 
     // ---- main loop                                                               RBL_gpu.jl:162-194 ----
     int64_t i = 1;
-    int64_t final_i = 0;
     bool converged = false;
-    TopKResult final_res;
     std::future<TopKResult> pending;
     int64_t pending_i = 0;
-    int64_t last_check_i = 0;
-    int checks = 0;
-    double t_wait = 0.0;
-    // Row-sharded runs: only rank 0 evaluates the host check; the decision (and, on acceptance, D and S)
-    // is summed over ranks with every other rank contributing zeros, so all ranks follow the same control
-    // flow and use the same Ritz basis.
-    const bool is_root = (h->rank == 0);
-    const bool multi = h->comm.active();
-    // kept in the workspace: with peer access enabled by NCCL every cudaMalloc / cudaFree / cudaFreeHost is expensive
-    DevBuf<double>& d_ctrl = h->ws_ref().ctrl;
-    PinnedBuf<double>& h_ctrl = h->ws_ref().h_ctrl;
-    if (multi) {
-        d_ctrl.ensure(2);
-        h_ctrl.ensure(2);
-    }
-    auto agree_flag = [&](bool local) -> bool {
-        if (!multi) return local;
-        h_ctrl.p[0] = (is_root && local) ? 1.0 : 0.0;
-        RBL_CUDA(cudaMemcpyAsync(d_ctrl.p, h_ctrl.p, 8, cudaMemcpyHostToDevice, c.st));
-        c.allreduce(d_ctrl.p, 1);
-        RBL_CUDA(cudaMemcpyAsync(h_ctrl.p + 1, d_ctrl.p, 8, cudaMemcpyDeviceToHost, c.st));
-        RBL_CUDA(cudaStreamSynchronize(c.st));
-        return h_ctrl.p[1] > 0.5;
-    };
-    auto share_result = [&](TopKResult& r, int64_t Nrows) {
-        if (!multi) return;
-        const size_t cnt = (size_t)k + (size_t)Nrows * k;
-        std::vector<double> hbuf(cnt, 0.0);
-        if (is_root) {
-            std::copy(r.d.begin(), r.d.begin() + k, hbuf.begin());
-            std::copy(r.s.begin(), r.s.begin() + (size_t)Nrows * k, hbuf.begin() + k);
-        }
-        DevBuf<double>& dbuf = h->ws_ref().share;
-        dbuf.ensure(cnt);
-        RBL_CUDA(cudaMemcpyAsync(dbuf.p, hbuf.data(), cnt * 8, cudaMemcpyHostToDevice, c.st));
-        c.allreduce(dbuf.p, cnt);
-        RBL_CUDA(cudaMemcpyAsync(hbuf.data(), dbuf.p, cnt * 8, cudaMemcpyDeviceToHost, c.st));
-        RBL_CUDA(cudaStreamSynchronize(c.st));
-        r.N = Nrows;
-        r.d.assign(hbuf.begin(), hbuf.begin() + k);
-        r.s.assign(hbuf.begin() + k, hbuf.end());
-    };
     bool check_in_flight = false;
-    auto harvest = [&]() -> bool {  // wait for the in-flight check; true when it accepted
+    std::string root_error;
+    // waits for the in-flight check; true when it accepted.  Row-sharded runs: only rank 0 evaluates the host
+    // check; the decision code (and, on acceptance, D, S and the bounds) is summed over ranks with every other
+    // rank contributing zeros, so all ranks follow the same control flow and use the same Ritz basis; a failure
+    // of the root's check is broadcast as code 2 and every rank leaves with the same error instead of hanging.
+    auto harvest = [&]() -> bool {
         if (!check_in_flight) return false;
         check_in_flight = false;
         TopKResult r;
-        bool local = false;
+        int code = 0;
         if (is_root) {
             const double t0 = now_s();
-            r = pending.get();
-            t_wait += now_s() - t0;
-            if (opt.verbose > 1) std::fprintf(stderr, "[rbl] harvest it=%lld waited %.2f ms\n", (long long)pending_i, (now_s() - t0) * 1e3);
-            local = r.converged;
+            double idle_from = -1.0;
+            try {
+                while (pending.wait_for(std::chrono::microseconds(200)) != std::future_status::ready)
+                    if (idle_from < 0 && cudaEventQuery(tail_event) == cudaSuccess) idle_from = now_s();
+                r = pending.get();
+                code = r.converged ? 1 : 0;
+            } catch (const std::exception& e) {
+                root_error = e.what();
+                code = 2;
+            }
+            const double t1 = now_s();
+            t_blocked += t1 - t0;
+            if (idle_from >= 0) t_idle += t1 - idle_from;
+            if (opt.verbose > 1) std::fprintf(stderr, "[rbl] harvest it=%lld blocked %.2f ms\n", (long long)pending_i, (t1 - t0) * 1e3);
         }
         ++checks;
-        last_check_i = pending_i;
-        if (agree_flag(local)) {
+        code = agree(code);
+        if (code >= 2) throw Error(RBL_BREAKDOWN, "rbl_solve: host eigen-check failed: " + (root_error.empty() ? std::string("(on rank 0)") : root_error));
+        if (code == 1) {
             converged = true;
-            final_i = pending_i;
-            final_res = std::move(r);
-            share_result(final_res, final_i * b);
+            out.final_i = pending_i;
+            out.res = std::move(r);
+            share_result(out.res, out.final_i * b, k_rem);
             return true;
         }
         return false;
     };
 
-    while (i * b < kryl_sz && i < m_cap) {
+    while (i < max_steps && nlb + i < m_cap) {
         ++i;
-        if (i % reorth_period == 0 && i > 2) {
-            // hybrid_part_reorth!: project Q_i and Q_{i-1} against blocks 1..i-2, all at once (block CGS)
-            const int64_t m = i - 2;
-            ReorthPlan p = reorth_plan(B, c.fp32, c.nloc, m);
-            c.tm.mark(PH_RGRAM);
-            if (c.use_d) {
-                launch_reorth_gram_d(p, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.st);
-                c.launches += 2;
-                if (h->comm.active()) {
-                    std::string err;
-                    c.nccl(h->comm.allreduce_f64((double*)c.Cmat.p, (size_t)m * B * 2 * B, c.st, err), err);
-                }
-                c.tm.mark(PH_RUPD);
-                launch_reorth_update_d(p, c.buf.p, c.bstride, c.Cmat.p, cur, prev, c.slot(i - 2), c.st);
-                ++c.launches;
-            } else if (c.use_h) {
-                launch_reorth_gram_h(p, h->n, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.tc_scratch.p, m_cap,
-                                     c.split_scale != 0.f, c.st);
-                c.launches += 4;
-                if (h->comm.active()) {
-                    std::string err;
-                    const size_t cnt = (size_t)m * B * 2 * B;
-                    c.nccl(h->comm.allreduce_f32((float*)c.Cmat.p, cnt, c.st, err), err);
-                }
-                launch_reorth_coeff_h(p, c.Cmat.p, c.tc_scratch.p, m_cap, h->comm.active() ? 1 : 0, c.st);
-                ++c.launches;
-                c.tm.mark(PH_RUPD);
-                launch_reorth_update_h(p, h->n, c.buf.p, c.bstride, cur, prev, c.slot(i - 2), c.tc_scratch.p, m_cap,
-                                       c.split_scale != 0.f, c.st);
-                ++c.launches;
-            } else if (c.use_tc) {
-                launch_reorth_gram_tc(p, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.tc_scratch.p, m_cap, c.st);
-                c.launches += 3;
-                if (h->comm.active()) {
-                    // the hi/lo parts are not additive across ranks: reduce C, then re-split on every rank
-                    std::string err;
-                    const size_t cnt = (size_t)m * B * 2 * B;
-                    c.nccl(h->comm.allreduce_f32((float*)c.Cmat.p, cnt, c.st, err), err);
-                    ReorthPlan one = p;
-                    one.ranges = 1;
-                    launch_reorth_gram_tc_resplit(one, c.Cmat.p, c.tc_scratch.p, m_cap, c.st);
-                    ++c.launches;
-                }
-                c.tm.mark(PH_RUPD);
-                launch_reorth_update_tc(p, c.buf.p, c.bstride, cur, prev, c.slot(i - 2), c.tc_scratch.p, m_cap, c.st);
-                ++c.launches;
-            } else {
-                launch_reorth_gram(p, c.buf.p, c.bstride, cur, prev, c.rpart.p, c.Cmat.p, c.st);
-                c.launches += 2;
-                if (h->comm.active()) {
-                    std::string err;
-                    const size_t cnt = (size_t)m * B * 2 * B;
-                    c.nccl(c.fp32 ? h->comm.allreduce_f32((float*)c.Cmat.p, cnt, c.st, err)
-                                  : h->comm.allreduce_f64((double*)c.Cmat.p, cnt, c.st, err), err);
-                }
-                c.tm.mark(PH_RUPD);
-                launch_reorth_update(p, c.buf.p, c.bstride, c.Cmat.p, cur, prev, c.slot(i - 2), c.st);
-                ++c.launches;
-            }
-            ++c.n_rgram; ++c.n_rupd;
-            c.bytes_rgram += (double)c.ssz * (double)c.nloc * (double)m * B + 8.0 * (double)c.nloc * 2 * B;
-            c.bytes_rupd += (double)c.ssz * (double)c.nloc * (double)m * B + 2 * 8.0 * (double)c.nloc * 2 * B +
-                            (double)c.ssz * (double)c.nloc * B;
+        const int64_t m = nlb + i - 2;  // stored blocks the two newest are re-orthogonalised against
+        if (i % reorth_period == 0 && m > 0) {
+            // hybrid_part_reorth! (+ restart_reorth_gpu! for the locked blocks): project Q_i and Q_{i-1} against
+            // everything stored before them, all at once (block CGS)
+            tm.mark(PH_RGRAM);
+            reorth_gram(m, cur, prev);
+            tm.mark(PH_RUPD);
+            reorth_update(m, cur, prev, slot(nlb + i - 2));
         }
         // loc_reorth_gpu! (effective): Q_i -= Q_{i-1} (Q_{i-1}' Q_i); then the block joins the buffer (:167-172)
-        c.tm.mark(PH_LOC);
+        tm.mark(PH_LOC);
         {
             RowOpArgs a;
-            a.n = c.nloc; a.y = cur; a.gram_z = prev; a.do_gram = 1; a.partials = c.part.p;
-            c.rowop(a);
-            c.finish_gram(c.Gloc());
+            a.n = nloc; a.y = cur; a.gram_z = prev; a.do_gram = 1; a.partials = w.part.p;
+            rowop(a);
+            finish_gram(Gloc());
             RowOpArgs a2;
-            a2.n = c.nloc; a2.y = cur; a2.x1 = prev; a2.m1 = c.Gloc(); a2.write_y = 1;
-            a2.store = c.slot(i - 1); a2.store_fp32 = c.fp32; a2.store_split_scale = c.split_scale;
-            c.rowop(a2);
+            a2.n = nloc; a2.y = cur; a2.x1 = prev; a2.m1 = Gloc(); a2.write_y = 1;
+            a2.store = slot(nlb + i - 1); a2.store_fp32 = fp32; a2.store_split_scale = split_scale;
+            rowop(a2);
         }
-        c.tm.mark(PH_SPMM);
-        c.spmm(cur, U);                                                        // :176
-        c.tm.mark(PH_3TERM);
+        tm.mark(PH_SPMM);
+        apply_op(cur, U);                                                      // :176
+        tm.mark(PH_3TERM);
         {
             RowOpArgs a;                                                       // :177-178
-            a.n = c.nloc; a.y = U; a.x1 = prev; a.m1 = c.Bp(); a.m1_transposed = 1; a.write_y = 1;
-            a.gram_z = cur; a.do_gram = 1; a.partials = c.part.p;
-            c.rowop(a);
-            c.finish_gram(c.Ai());
+            a.n = nloc; a.y = U; a.x1 = prev; a.m1 = Bp(); a.m1_transposed = 1; a.write_y = 1;
+            a.gram_z = cur; a.do_gram = 1; a.partials = w.part.p;
+            rowop(a);
+            finish_gram(Ai());
             RowOpArgs a2;                                                      // :179 (+ Gram for the QR)
-            a2.n = c.nloc; a2.y = U; a2.x1 = cur; a2.m1 = c.Ai(); a2.write_y = 1; a2.do_gram = 1; a2.partials = c.part.p;
-            c.rowop(a2);
+            a2.n = nloc; a2.y = U; a2.x1 = cur; a2.m1 = Ai(); a2.write_y = 1; a2.do_gram = 1; a2.partials = w.part.p;
+            rowop(a2);
         }
-        c.tm.mark(PH_QR);
-        c.block_qr(U, 0);                                                      // :180-184
+        tm.mark(PH_QR);
+        block_qr(U, 0);                                                        // :180-184
         record_step(i);
-        c.tm.mark(PH_NONE);
+        tm.mark(PH_NONE);
         { double* t = prev; prev = cur; cur = U; U = t; }
 
-        if (i * b > k && i % check_period == 0) {                               // :186
+        if (!probe && i * b > k_rem && i % check_period == 0) {                 // :186
+            RBL_CUDA(cudaEventRecord(tail_event, st));
             if (harvest()) break;
-            RBL_CUDA(cudaEventCreateWithFlags(&step_event[i], cudaEventDisableTiming));
-            RBL_CUDA(cudaEventRecord(step_event[i], c.st));
+            mark_event(i);
             pending_i = i;
             check_in_flight = true;
             const int64_t it = i;
             if (is_root) {
                 if (async_ok) {
-                    pending = std::async(std::launch::async, [&, it]() { return run_check(it, false); });
+                    pending = std::async(std::launch::async, [&, it]() { return run_check(it, false, k_rem); });
                 } else {
                     std::promise<TopKResult> pr;
-                    pr.set_value(run_check(it, false));
+                    const double t0 = now_s();
+                    try {
+                        pr.set_value(run_check(it, false, k_rem));
+                    } catch (...) {
+                        pr.set_exception(std::current_exception());
+                    }
+                    t_idle += now_s() - t0;   // synchronous order: the device waits for the whole check
                     pending = pr.get_future();
                 }
             }
             if (!async_ok && harvest()) break;
         }
     }
+    RBL_CUDA(cudaEventRecord(tail_event, st));
     if (!converged) harvest();
-    const double t_loop_done = now_s();
-    const int64_t iterations_run = i;
-    RBL_CUDA(cudaStreamSynchronize(c.st));
-    int status = RBL_OK;
+    out.iterations_run = i;
+    out.converged = converged;
+    RBL_CUDA(cudaStreamSynchronize(st));
     if (!converged) {
-        // cap reached: the reference returns a stale check or throws; here: best effort + status
-        status = RBL_NOT_CONVERGED;
-        int64_t it = last_check_i > 0 ? last_check_i : i;
-        if (it * b < k) throw Error(RBL_INVALID, "rbl_solve: Krylov cap smaller than k, no Ritz pairs available");
-        if (!step_event[it]) {
-            RBL_CUDA(cudaEventCreateWithFlags(&step_event[it], cudaEventDisableTiming));
-            RBL_CUDA(cudaEventRecord(step_event[it], c.st));
+        // cap reached (or probe finished): the kk_end leading pairs of the last T.  SURVEY Q4: the reference returns a
+        // stale check or throws here; this is what restarts lock from and what NOT_CONVERGED returns as best effort.
+        const int64_t it = i;
+        if (it * b < std::min<int64_t>(k_rem, kk_end)) throw Error(RBL_INVALID, "rbl_solve: Krylov cap smaller than k, no Ritz pairs available");
+        mark_event(it);
+        int code = 0;
+        if (is_root) {
+            try {
+                out.res = run_check(it, true, kk_end);
+                if (!out.res.have_all) throw Error(RBL_BREAKDOWN, "could not isolate the leading Ritz pairs of T");
+            } catch (const std::exception& e) {
+                root_error = e.what();
+                code = 2;
+            }
         }
-        if (it < t_blocks) {  // T already grew past `it` (cannot happen with one check in flight) - rebuild
-            T.reset(0, b);
-            t_blocks = 0;
-        }
-        if (is_root) final_res = run_check(it, true);
-        share_result(final_res, it * b);
+        if (agree(code) >= 2) throw Error(RBL_BREAKDOWN, "rbl_solve: host eigen-check failed: " + (root_error.empty() ? std::string("(on rank 0)") : root_error));
+        share_result(out.res, it * b, std::min<int64_t>(kk_end, it * b));
         ++checks;
-        final_i = it;
+        out.final_i = it;
     }
-    for (auto e : step_event)
-        if (e) cudaEventDestroy(e);
-
+    full_checks += checker.full_checks;
+    host_factorizations += checker.total_factorizations;
+    if (opt.verbose)
+        std::fprintf(stderr, "[rbl] cycle: %lld blocks (+%lld locked), ran %lld, converged %d; host checks: witness %d (%.3f s), bracketed %d (%.3f s), full %d (%.3f s); factorisations %lld (+%lld resumed)\n",
+                     (long long)out.final_i, (long long)nlb, (long long)i, (int)converged, checker.stage_hits[0], checker.stage_sec[0],
+                     checker.stage_hits[1], checker.stage_sec[1], checker.stage_hits[2], checker.stage_sec[2],
+                     (long long)checker.total_factorizations, (long long)checker.resumed_factorizations);
     if (const char* dump = std::getenv("RBL_DUMP_T")) {
         // debugging aid: the A_i / B_i blocks of T (what the host checks saw), for tools/replay_dump.py
         if (is_root && dump[0]) {
             if (FILE* f = std::fopen(dump, "wb")) {
-                const int64_t hdr[4] = {iterations_run, (int64_t)B, (int64_t)b, final_i};
+                const int64_t hdr[4] = {i, (int64_t)B, (int64_t)b, out.final_i};
                 std::fwrite(hdr, sizeof(int64_t), 4, f);
-                std::fwrite(c.hA.p, sizeof(double), (size_t)iterations_run * B * B, f);
-                std::fwrite(c.hB.p, sizeof(double), (size_t)iterations_run * B * B, f);
+                std::fwrite(w.hA.p, sizeof(double), (size_t)i * B * B, f);
+                std::fwrite(w.hB.p, sizeof(double), (size_t)i * B * B, f);
                 std::fclose(f);
             }
         }
     }
+    return out;
+}
+
+// V[:, j] = Qbuf[nlb .. nlb+mfin) * S[:, cols[j]]   (recover_eigvec, RBL_gpu.jl:106-132; S narrowed like cu(), :119)
+void Run::ritz(int64_t nlb, int64_t mfin, const TopKResult& res, const std::vector<int64_t>& cols, void* Vdev, int64_t ldv,
+               bool out_fp32, rbl_stats& stats) {
+    const int64_t kc = (int64_t)cols.size();
+    if (kc == 0) return;
+    const int kpad = (int)((kc + 15) / 16 * 16);
+    std::vector<unsigned char> Sh((size_t)mfin * B * kpad * ssz, 0);
+    for (int64_t j = 0; j < mfin; ++j)
+        for (int cc = 0; cc < b; ++cc)
+            for (int64_t t = 0; t < kc; ++t) {
+                const double v = res.s[(size_t)cols[t] * res.N + (size_t)j * b + cc];
+                const size_t idx = ((size_t)j * B + cc) * kpad + t;
+                if (fp32) reinterpret_cast<float*>(Sh.data())[idx] = (float)v;
+                else reinterpret_cast<double*>(Sh.data())[idx] = v;
+            }
+    DevBuf<unsigned char>& dS = w.ritzS;
+    dS.ensure(Sh.size());
+    RBL_CUDA(cudaMemcpyAsync(dS.p, Sh.data(), Sh.size(), cudaMemcpyHostToDevice, st));
+    tm.mark(PH_RITZ);
+    if (split_scale != 0.f) {
+        w.ritz_words.ensure(ritz_h_scratch_words(B, mfin, kpad));
+        launch_ritz_h(B, nloc, mfin, (int)kc, kpad, slot(nlb), bstride, dS.p, Vdev, ldv, out_fp32 ? 1 : 0, split_scale, w.ritz_words.p, st);
+        ++launches;
+    } else {
+        launch_ritz(B, fp32, nloc, mfin, (int)kc, kpad, slot(nlb), bstride, dS.p, Vdev, ldv, out_fp32 ? 1 : 0, 0.f, st);
+    }
+    ++launches;
+    tm.mark(PH_NONE);
+    RBL_CUDA(cudaStreamSynchronize(st));   // Sh goes out of scope
+    stats.bytes_ritz += (double)ssz * (double)nloc * (double)mfin * B + (out_fp32 ? 4.0 : 8.0) * (double)nloc * (double)kc;
+    stats.flops_ritz += 2.0 * (double)nloc * (double)mfin * B * (double)kc;
+}
+
+// Rayleigh quotients lam_c = v'op(A)v / v'v and residual norms ||op(A)v - lam v|| / ||v|| of `ncols` column-major
+// fp64 vectors (leading dimension nloc), b columns at a time through the block kernels.
+void Run::rayleigh(double* V, int64_t ncols, std::vector<double>& lam, std::vector<double>& resn) {
+    lam.assign(ncols, 0.0);
+    resn.assign(ncols, 0.0);
+    std::vector<double> g0((size_t)B * B), g1((size_t)B * B), g2((size_t)B * B), m1((size_t)B * B);
+    double* Xa = cur;
+    double* Xb = U;
+    for (int64_t c0 = 0; c0 < ncols; c0 += b) {
+        const int nb = (int)std::min<int64_t>(b, ncols - c0);
+        launch_colmajor_to_block(B, nloc, nb, V + (size_t)c0 * nloc, nloc, Xa, st);
+        ++launches;
+        apply_plain(Xa, Xb);
+        RowOpArgs a0;
+        a0.n = nloc; a0.y = Xa; a0.do_gram = 1; a0.partials = w.part.p;
+        rowop(a0);
+        finish_gram(G());
+        RowOpArgs a1;
+        a1.n = nloc; a1.y = Xb; a1.gram_z = Xa; a1.do_gram = 1; a1.partials = w.part.p;
+        rowop(a1);
+        finish_gram(Ai());
+        RBL_CUDA(cudaMemcpyAsync(g0.data(), G(), g0.size() * 8, cudaMemcpyDeviceToHost, st));
+        RBL_CUDA(cudaMemcpyAsync(g1.data(), Ai(), g1.size() * 8, cudaMemcpyDeviceToHost, st));
+        RBL_CUDA(cudaStreamSynchronize(st));
+        std::fill(m1.begin(), m1.end(), 0.0);
+        for (int c = 0; c < nb; ++c) {
+            const double vv = g0[(size_t)c * B + c];
+            lam[c0 + c] = vv > 0 ? g1[(size_t)c * B + c] / vv : 0.0;
+            m1[(size_t)c * B + c] = lam[c0 + c];
+        }
+        RBL_CUDA(cudaMemcpyAsync(Gloc(), m1.data(), m1.size() * 8, cudaMemcpyHostToDevice, st));
+        RowOpArgs a2;
+        a2.n = nloc; a2.y = Xb; a2.x1 = Xa; a2.m1 = Gloc(); a2.write_y = 1; a2.do_gram = 1; a2.partials = w.part.p;
+        rowop(a2);
+        finish_gram(G());
+        RBL_CUDA(cudaMemcpyAsync(g2.data(), G(), g2.size() * 8, cudaMemcpyDeviceToHost, st));
+        RBL_CUDA(cudaStreamSynchronize(st));
+        for (int c = 0; c < nb; ++c) {
+            const double vv = g0[(size_t)c * B + c];
+            resn[c0 + c] = vv > 0 ? std::sqrt(std::max(0.0, g2[(size_t)c * B + c]) / vv) : 0.0;
+        }
+    }
+}
+
+void fill_stats(rbl_stats* s, Run& c, double* sec) {
+    s->t_spmm = sec[PH_SPMM];
+    s->t_3term = sec[PH_3TERM];
+    s->t_qr = sec[PH_QR];
+    s->t_loc_reorth = sec[PH_LOC];
+    s->t_part_reorth = sec[PH_RGRAM] + sec[PH_RUPD];
+    s->t_reorth_gram = sec[PH_RGRAM];
+    s->t_reorth_update = sec[PH_RUPD];
+    s->t_ritz = sec[PH_RITZ];
+    s->t_ritz_kernel = sec[PH_RITZ];
+    s->bytes_reorth_gram = c.bytes_rgram;
+    s->bytes_reorth_update = c.bytes_rupd;
+    s->bytes_part_reorth = c.bytes_rgram + c.bytes_rupd;
+    s->bytes_spmm = c.bytes_spmm;
+    s->launches_reorth_gram = c.n_rgram;
+    s->launches_reorth_update = c.n_rupd;
+    s->launches_spmm = c.n_spmm;
+    s->kernel_launches = c.launches;
+}
+
+}  // namespace
+
+int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_out, rbl_stats* stats_out) {
+    const double t_begin = now_s();
+    rbl_stats stats;
+    std::memset(&stats, 0, sizeof(stats));
+    const rbl_options& opt = h->opt;
+    if (k <= 0 || b_in <= 0 || b_in > 32) throw Error(RBL_INVALID, "rbl_solve: need k >= 1 and 1 <= b <= 32");
+    if (k > h->n) throw Error(RBL_INVALID, "rbl_solve: k > n");
+    if (!d_out || !io.v) throw Error(RBL_INVALID, "rbl_solve: null output");
+    RBL_CUDA(cudaSetDevice(h->device));
+    Run c(h);
+    Workspace& w = c.w;
+    c.b = (int)b_in; c.B = padded_block(c.b); c.k = k;
+    c.fp32 = opt.precision == RBL_PRECISION_MIXED;
+    c.ssz = c.fp32 ? 4 : 8;
+    c.nloc = h->nloc; c.next = h->nloc + h->n_halo;
+    c.bstride = c.nloc * c.B;
+    c.tm.h = h; c.tm.st = c.st;
+    c.multi = h->comm.active();
+    c.is_root = (h->rank == 0);
+    const int b = c.b, B = c.B;
+    c.kryl_sz = std::max<int64_t>(opt.max_kryl_sz, b);
+    int64_t m_req = (c.kryl_sz + b - 1) / b;
+    c.reorth_period = std::max(1, opt.reorth_period);
+    c.check_period = std::max(1, opt.check_period);
+    // the asynchronous order equals the synchronous one only if the speculative steps never touch an accepted block:
+    // checks fall on reorth steps and the refresh of slot(i-2) stays behind them (reorth_period >= 2)
+    c.async_ok = opt.async_check && c.reorth_period >= 2 && (c.check_period % c.reorth_period == 0);
+    int fdeg = opt.filter_degree < 0 ? 8 : opt.filter_degree;
+    const bool filtering = fdeg > 0;
+    const bool extra = filtering || opt.restart;
+    c.base = (opt.op == RBL_OP_SHIFT_MINUS_A) ? SpmmCoef{-1.0, opt.sigma, 0.0} : SpmmCoef{1.0, 0.0, 0.0};
+    RBL_CUDA(cudaEventCreateWithFlags(&c.tail_event, cudaEventDisableTiming));
+    w.ctrl.ensure(4);
+    w.h_ctrl.ensure(4);
+
+    // ---- memory plan (gpu_buffer_size, RBL_gpu.jl:95-104: how many Krylov blocks fit) ---------------
+    MemPlan plan = plan_memory(h, k, b, m_req);
+    int64_t m_fit = plan.m_fit;
+    if (c.multi) {
+        // every rank must leave the iteration at the same step: agree on the smallest capacity
+        DevBuf<int64_t> d_s, d_r;
+        d_s.alloc(1);
+        d_r.alloc(h->world);
+        std::string err;
+        RBL_CUDA(cudaMemcpyAsync(d_s.p, &m_fit, 8, cudaMemcpyHostToDevice, c.st));
+        c.nccl(h->comm.allgather_i64(d_s.p, d_r.p, 1, c.st, err), err);
+        std::vector<int64_t> all(h->world);
+        RBL_CUDA(cudaMemcpyAsync(all.data(), d_r.p, all.size() * 8, cudaMemcpyDeviceToHost, c.st));
+        RBL_CUDA(cudaStreamSynchronize(c.st));
+        m_fit = *std::min_element(all.begin(), all.end());
+    }
+    if (m_fit < 3) throw Error(RBL_OOM, "rbl_solve: problem does not fit device memory (fewer than 3 Krylov blocks)");
+    int64_t m_cap = std::min(m_req, m_fit);
+    const bool mem_capped = m_fit < m_req;
+    if (mem_capped && !opt.restart)
+        std::fprintf(stderr, "[rbl] warning: Krylov buffer capped at %lld blocks by device memory (%lld requested); "
+                             "set opts.restart to continue past the cap\n", (long long)m_cap, (long long)m_req);
+    c.m_cap = m_cap;
+    stats.buffer_blocks = m_cap;
+    c.rgrid = rowop_grid(B, c.nloc);
+    const int nX = 3 + (filtering ? 1 : 0);
+    for (int i = 0; i < nX; ++i) w.X[i].ensure((size_t)c.next * B);
+    w.buf.ensure((size_t)m_cap * c.bstride * c.ssz);
+    w.part.ensure((size_t)c.rgrid * B * B);
+    w.small.ensure(4 * (size_t)B * B);
+    w.qr.ensure(1);
+    w.Cmat.ensure((size_t)m_cap * B * 2 * B * c.ssz);
+    w.rpart.ensure(std::max<size_t>(1, reorth_max_partial_elems(B, c.fp32, c.nloc, m_cap)) * c.ssz);
+    if (opt.reorth_impl >= 3 && !reorth_h_supported(B, c.fp32))
+        throw Error(RBL_INVALID, "rbl_solve: FP16-split tensor-core reorth needs precision=mixed and padded block size 16 or 32");
+    if (opt.reorth_impl == 2) throw Error(RBL_INVALID, "rbl_solve: reorth_impl 2 (3xTF32) was removed; use 0, 1, 3 or 4");
+    c.use_h = reorth_h_supported(B, c.fp32) && opt.reorth_impl != 1;
+    c.split_scale = (c.use_h && opt.reorth_impl != 3) ? reorth_h_scale(h->n) : 0.f;
+    c.use_d = reorth_d_supported(B, c.fp32) && opt.reorth_impl != 1;
+    if (c.use_h) w.tc_scratch.ensure(reorth_h_scratch_words(B, c.nloc, m_cap));
+    if (c.multi) w.sendbuf.ensure(std::max<int64_t>(1, h->send_ptr[h->world]) * (size_t)B);
+    w.hA.ensure((size_t)m_cap * B * B);
+    w.hB.ensure((size_t)m_cap * B * B);
+    w.hqr.ensure(1);
+    if (extra) w.Vacc.ensure((size_t)c.nloc * k);
+    const double t_alloc_done = now_s();
+    RBL_CUDA(cudaMemsetAsync(w.qr.p, 0, sizeof(QrState), c.st));
+    RBL_CUDA(cudaMemsetAsync(w.small.p, 0, 4 * (size_t)B * B * 8, c.st));
+    for (int i = 0; i < nX; ++i) RBL_CUDA(cudaMemsetAsync(w.X[i].p, 0, (size_t)c.next * B * 8, c.st));
+    h->last = KrylovInfo{};
+
+    // ---- start block: Q1 = thin-Q of qr(A * Omega)                              RBL_gpu.jl:213-214 ----
+    DevBuf<double>& d_omega = w.omega;
+    const double* om_dev = nullptr;
+    int64_t om_ld = c.nloc;
+    {
+        const double t0 = now_s();
+        if (io.omega && io.omega_on_device) {
+            om_dev = io.omega;
+            om_ld = io.ld_omega;
+        } else {
+            d_omega.ensure((size_t)c.nloc * b);
+            if (io.omega) {
+                RBL_CUDA(cudaMemcpy2DAsync(d_omega.p, (size_t)c.nloc * 8, io.omega, (size_t)io.ld_omega * 8, (size_t)c.nloc * 8, b,
+                                           cudaMemcpyHostToDevice, c.st));
+            } else {
+                const uint64_t seed = opt.seed ? (uint64_t)(uint32_t)opt.seed : 0x5eedull;
+                for (int col = 0; col < b; ++col)
+                    launch_randn(c.nloc, seed, (uint64_t)col * (uint64_t)h->n + (uint64_t)h->row0,
+                                 d_omega.p + (size_t)col * c.nloc, c.st);
+            }
+            om_dev = d_omega.p;
+            RBL_CUDA(cudaStreamSynchronize(c.st));
+        }
+        stats.t_h2d = (now_s() - t0) + h->t_h2d_create;
+    }
+    c.cur = w.X[1].p; c.prev = w.X[0].p; c.U = w.X[2].p; c.P1 = filtering ? w.X[3].p : nullptr;
+    launch_colmajor_to_block(B, c.nloc, b, om_dev, om_ld, w.X[0].p, c.st);
+    ++c.launches;
+    c.tm.mark(PH_SPMM);
+    c.apply_plain(w.X[0].p, c.cur);
+    c.tm.mark(PH_QR);
+    {
+        c.gram_then_qr(c.cur, 1);
+        // a start block of rank 0 (Omega = 0, or A*Omega = 0) spans no Krylov space: report it instead of
+        // iterating on zero columns (the reference's Householder QR would continue with arbitrary unit vectors)
+        RBL_CUDA(cudaMemcpyAsync(w.hqr.p, w.qr.p, sizeof(QrState), cudaMemcpyDeviceToHost, c.st));
+        RBL_CUDA(cudaStreamSynchronize(c.st));
+        if (w.hqr.p->bad) throw Error(RBL_INVALID, "rbl_solve: A*Omega contains non-finite values");
+        if (w.hqr.p->ndeflated >= B) throw Error(RBL_BREAKDOWN, "rbl_solve: the start block A*Omega has rank 0");
+    }
+    c.tm.mark(PH_NONE);
+
+    // ---- filter placement: a short plain probe run locates the wanted end of the spectrum ------------------
+    if (filtering) {
+        const int64_t kk = k + b;
+        int64_t s = opt.probe_steps > 0 ? opt.probe_steps : std::max<int64_t>(8, 2 * ((kk + b - 1) / b));
+        s = std::min<int64_t>(s, m_cap);
+        if (s * b < k) throw Error(RBL_INVALID, "rbl_solve: Krylov cap too small for the filter probe");
+        // keep Q1: the probe rotates the active blocks
+        RBL_CUDA(cudaMemcpyAsync(c.P1, c.cur, (size_t)c.nloc * B * 8, cudaMemcpyDeviceToDevice, c.st));
+        CycleOut pr = c.cycle(0, k, std::min<int64_t>(kk, s * b), true, s);
+        const TopKResult& r = pr.res;
+        const int64_t have = (int64_t)r.d.size();
+        const int64_t kq = std::min<int64_t>(k, have);
+        FilterPlan f;
+        f.degree = fdeg;
+        const double cut = std::fabs(r.d[have - 1]);
+        bool allpos = true, allneg = true;
+        for (int64_t j = 0; j < have; ++j) { allpos &= r.d[j] > 0; allneg &= r.d[j] < 0; }
+        const double s_lo = c.base.alpha > 0 ? c.base.alpha * h->gersh_lo + c.base.beta : c.base.alpha * h->gersh_hi + c.base.beta;
+        const double s_hi = c.base.alpha > 0 ? c.base.alpha * h->gersh_hi + c.base.beta : c.base.alpha * h->gersh_lo + c.base.beta;
+        if (allpos) { f.a = s_lo < cut ? s_lo : cut - std::fabs(cut); f.b = cut; }
+        else if (allneg) { f.a = -cut; f.b = s_hi > -cut ? s_hi : -cut + std::fabs(cut); }
+        else { f.two_sided = true; f.a = -cut; f.b = cut; if (!(f.degree & 1)) ++f.degree; }
+        if (!(f.e() > 0)) throw Error(RBL_BREAKDOWN, "rbl_solve: filter probe found a degenerate spectrum interval");
+        f.rho = 1.0;
+        const double tk = std::fabs(f.eval(r.d[kq - 1]));
+        const double xk = std::fabs((r.d[kq - 1] - f.c()) / f.e());
+        f.rho = (tk > 0 && xk > 1.0) ? std::fabs(r.d[0]) / tk : 1.0;
+        c.flt = f;
+        stats.filter_cut = cut;
+        stats.filter_degree = f.degree;
+        stats.filter_two_sided = f.two_sided ? 1 : 0;
+        if (opt.verbose)
+            std::fprintf(stderr, "[rbl] filter: probe %lld steps, degree %d, damped [%.6g, %.6g], rho %.3e, %s\n", (long long)pr.iterations_run,
+                         f.degree, f.a, f.b, f.rho, f.two_sided ? "two-sided" : "one-sided");
+        c.total_steps_run += pr.iterations_run;
+        // restart from Q1
+        c.cur = w.X[1].p; c.prev = w.X[0].p; c.U = w.X[2].p;
+        RBL_CUDA(cudaMemcpyAsync(c.cur, c.P1, (size_t)c.nloc * B * 8, cudaMemcpyDeviceToDevice, c.st));
+    }
+
+    // ---- cycles: iterate; at the cap lock what converged and restart (restarted.jl:98-146) ---------------
+    int64_t nlock = 0;                 // locked Ritz vectors (columns of Vacc)
+    std::vector<double> d_lock;
+    int status = RBL_OK;
+    CycleOut last;
+    int64_t nlb = 0;
+    int64_t cycles = 0;
+    const int64_t max_cycles = 50;
+    bool converged = false;
+    double t_loop_done = now_s();
+    for (;;) {
+        ++cycles;
+        const int64_t k_rem = k - nlock;
+        const int64_t kk_end = opt.restart ? k_rem + b : k_rem;
+        const int64_t max_steps = std::max<int64_t>(1, (c.kryl_sz + b - 1) / b - nlb);
+        last = c.cycle(nlb, k_rem, kk_end, false, max_steps);
+        c.total_steps += last.final_i;
+        c.total_steps_run += last.iterations_run;
+        if (last.converged) { converged = true; break; }
+        if (!opt.restart || cycles >= max_cycles) { status = RBL_NOT_CONVERGED; break; }
+        // ---- lock + restart -------------------------------------------------------------------------------
+        const TopKResult& r = last.res;
+        const int64_t have = (int64_t)r.d.size();
+        std::vector<int64_t> lock, rest;
+        for (int64_t j = 0; j < have; ++j) {
+            if (j < k_rem && r.resid[j] <= opt.tol) lock.push_back(j);
+            else if ((int64_t)rest.size() < b) rest.push_back(j);
+        }
+        {   // is there room for another cycle once these are locked?  If not: best effort from this cycle, as at the cap
+            const int64_t nlb_next = (nlock + (int64_t)lock.size() + b - 1) / b;
+            const bool done = nlock + (int64_t)lock.size() >= k;
+            if (!done && (m_cap - nlb_next < 3 || (c.kryl_sz + b - 1) / b - nlb_next < 3)) { status = RBL_NOT_CONVERGED; break; }
+        }
+        std::vector<int64_t> cols = lock;
+        cols.insert(cols.end(), rest.begin(), rest.end());
+        w.ritzV.ensure((size_t)c.nloc * (size_t)std::max<int64_t>(((int64_t)lock.size() + b) * 8, k * (opt.v_fp32 ? 4 : 8)));
+        double* Vtmp = reinterpret_cast<double*>(w.ritzV.p);
+        // with the tensor-core Ritz kernel on a split16 slab or an fp32 slab the vectors are fp32-grade, as in the reference
+        c.ritz(nlb, last.final_i, r, cols, Vtmp, c.nloc, false, stats);
+        const int64_t nl = (int64_t)lock.size();
+        if (nl) RBL_CUDA(cudaMemcpyAsync(w.Vacc.p + (size_t)nlock * c.nloc, Vtmp, (size_t)nl * c.nloc * 8, cudaMemcpyDeviceToDevice, c.st));
+        for (int64_t j = 0; j < nl; ++j) d_lock.push_back(r.d[lock[j]]);
+        // the slab head holds the locked vectors in whole blocks of b columns (zero padded)
+        const int64_t first_blk = nlock / b;
+        nlock += nl;
+        const int64_t nlb_new = (nlock + b - 1) / b;
+        for (int64_t blk = first_blk; blk < nlb_new; ++blk) {
+            const int ncol = (int)std::min<int64_t>(b, nlock - blk * b);
+            launch_colmajor_to_block(B, c.nloc, ncol, w.Vacc.p + (size_t)blk * b * c.nloc, c.nloc, c.U, c.st);
+            launch_store_block(B, c.nloc, c.U, c.slot(blk), c.fp32, c.split_scale, c.st);
+            c.launches += 2;
+        }
+        nlb = nlb_new;
+        stats.restarts = cycles;
+        stats.locked = nlock;
+        if (opt.verbose)
+            std::fprintf(stderr, "[rbl] restart %lld: locked %lld (+%lld), %lld blocks of the slab hold locked vectors\n", (long long)cycles,
+                         (long long)nlock, (long long)nl, (long long)nlb);
+        if (nlock >= k) { converged = true; last.final_i = 0; break; }
+        // restart block: the best b not-locked Ritz vectors (missing columns: fresh random directions)
+        c.cur = w.X[1].p; c.prev = w.X[0].p; c.U = w.X[2].p;
+        const int nr = (int)rest.size();
+        if (nr < b) {
+            for (int col = nr; col < b; ++col)
+                launch_randn(c.nloc, 0x5eedull + (uint64_t)cycles, (uint64_t)col * (uint64_t)h->n + (uint64_t)h->row0,
+                             Vtmp + (size_t)(nl + col) * c.nloc, c.st);
+        }
+        launch_colmajor_to_block(B, c.nloc, b, Vtmp + (size_t)nl * c.nloc, c.nloc, c.cur, c.st);
+        ++c.launches;
+        RBL_CUDA(cudaMemsetAsync(c.prev, 0, (size_t)c.next * B * 8, c.st));
+        if (nlb > 0) {   // restart_reorth_gpu! (restarted.jl:1-21): start block orthogonal to the locked vectors
+            c.reorth_gram(nlb, c.cur, c.prev);
+            c.reorth_update(nlb, c.cur, c.prev, nullptr);
+        }
+        c.gram_then_qr(c.cur, 1);
+    }
+    t_loop_done = now_s();
+    stats.restarts = cycles - 1;
+    stats.locked = nlock;
+
     const double t_final_done = now_s();
     // ---- Ritz vectors V = Qbuf * S                                              RBL_gpu.jl:106-132,219 ----
-    const int64_t mfin = final_i;
-    const int kpad = (int)((k + 15) / 16 * 16);
-    {
-        std::vector<unsigned char> Sh((size_t)mfin * B * kpad * c.ssz, 0);
-        for (int64_t j = 0; j < mfin; ++j)
-            for (int cc = 0; cc < b; ++cc)
-                for (int64_t t = 0; t < k; ++t) {
-                    const double v = final_res.s[(size_t)t * final_res.N + (size_t)j * b + cc];
-                    const size_t idx = ((size_t)j * B + cc) * kpad + t;
-                    if (c.fp32) reinterpret_cast<float*>(Sh.data())[idx] = (float)v;   // cu() narrows S, RBL_gpu.jl:119
-                    else reinterpret_cast<double*>(Sh.data())[idx] = v;
-                }
-        const double tr0 = now_s();
-        DevBuf<unsigned char>&dS = h->ws_ref().ritzS, &dV = h->ws_ref().ritzV;
-        dS.ensure(Sh.size());
-        RBL_CUDA(cudaMemcpyAsync(dS.p, Sh.data(), Sh.size(), cudaMemcpyHostToDevice, c.st));
-        const size_t vsz = opt.v_fp32 ? 4 : 8;
-        void* Vdev = v_out;
-        if (!v_on_device) {
-            dV.ensure((size_t)c.nloc * k * vsz);
-            Vdev = dV.p;
+    const size_t vsz = opt.v_fp32 ? 4 : 8;
+    const int64_t mfin = last.final_i;
+    const int64_t k_fin = k - nlock;
+    std::vector<double> d_all(d_lock);
+    for (int64_t t = 0; t < k_fin; ++t) d_all.push_back(last.res.d.size() > (size_t)t ? last.res.d[t] : 0.0);
+    std::vector<int64_t> fin_cols((size_t)k_fin);
+    std::iota(fin_cols.begin(), fin_cols.end(), 0);
+    if (!extra) {
+        // the reference's single-cycle path: the Ritz kernel writes straight into the caller's V
+        void* Vdev = io.v;
+        int64_t ldv = io.ldv;
+        if (!io.v_on_device) {
+            w.ritzV.ensure((size_t)c.nloc * k * vsz);
+            Vdev = w.ritzV.p;
+            ldv = c.nloc;
         }
-        const double tr1 = now_s();
-        c.tm.mark(PH_RITZ);
-        DevBuf<unsigned>& ritz_words = h->ws_ref().ritz_words;
-        if (c.split_scale != 0.f) {
-            ritz_words.ensure(ritz_h_scratch_words(B, mfin, kpad));
-            launch_ritz_h(B, c.nloc, mfin, (int)k, kpad, c.buf.p, c.bstride, dS.p, Vdev, c.nloc, opt.v_fp32, c.split_scale,
-                          ritz_words.p, c.st);
-            ++c.launches;
-        } else {
-            launch_ritz(B, c.fp32, c.nloc, mfin, (int)k, kpad, c.buf.p, c.bstride, dS.p, Vdev, c.nloc, opt.v_fp32, 0.f, c.st);
-        }
-        ++c.launches;
-        c.tm.mark(PH_NONE);
-        RBL_CUDA(cudaStreamSynchronize(c.st));
-        stats.bytes_ritz = (double)c.ssz * (double)c.nloc * (double)mfin * B + (double)vsz * (double)c.nloc * (double)k;
-        stats.flops_ritz = 2.0 * (double)c.nloc * (double)mfin * B * (double)k;
-        if (!v_on_device) {
+        c.ritz(0, mfin, last.res, fin_cols, Vdev, ldv, opt.v_fp32 != 0, stats);
+        if (!io.v_on_device) {
             const double t0 = now_s();
-            RBL_CUDA(cudaMemcpy(v_out, dV.p, (size_t)c.nloc * k * vsz, cudaMemcpyDeviceToHost));
+            RBL_CUDA(cudaMemcpy2D(io.v, (size_t)io.ldv * vsz, w.ritzV.p, (size_t)c.nloc * vsz, (size_t)c.nloc * vsz, k, cudaMemcpyDeviceToHost));
             stats.t_d2h = now_s() - t0;
         }
-        if (opt.verbose) std::fprintf(stderr, "[rbl] ritz section: setup %.3f kernel+sync %.3f\n", tr1 - tr0, now_s() - tr1 - stats.t_d2h);
+        for (int64_t t = 0; t < k; ++t) d_out[t] = d_all[t];
+    } else {
+        if (k_fin > 0 && mfin > 0) c.ritz(nlb, mfin, last.res, fin_cols, w.Vacc.p + (size_t)nlock * c.nloc, c.nloc, false, stats);
+        std::vector<double> lam = d_all, resn;
+        if (filtering) {
+            // eigenvalues of op(A) from the Ritz vectors of p(op(A)); true residuals measured in fp64
+            c.cur = w.X[1].p; c.U = w.X[2].p;
+            c.rayleigh(w.Vacc.p, k, lam, resn);
+            stats.max_residual = *std::max_element(resn.begin(), resn.end());
+        }
+        std::vector<int64_t> perm((size_t)k);
+        std::iota(perm.begin(), perm.end(), 0);
+        std::stable_sort(perm.begin(), perm.end(), [&](int64_t x, int64_t y) { return std::fabs(lam[x]) > std::fabs(lam[y]); });
+        for (int64_t t = 0; t < k; ++t) d_out[t] = lam[perm[t]];
+        // output column t = Vacc column perm[t] (descending |lambda|, RBL.jl:116)
+        const double t0 = now_s();
+        if (!opt.v_fp32) {
+            for (int64_t t = 0; t < k; ++t)
+                RBL_CUDA(cudaMemcpyAsync((char*)io.v + (size_t)t * io.ldv * 8, w.Vacc.p + (size_t)perm[t] * c.nloc, (size_t)c.nloc * 8,
+                                         io.v_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.st));
+        } else {
+            w.ritzV.ensure((size_t)c.nloc * k * 4);
+            for (int64_t t = 0; t < k; ++t) {
+                launch_convert_s(c.nloc, w.Vacc.p + (size_t)perm[t] * c.nloc, w.ritzV.p + (size_t)t * c.nloc * 4, 1, c.st);
+                RBL_CUDA(cudaMemcpyAsync((char*)io.v + (size_t)t * io.ldv * 4, w.ritzV.p + (size_t)t * c.nloc * 4, (size_t)c.nloc * 4,
+                                         io.v_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.st));
+            }
+        }
+        RBL_CUDA(cudaStreamSynchronize(c.st));
+        if (!io.v_on_device) stats.t_d2h = now_s() - t0;
     }
-    for (int64_t t = 0; t < k; ++t) d_out[t] = final_res.d[t];
-    RBL_CUDA(cudaMemcpy(c.hqr.p, c.qr.p, sizeof(QrState), cudaMemcpyDeviceToHost));
+    RBL_CUDA(cudaMemcpy(w.hqr.p, w.qr.p, sizeof(QrState), cudaMemcpyDeviceToHost));
+    h->last.B = B; h->last.b = b; h->last.blocks = nlb + mfin; h->last.fp32 = c.fp32; h->last.split_scale = c.split_scale;
+    h->last.bstride = c.bstride; h->last.ssz = c.ssz; h->last.use_h = c.use_h; h->last.use_d = c.use_d; h->last.m_cap = m_cap;
 
     double sec[PH_COUNT];
-    const double tc0 = now_s();
     c.tm.collect(sec);
-    if (opt.verbose) std::fprintf(stderr, "[rbl] event collect %.3f s (%zu events)\n", now_s() - tc0, c.tm.used);
     fill_stats(&stats, c, sec);
-    stats.iterations = final_i;
-    stats.kryl_sz = final_i * b;
-    stats.iterations_run = iterations_run;
+    stats.iterations = c.total_steps;
+    stats.kryl_sz = c.total_steps * b;
+    stats.iterations_run = c.total_steps_run;
     stats.converged = converged ? 1 : 0;
-    stats.checks = checks;
-    stats.full_checks = checker.full_checks;
-    stats.host_factorizations = checker.total_factorizations;
-    stats.deflated = c.hqr.p->ndeflated - (B - b);
-    stats.t_eig = t_eig;
-    stats.t_eig_wait = t_wait;
+    stats.checks = c.checks;
+    stats.full_checks = c.full_checks;
+    stats.host_factorizations = c.host_factorizations;
+    stats.deflated = w.hqr.p->ndeflated - (B - b);
+    stats.t_eig = c.t_eig;
+    stats.t_eig_wait = c.t_idle;
+    stats.t_host_blocked = c.t_blocked;
     stats.t_total = now_s() - t_begin;
-    if (c.hqr.p->bad) status = RBL_BREAKDOWN;
+    if (w.hqr.p->bad) status = RBL_BREAKDOWN;
     if (stats_out) *stats_out = stats;
     if (opt.verbose)
-        std::fprintf(stderr, "[rbl] host checks: witness %d (%.3f s), bracketed %d (%.3f s), full %d (%.3f s); factorisations %lld (+%lld resumed)\n",
-                     checker.stage_hits[0], checker.stage_sec[0], checker.stage_hits[1], checker.stage_sec[1], checker.stage_hits[2],
-                     checker.stage_sec[2], (long long)checker.total_factorizations, (long long)checker.resumed_factorizations);
+        std::fprintf(stderr, "[rbl] timeline: alloc %.3f  start+loop %.3f  ritz+d2h %.3f (d2h %.3f, h2d %.3f)\n",
+                     t_alloc_done - t_begin, t_loop_done - t_alloc_done, now_s() - t_final_done, stats.t_d2h, stats.t_h2d);
     if (opt.verbose)
-        std::fprintf(stderr, "[rbl] timeline: alloc %.3f  start+loop %.3f  final-check %.3f  ritz+d2h %.3f (d2h %.3f, h2d %.3f)\n",
-                     t_alloc_done - t_begin, t_loop_done - t_alloc_done, t_final_done - t_loop_done,
-                     now_s() - t_final_done, stats.t_d2h, stats.t_h2d);
-    if (opt.verbose)
-        std::fprintf(stderr, "[rbl] Iterations: %lld and kryl_sz: %lld (ran %lld), checks %d (full %d), t=%.3fs eig=%.3fs wait=%.3fs\n",
-                     (long long)final_i, (long long)(final_i * b), (long long)iterations_run, checks,
-                     checker.full_checks, stats.t_total, t_eig, t_wait);
+        std::fprintf(stderr, "[rbl] Iterations: %lld and kryl_sz: %lld (ran %lld), cycles %lld, locked %lld, checks %d (full %d), t=%.3fs eig=%.3fs device-idle=%.3fs\n",
+                     (long long)c.total_steps, (long long)(c.total_steps * b), (long long)c.total_steps_run, (long long)cycles, (long long)nlock,
+                     c.checks, c.full_checks, stats.t_total, c.t_eig, c.t_idle);
     return status;
+}
+
+// ------------------------------------------------------------------------------------------------ basis exports
+void krylov_block(rbl_handle* h, int64_t j, double* out_colmajor) {
+    const KrylovInfo& L = h->last;
+    if (L.blocks <= 0) throw Error(RBL_INVALID, "rbl_krylov_block: no solve has run on this handle");
+    if (j < 0 || j >= L.blocks) throw Error(RBL_INVALID, "rbl_krylov_block: block index out of range");
+    RBL_CUDA(cudaSetDevice(h->device));
+    Workspace& w = h->ws_ref();
+    const int64_t nloc = h->nloc;
+    double* blk = w.X[0].p;
+    launch_decode_block(L.B, nloc, w.buf.p + (size_t)j * L.bstride * L.ssz, L.fp32, L.split_scale, blk, h->stream);
+    DevBuf<double> cm;
+    cm.alloc((size_t)nloc * L.b);
+    launch_block_to_colmajor(L.B, nloc, L.b, blk, cm.p, nloc, h->stream);
+    RBL_CUDA(cudaStreamSynchronize(h->stream));
+    RBL_CUDA(cudaMemcpy(out_colmajor, cm.p, (size_t)nloc * L.b * 8, cudaMemcpyDeviceToHost));
+}
+
+// max |(Q'Q - I)_ij| and ||Q'Q - I||_F over the stored basis, with the Gram kernels of the re-orthogonalisation
+void orthogonality(rbl_handle* h, double* max_abs, double* fro) {
+    const KrylovInfo& L = h->last;
+    if (L.blocks <= 0) throw Error(RBL_INVALID, "rbl_orthogonality: no solve has run on this handle");
+    RBL_CUDA(cudaSetDevice(h->device));
+    Run c(h);
+    Workspace& w = c.w;
+    c.B = L.B; c.b = L.b; c.fp32 = L.fp32; c.ssz = L.ssz; c.nloc = h->nloc; c.next = h->nloc + h->n_halo;
+    c.bstride = L.bstride; c.split_scale = L.split_scale; c.use_h = L.use_h; c.use_d = L.use_d; c.m_cap = L.m_cap;
+    c.multi = h->comm.active();
+    c.is_root = h->rank == 0;
+    c.tm.enabled = false;
+    c.tm.h = h; c.tm.st = c.st;
+    DevBuf<double> acc;
+    acc.alloc(2);
+    RBL_CUDA(cudaMemsetAsync(acc.p, 0, 16, c.st));
+    const int64_t m = L.blocks;
+    if (!L.fp32) {
+        for (int64_t j0 = 0; j0 < m; j0 += 2) {
+            const int nt = (int)std::min<int64_t>(2, m - j0);
+            launch_decode_block(L.B, c.nloc, c.slot(j0), 0, 0.f, w.X[0].p, c.st);
+            if (nt == 2) launch_decode_block(L.B, c.nloc, c.slot(j0 + 1), 0, 0.f, w.X[1].p, c.st);
+            else RBL_CUDA(cudaMemsetAsync(w.X[1].p, 0, (size_t)c.nloc * L.B * 8, c.st));
+            c.reorth_gram(m, w.X[0].p, w.X[1].p);
+            launch_ortho_accumulate(L.B, m, j0, nt, 0, w.Cmat.p, acc.p, c.st);
+        }
+    } else {
+        // A 4-byte slab is measured in fp64: the stored values are decoded exactly (chunk-wise, into a temporary fp64
+        // slab) and the fp64 Gram kernels accumulate - the fp32-grade reorth kernels themselves have a noise floor
+        // of ~1e-8 per entry, the size of the quantity being measured.
+        size_t free_b = 0, total_b = 0;
+        RBL_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t blk_bytes = (size_t)c.nloc * L.B * 8;
+        int64_t chunk = (int64_t)std::min<double>((double)m, std::max(1.0, (0.7 * (double)free_b) / (double)blk_bytes));
+        DevBuf<double> tmp, Cd, part;
+        tmp.alloc((size_t)chunk * c.nloc * L.B);
+        Cd.alloc((size_t)chunk * L.B * 2 * L.B);
+        part.alloc(std::max<size_t>(1, reorth_max_partial_elems(L.B, 0, c.nloc, chunk)));
+        const bool dmma = reorth_d_supported(L.B, 0);
+        for (int64_t c0 = 0; c0 < m; c0 += chunk) {
+            const int64_t cn = std::min<int64_t>(chunk, m - c0);
+            for (int64_t j = 0; j < cn; ++j)
+                launch_decode_block(L.B, c.nloc, c.slot(c0 + j), 1, L.split_scale, tmp.p + (size_t)j * c.nloc * L.B, c.st);
+            ReorthPlan p = reorth_plan(L.B, 0, c.nloc, cn);
+            for (int64_t j0 = 0; j0 < m; j0 += 2) {
+                const int nt = (int)std::min<int64_t>(2, m - j0);
+                launch_decode_block(L.B, c.nloc, c.slot(j0), 1, L.split_scale, w.X[0].p, c.st);
+                if (nt == 2) launch_decode_block(L.B, c.nloc, c.slot(j0 + 1), 1, L.split_scale, w.X[1].p, c.st);
+                else RBL_CUDA(cudaMemsetAsync(w.X[1].p, 0, (size_t)c.nloc * L.B * 8, c.st));
+                if (dmma) launch_reorth_gram_d(p, tmp.p, L.bstride, w.X[0].p, w.X[1].p, part.p, Cd.p, c.st);
+                else launch_reorth_gram(p, tmp.p, L.bstride, w.X[0].p, w.X[1].p, part.p, Cd.p, c.st);
+                if (c.multi) { std::string err; c.nccl(h->comm.allreduce_f64(Cd.p, (size_t)cn * L.B * 2 * L.B, c.st, err), err); }
+                launch_ortho_accumulate(L.B, cn, j0 - c0, nt, 0, Cd.p, acc.p, c.st);
+            }
+        }
+        RBL_CUDA(cudaStreamSynchronize(c.st));
+    }
+    double hacc[2];
+    RBL_CUDA(cudaMemcpyAsync(hacc, acc.p, 16, cudaMemcpyDeviceToHost, c.st));
+    RBL_CUDA(cudaStreamSynchronize(c.st));
+    if (max_abs) *max_abs = hacc[0];
+    if (fro) *fro = std::sqrt(hacc[1]);
 }
 
 }  // namespace rbl

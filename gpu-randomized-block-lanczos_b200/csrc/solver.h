@@ -84,7 +84,7 @@ namespace rbl {
 // a process-wide cache when a handle is destroyed and picked up by the next handle on the same device;
 // rbl_release_cached_memory() returns it to the driver (the analogue of CUDA.reclaim(), RBL_gpu.jl:201).
 struct Workspace {
-    DevBuf<double> X[3];
+    DevBuf<double> X[4];                 // three active blocks + the Chebyshev scratch block
     DevBuf<unsigned char> buf;
     DevBuf<double> part, small;
     DevBuf<QrState> qr;
@@ -94,6 +94,7 @@ struct Workspace {
     DevBuf<unsigned char> ritzS, ritzV;   // Ritz coefficient matrix and (host-output solves) the device copy of V
     DevBuf<unsigned> ritz_words;          // f16 hi/lo words of S for the tensor-core Ritz kernel
     DevBuf<double> omega;
+    DevBuf<double> Vacc;                  // restarted / filtered solves: fp64 locked + final Ritz vectors (nloc x k)
     DevBuf<double> ctrl, share;           // row-sharded runs: decision flag and the shared (D, S) of the accepting check
     PinnedBuf<double> h_ctrl;
     PinnedBuf<double> hA, hB;
@@ -116,8 +117,24 @@ void workspace_park(int device, Workspace* ws);
 void slab_cache_release_all();
 }  // namespace rbl
 
+namespace rbl {
+// what the last solve left in the Krylov slab (debug / parity exports rbl_krylov_block, rbl_orthogonality)
+struct KrylovInfo {
+    int B = 0, b = 0;
+    int64_t blocks = 0, bstride = 0, m_cap = 0;
+    bool fp32 = false, use_h = false, use_d = false;
+    float split_scale = 0.f;
+    size_t ssz = 8;
+};
+}  // namespace rbl
+
 struct rbl_handle {
     rbl_options opt{};
+    // opts.ngpus > 1: this is a group handle; the per-device handles do the work (one host thread each)
+    std::vector<rbl_handle*> parts;
+    std::vector<int64_t> part_rows;       // parts.size()+1 global row offsets
+    double gersh_lo = 0.0, gersh_hi = 0.0;  // Gershgorin interval of A (global)
+    rbl::KrylovInfo last;
     rbl::Workspace* wsp = nullptr;   // adopted from / returned to the process-wide cache
     rbl::Workspace& ws_ref() { return *wsp; }
     int device = 0;
@@ -142,8 +159,24 @@ namespace rbl {
 rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, const int64_t* rowptr,
                           const int64_t* colidx, const double* vals, int index_base, int rank, int world,
                           const void* nccl_uid, const rbl_options* opts);
-int solve(rbl_handle* h, int64_t k, int64_t b, const double* omega, bool omega_on_device, double* d_out, void* v_out,
-          bool v_on_device, rbl_stats* stats);
+// where the start block comes from and where the Ritz vectors go: column-major, leading dimensions in elements
+// (a row-sharded part of a group solve addresses its row slice of the caller's full arrays)
+struct SolveIO {
+    const double* omega = nullptr;
+    int64_t ld_omega = 0;
+    bool omega_on_device = false;
+    void* v = nullptr;
+    int64_t ldv = 0;
+    bool v_on_device = false;
+};
+int solve(rbl_handle* h, int64_t k, int64_t b, const SolveIO& io, double* d_out, rbl_stats* stats);
+struct MemPlan {
+    double budget = 0, fixed = 0, per_block = 0;
+    int64_t m_fit = 0;
+};
+MemPlan plan_memory(rbl_handle* h, int64_t k, int b, int64_t m_req);
+void krylov_block(rbl_handle* h, int64_t j, double* out_colmajor);
+void orthogonality(rbl_handle* h, double* max_abs, double* fro);
 void default_options(rbl_options* o);
 
 }  // namespace rbl

@@ -59,9 +59,25 @@ typedef struct {
     int32_t host_threads;  /* worker threads for the final host eigensolve (0: hardware)          */
     int32_t v_fp32;        /* 1: V_out is float (reference's FLOAT=Float32 build), else double    */
     int32_t verbose;
-    int32_t reorth_impl;   /* 0: auto; 1: SIMT; 2: tensor-core TF32x3; 3: tensor-core scaled FP16 split of an
-                              fp32 buffer; 4: the same with the buffer stored pre-split (auto picks 4)     */
-    int32_t reserved[7];
+    int32_t reorth_impl;   /* 0: auto; 1: SIMT; 3: tensor-core scaled FP16 split of an fp32 buffer; 4: the same
+                              with the buffer stored pre-split (auto picks 4 in mixed precision, B = 16/32) */
+    int32_t seed;          /* stream of the counter-based device generator used when omega == NULL (the reference
+                              never seeds CUDA.randn, RBL_gpu.jl:213); 0 selects the default stream           */
+    int32_t ngpus;         /* > 1: rbl_create row-shards A over devices [device, device+ngpus) of THIS process
+                              (one host thread + one NCCL rank per device); rbl_solve then takes / returns the
+                              full n x b Omega and n x k V like the single-GPU call                          */
+    int32_t filter_degree; /* 0: iterate with the operator itself (the reference); d > 0: iterate with the
+                              degree-d Chebyshev-filtered operator p(op(A)) (N1, generalises restarted.jl);
+                              -1: pick a degree                                                              */
+    int32_t restart;       /* 1: when the Krylov cap (max_kryl_sz or device memory) is reached, lock the converged
+                              Ritz pairs and restart from the best unconverged ones (restarted.jl:23-146)
+                              instead of returning RBL_NOT_CONVERGED                                         */
+    int32_t spill;         /* 1: Krylov blocks that do not fit device memory are kept in pinned host memory and
+                              streamed back for the re-orthogonalisation (hybrid_part_reorth!, RBL_gpu.jl:59-81) */
+    int32_t probe_steps;   /* filtered solves: plain block steps used to locate the wanted end of the spectrum
+                              (0: automatic)                                                                 */
+    int32_t mem_limit_mb;  /* device-memory budget of a solve in MiB (0: what cudaMemGetInfo reports); lets the
+                              capped / spill / restart paths be exercised on small problems                  */
 } rbl_options;
 
 /* Per-solve statistics; phase labels are the reference's TimerOutputs labels (RBL_gpu.jl:152-187,219). */
@@ -83,7 +99,8 @@ typedef struct {
     double t_ritz;           /* "Ritz vectors" device seconds                                     */
     double t_h2d;            /* upload of A and Omega (e2e accounting)                            */
     double t_d2h;            /* download of V                                                     */
-    double t_eig_wait;       /* host seconds the device loop was stalled waiting for a check      */
+    double t_eig_wait;       /* seconds the DEVICE sat idle because the host was still waiting for the
+                                result of a convergence check (measured by polling the stream)     */
     double bytes_part_reorth;/* algorithmic HBM bytes streamed by the reorth Gram+update kernels  */
     double bytes_spmm;       /* algorithmic bytes of all SpMM launches                            */
     int64_t kernel_launches; /* kernels of this library launched during the solve                 */
@@ -98,7 +115,16 @@ typedef struct {
     double bytes_ritz;
     double flops_ritz;
     int64_t host_factorizations; /* band factorisations done by the host eigen-checks              */
-    double reserved[8];
+    int64_t restarts;        /* restart cycles after the first (opts.restart)                      */
+    int64_t locked;          /* Ritz pairs locked by restarts                                      */
+    int64_t spilled_blocks;  /* Krylov blocks that lived in pinned host memory (opts.spill)        */
+    int64_t buffer_blocks;   /* Krylov blocks the device buffer of this solve could hold           */
+    double max_residual;     /* filtered solves: max ||A v - lambda v|| over the returned pairs, measured on
+                                the device in fp64 with op(A) itself (0 when not computed)          */
+    double t_host_blocked;   /* host seconds the solve thread spent blocked on check results        */
+    double filter_cut;       /* |lambda| below which the filter damps (0: no filter)               */
+    int32_t filter_degree;   /* degree actually used                                               */
+    int32_t filter_two_sided;/* 1: wanted pairs on both ends of the spectrum (odd filter)          */
 } rbl_stats;
 
 typedef struct rbl_handle rbl_handle;
@@ -107,6 +133,8 @@ const char* rbl_last_error(void);
 const char* rbl_version(void);
 int rbl_device_count(void);
 int rbl_options_default(rbl_options* opts);
+/* sizeof(rbl_options), sizeof(rbl_stats) as compiled: lets a binding (ccall / ctypes) verify its struct mirrors. */
+int rbl_struct_sizes(int64_t* options_bytes, int64_t* stats_bytes);
 
 /* Replaces `Ag = adapt(CuArray, A)` (RBL_gpu.jl:209) + `matrix_size` (RBL_gpu.jl:8-22).
  * colptr (n+1), rowval (nnz), nzval (nnz): Julia SparseMatrixCSC fields of a SYMMETRIC matrix
@@ -149,8 +177,21 @@ int rbl_solve(rbl_handle* h, int64_t k, int64_t b, const double* omega, double* 
 int rbl_solve_device(rbl_handle* h, int64_t k, int64_t b, const void* omega_dev, double* d_out, void* v_dev,
                      rbl_stats* stats);
 
-/* `gpu_buffer_size` (RBL_gpu.jl:95-104): number of Krylov blocks of width b that fit the device now. */
+/* `gpu_buffer_size` (RBL_gpu.jl:95-104): number of Krylov blocks of width b that fit the device now.
+ * rbl_plan_blocks is the memory plan rbl_solve(h, k, b) itself uses (it also reserves the n x k Ritz-vector
+ * buffer); rbl_buffer_blocks == rbl_plan_blocks with k = 0. */
 int rbl_buffer_blocks(rbl_handle* h, int64_t b, int64_t* blocks_out);
+int rbl_plan_blocks(rbl_handle* h, int64_t k, int64_t b, int64_t* blocks_out);
+
+/* Debug / parity exports on the Krylov basis of the LAST solve of this handle (the reference keeps it in the
+ * `Q` / `Qgpu` vectors, RBL_gpu.jl:136-151).  Single-GPU handles.
+ *   rbl_krylov_info   number of stored blocks (locked blocks of restarted solves first) and block width b
+ *   rbl_krylov_block  block j decoded to fp64, n x b column-major, on the host
+ *   rbl_orthogonality max_abs_out = max |(Q'Q - I)_ij|, fro_out = ||Q'Q - I||_F over all stored columns, computed
+ *                     on the device with the K5a Gram kernels (an upper bound of the 2-norm the north star quotes) */
+int rbl_krylov_info(rbl_handle* h, int64_t* blocks_out, int64_t* b_out);
+int rbl_krylov_block(rbl_handle* h, int64_t j, double* out_colmajor);
+int rbl_orthogonality(rbl_handle* h, double* max_abs_out, double* fro_out);
 /* `CUDA.available_memory()` (RBL_gpu.jl:25,96). */
 int rbl_query_memory(int device, int64_t* free_bytes, int64_t* total_bytes);
 
@@ -176,7 +217,8 @@ int rbl_block_qr(int64_t n, int64_t b, double* u_inout, double* r_out, int32_t* 
  *   qbuf   m blocks, each n x b row-major, contiguous (fp32 when storage_fp32, else fp64)
  *   w      n x (2b) given as two n x b row-major fp64 blocks w0,w1 (Q_i and Q_{i-1})
  *   c_out  optional m*b x 2b row-major coefficients (float or double as storage), may be NULL
- *   impl   0 auto, 1 SIMT, 2 tensor-core TF32x3, 3 tensor-core scaled FP16 split (needs |entries| <= 1) */
+ *   impl   0 auto, 1 SIMT, 3 tensor-core scaled FP16 split of an fp32 slab, 4 the same on the pre-split slab
+ *          format the solver uses (both need |entries| <= 1) */
 int rbl_reorth(int64_t n, int64_t b, int64_t m, int storage_fp32, const void* qbuf, double* w0, double* w1,
                void* c_out, int impl);
 

@@ -1,0 +1,273 @@
+"""CPU twin of the restarted / filtered RBL solve.
+
+TEST INFRASTRUCTURE ONLY (see rbl_oracle.py header): imported by tests/ and bench.py's CPU arm, never by the product.
+
+The reference's restart is ``Julia/restarted.jl``: ``RBL_restarted`` (:196-246, CPU) / ``RBL_gpu_restarted``
+(:98-146, GPU) run a short Lanczos cycle (``new_lanczos_iteration`` :148-194 / ``lanczos_iteration_res`` :23-96),
+take the Ritz pairs in descending order, LOCK the leading ones whose residual bound is below 1e-7
+(:122-131 / :222-227: ``push!(Qlock, qv)``), restart from the first unconverged Ritz vector (:133-135 / :229-230)
+and keep every new Lanczos block orthogonal to the locked vectors (``restart_reorth_gpu!`` :1-21, called at :40,:58-59;
+``part_reorth!(length(Qlock),Qlock,...)`` :172,:187).  It is hard-wired to b = 1, never fills ``V`` (:100,:145) and
+has no tests.  What is restated here - and built on the device in csrc/solver.cu - is its generalisation:
+
+* block size b: the restart block is the b best not-yet-locked Ritz vectors (restarted.jl restarts from one);
+* every pair among the wanted ones whose bound is below tol is locked (restarted.jl stops at the first
+  unconverged one); the answer is the k largest |lambda| of locked + final pairs, and ``V`` is returned;
+* optionally the cycle iterates with a Chebyshev-filtered operator p(A) = rho * T_d((A - c)/e) that damps the
+  unwanted interval [a, b] = [c - e, c + e]: Ritz VECTORS of p(A) are Ritz vectors of A, the eigenvalues are
+  recovered as Rayleigh quotients with A, and ||A v - lambda v|| is measured explicitly.  The interval comes from a
+  short plain probe run (its Ritz values) and the Gershgorin bounds of A.
+
+Functions cite the reference lines they generalise; the arithmetic inside a cycle is rbl_oracle.lanczos_iteration
+(RBL.jl:74-117) with the locked vectors added to the periodic re-orthogonalisation.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import rbl_oracle as ro
+
+DOUBLE = np.float64
+
+
+# --------------------------------------------------------------------------- filter
+@dataclass
+class ChebFilter:
+    degree: int = 0          # 0: identity (plain operator)
+    a: float = 0.0           # damped interval [a, b]
+    b: float = 0.0
+    rho: float = 1.0         # p = rho * T_d((x - c)/e)
+    two_sided: bool = False
+
+    @property
+    def c(self):
+        return 0.5 * (self.a + self.b)
+
+    @property
+    def e(self):
+        return 0.5 * (self.b - self.a)
+
+    def scalar(self, lam):
+        """p(lam) for scalars / arrays (host-side bookkeeping only)."""
+        if self.degree == 0:
+            return np.asarray(lam, dtype=DOUBLE)
+        x = (np.asarray(lam, dtype=DOUBLE) - self.c) / self.e
+        ax = np.abs(x)
+        out = np.where(ax <= 1.0, np.cos(self.degree * np.arccos(np.clip(x, -1, 1))),
+                       np.cosh(self.degree * np.arccosh(np.maximum(ax, 1.0))) * np.where((x < 0) & (self.degree % 2 == 1), -1.0, 1.0))
+        return self.rho * out
+
+    def apply(self, A, Q):
+        """p(A) Q by the three-term recurrence t_{j+1} = 2 (A - c)/e t_j - t_{j-1}; rho folded into the last step."""
+        if self.degree == 0:
+            return np.asarray(A @ Q, dtype=DOUBLE)
+        c, e = self.c, self.e
+        t_prev = Q
+        t = (np.asarray(A @ Q, dtype=DOUBLE) - c * Q) / e
+        if self.degree == 1:
+            return self.rho * t
+        for j in range(2, self.degree + 1):
+            s = self.rho if j == self.degree else 1.0
+            t_next = s * ((2.0 / e) * (np.asarray(A @ t, dtype=DOUBLE) - c * t) - t_prev)
+            t_prev, t = t, t_next
+        return t
+
+
+def gershgorin(A):
+    """Rigorous bounds [lo, hi] of the spectrum of a symmetric sparse / dense matrix."""
+    if sp.issparse(A):
+        M = sp.csr_matrix(A)
+        d = M.diagonal()
+        r = np.asarray(abs(M).sum(axis=1)).ravel() - np.abs(d)
+    else:
+        M = np.asarray(A)
+        d = np.diag(M)
+        r = np.abs(M).sum(axis=1) - np.abs(d)
+    return float(np.min(d - r)), float(np.max(d + r))
+
+
+def place_filter(theta: np.ndarray, k: int, kk: int, degree: int, glo: float, ghi: float) -> ChebFilter:
+    """Filter from the probe's Ritz values (sorted by descending |theta|, at least kk of them).
+
+    one-sided (all k leading Ritz values of one sign): damp [gershgorin end, theta_kk]
+    two-sided: damp [-|theta_kk|, |theta_kk|] with an odd degree (p(-x) = -p(x) keeps +lambda and -lambda apart)
+    rho makes p(theta_k) = |theta_1| so that the absolute tolerance of check_convergence (common.jl:56-65) keeps its
+    meaning relative to ||A||.
+    """
+    th = np.asarray(theta, dtype=DOUBLE)
+    assert len(th) >= kk >= k >= 1
+    cut = abs(th[kk - 1])
+    lead = th[:kk]
+    f = ChebFilter(degree=degree)
+    if np.all(lead > 0):
+        f.a, f.b = (glo if glo < cut else cut - abs(cut)), cut
+    elif np.all(lead < 0):
+        f.a, f.b = -cut, (ghi if ghi > -cut else -cut + abs(cut))
+    else:
+        f.two_sided = True
+        f.a, f.b = -cut, cut
+        if degree % 2 == 0:
+            f.degree = degree + 1
+    xk = abs((th[k - 1] - f.c) / f.e)
+    f.rho = 1.0
+    tk = abs(float(f.scalar(th[k - 1])))
+    f.rho = abs(th[0]) / tk if tk > 0 and xk > 1.0 else 1.0
+    return f
+
+
+# --------------------------------------------------------------------------- one Lanczos cycle with locking
+@dataclass
+class CycleResult:
+    converged: bool
+    iterations: int
+    D: np.ndarray            # kk Ritz values of the cycle operator, descending |theta|
+    S: np.ndarray            # (iterations*b) x kk eigenvectors of T
+    bounds: np.ndarray       # kk residual bounds ||B_i S[end-b+1:end, j]||
+    Q: list = field(default_factory=list)
+
+
+def _orth_against(Y, W):
+    """restart_reorth_gpu! (restarted.jl:1-21): W -= Y (Y' W), in place."""
+    if Y is not None and Y.shape[1] > 0:
+        W -= Y @ (Y.T @ W)
+
+
+def lanczos_cycle(A, flt: ChebFilter, k_rem: int, kk: int, b: int, max_blocks: int, Q1: np.ndarray, Ylock, *,
+                  tol: float, reorth_period: int = 2, check_period: int = 4, run_to_cap: bool = False) -> CycleResult:
+    """rbl_oracle.lanczos_iteration (RBL.jl:74-117) on the operator flt(A), blocks kept orthogonal to `Ylock`
+    (restarted.jl:40,58-59,172).  Stops at the first check whose k_rem leading bounds are all <= tol, or when
+    max_blocks blocks are stored; the result then carries the kk leading Ritz pairs of the last T."""
+    Q = [Q1]
+    Qi = Q1
+    U = flt.apply(A, Qi)
+    Ai = Qi.T @ U
+    U -= Qi @ Ai
+    Qn, R = np.linalg.qr(U)
+    Qi, Bi = Qn, R
+    T = ro.insert_a(Ai, b)
+    ro.insert_b(Bi, T, b, 1)
+    i = 1
+    out = None
+    while i < max_blocks:
+        i += 1
+        Q.append(Qi)
+        if i % reorth_period == 0:
+            if Ylock is not None and Ylock.shape[1] > 0:      # locked vectors take part in the periodic reorth
+                _orth_against(Ylock, Q[i - 1])
+                _orth_against(Ylock, Q[i - 2])
+            ro.part_reorth(Q)
+        ro.loc_reorth(Q[i - 1], Q[i - 2])
+        U = flt.apply(A, Q[i - 1])
+        U -= Q[i - 2] @ Bi.T
+        Ai = Q[i - 1].T @ U
+        U -= Q[i - 1] @ Ai
+        Qn, R = np.linalg.qr(U)
+        Qi, Bi = Qn, R
+        T = np.hstack([T, ro.insert_a(Ai, b)])
+        last = i >= max_blocks
+        if (i * b > k_rem and i % check_period == 0 and not run_to_cap) or last:
+            Dall, Vall = ro.dsbev(T)
+            want = min(kk, T.shape[1])
+            D, S = ro.sort_eig_abs(Dall, Vall, want)
+            D, S = D[::-1].copy(), S[:, ::-1].copy()
+            bounds = ro.residual_bounds(Bi, S, b)
+            ok = bool(np.all(bounds[:k_rem] <= tol)) and not run_to_cap
+            out = CycleResult(ok, i, D, S, bounds, Q)
+            if ok:
+                return out
+        ro.insert_b(Bi, T, b, i)
+    return out
+
+
+# --------------------------------------------------------------------------- driver
+@dataclass
+class RestartStats:
+    cycles: int = 0
+    locked: int = 0
+    block_steps: int = 0          # filtered block steps over all cycles
+    probe_steps: int = 0
+    operator_applications: int = 0
+    converged: bool = False
+    filter: ChebFilter | None = None
+    max_residual: float = 0.0
+
+
+def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol: float = 1e-7, filter_degree: int = 0,
+                  probe_steps: int = 0, restart: bool = True, max_cycles: int = 50, reorth_period: int = 2,
+                  check_period: int = 4, return_details: bool = False):
+    """Generalised RBL_restarted / RBL_gpu_restarted (restarted.jl:98-146,196-246).
+
+    Returns (D, V): the k eigenvalues of A of largest magnitude (descending |lambda|) and their vectors.
+    `max_blocks` is the number of Krylov blocks the buffer holds (locked vectors included)."""
+    n = A.shape[0]
+    st = RestartStats()
+    Q1 = np.linalg.qr(np.asarray(A @ np.asarray(Omega, dtype=DOUBLE), dtype=DOUBLE))[0]      # RBL.jl:137
+    flt = ChebFilter(degree=0)
+    if filter_degree != 0:
+        d = filter_degree if filter_degree > 0 else 8
+        kk = k + b
+        s = probe_steps if probe_steps > 0 else max(8, 2 * -(-kk // b))
+        s = min(s, max_blocks)
+        pr = lanczos_cycle(A, flt, k, min(kk, s * b), b, s, Q1.copy(), None, tol=tol, reorth_period=reorth_period,
+                           check_period=check_period, run_to_cap=True)
+        st.probe_steps = pr.iterations
+        glo, ghi = gershgorin(A)
+        flt = place_filter(pr.D, min(k, len(pr.D)), len(pr.D), d, glo, ghi)
+        st.operator_applications += pr.iterations
+    st.filter = flt
+    Y = np.zeros((n, 0))
+    Dlock = np.zeros(0)
+    start = Q1
+    final = None
+    while True:
+        st.cycles += 1
+        k_rem = k - Y.shape[1]
+        nlb = -(-Y.shape[1] // b)                       # locked vectors occupy whole buffer blocks
+        room = max_blocks - nlb
+        if room < 3:
+            break
+        kk = k_rem + b
+        res = lanczos_cycle(A, flt, k_rem, kk, b, room, start, Y, tol=tol, reorth_period=reorth_period,
+                            check_period=check_period)
+        st.block_steps += res.iterations
+        st.operator_applications += res.iterations * max(1, flt.degree)
+        if res.converged or not restart or st.cycles >= max_cycles:
+            final = res
+            st.converged = res.converged
+            break
+        # lock every wanted pair whose bound passed (restarted.jl:122-131), restart from the best b others (:133-135)
+        nb = res.iterations
+        Qm = np.hstack(res.Q[:nb])
+        lock = [j for j in range(min(k_rem, len(res.D))) if res.bounds[j] <= tol]
+        rest = [j for j in range(len(res.D)) if j not in lock][:b]
+        if lock:
+            Y = np.hstack([Y, Qm @ res.S[:, lock]])
+            Dlock = np.concatenate([Dlock, res.D[lock]])
+        start = Qm @ res.S[:, rest]
+        if start.shape[1] < b:
+            start = np.hstack([start, np.random.default_rng(st.cycles).standard_normal((n, b - start.shape[1]))])
+        _orth_against(Y, start)
+        start = np.linalg.qr(start)[0]
+        st.locked = Y.shape[1]
+        if Y.shape[1] >= k:
+            break
+    # assemble: locked + the leading pairs of the last cycle
+    if final is not None:
+        k_rem = k - Y.shape[1]
+        Qm = np.hstack(final.Q[:final.iterations])
+        Vf = Qm @ final.S[:, :k_rem]
+        V = np.hstack([Y, Vf])
+    else:
+        V = Y[:, :k]
+    # eigenvalues of A: Rayleigh quotients (identity for the plain operator up to roundoff), then order by |lambda|
+    W = np.asarray(A @ V, dtype=DOUBLE)
+    lam = np.einsum("ij,ij->j", V, W) / np.einsum("ij,ij->j", V, V)
+    order = np.argsort(-np.abs(lam), kind="stable")
+    lam, V, W = lam[order], V[:, order], W[:, order]
+    st.max_residual = float(np.max(np.linalg.norm(W - V * lam[None, :], axis=0)))
+    if return_details:
+        return lam, V, st
+    return lam, V

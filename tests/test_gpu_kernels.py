@@ -101,11 +101,11 @@ def test_reorth_block_cgs(gpu, n, b, m, fp32):
     _reorth_case(gpu, n, b, m, fp32, impl=0)
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3, 4])
+@pytest.mark.parametrize("impl", [1, 3, 4])
 @pytest.mark.parametrize("n,b,m", [(4000, 16, 5), (10007, 16, 70), (700, 16, 33), (70000, 16, 3), (5000, 13, 9), (64, 16, 1),
                                    (20000, 16, 130)])
 def test_reorth_simt_and_tensor_core_paths(gpu, impl, n, b, m):
-    """All implementations of K5 (SIMT fp32 FMA / 3xTF32 MMA / scaled 2-term FP16 MMA on an fp32 buffer (3) and on the
+    """All implementations of K5 (SIMT fp32 FMA / scaled 2-term FP16 MMA on an fp32 buffer (3) and on the
     pre-split buffer format the solver uses (4)) meet the same fp32-grade bars."""
     _reorth_case(gpu, n, b, m, True, impl=impl)
 

@@ -141,3 +141,50 @@ def test_config3_reduced_er_b32_mixed(gpu):
     assert st.converged
     assert np.max(np.abs(D - Do) / np.abs(Do)) < 1e-8
     assert np.max(rbl_oracle.ritz_residuals(A, D, V)) < 1e-6
+
+
+# ---- single-process multi-GPU: RBL_gpu(A,k,b; ngpus=N) from ONE caller (RBL_gpu.jl:205) ------------
+def _need_gpus(gpu, n):
+    if gpu.lib().rbl_device_count() < n:
+        pytest.skip(f"needs {n} CUDA devices")
+
+
+@pytest.mark.parametrize("case", ["lap3d-20 fp64", "lap3d-24 mixed", "er-4000 fp64", "lap3d-24 mixed filtered", "lap3d-24 fp64 restart"])
+def test_multi_gpu_group_handle_equals_single_gpu(gpu, case):
+    """Row-sharded solve over 2 GPUs of this process == single-GPU solve == analytic spectrum; V comes back as one
+    n x k host matrix like the single-GPU call (was tools/multi_gpu_check.py under torchrun)."""
+    _need_gpus(gpu, 2)
+    kw = dict(max_kryl_sz=4000)
+    if case.startswith("lap3d-20"):
+        L, sigma, k, b, prec = matrices.laplacian_3d(20), 12.0, 20, 16, "fp64"
+    elif case.startswith("lap3d-24"):
+        L, sigma, k, b, prec = matrices.laplacian_3d(24), 12.0, 30, 16, ("mixed" if "mixed" in case else "fp64")
+        if "filtered" in case:
+            kw["filter_degree"] = 8
+        if "restart" in case:
+            kw.update(max_kryl_sz=40 * 16, restart=True)
+    else:
+        L, sigma, k, b, prec = matrices.erdos_renyi_sym(4000, 16, seed=1), None, 8, 8, "fp64"
+    n = L.shape[0]
+    Om = np.random.default_rng(5).standard_normal((n, b))
+    D1, V1, st1 = gpu.RBL_gpu(L, k, b, Omega=Om, shift=sigma, precision=prec, return_stats=True, **kw)
+    for ng in (2, 4, 8):
+        if gpu.lib().rbl_device_count() < ng:
+            break
+        D2, V2, st2 = gpu.RBL_gpu(L, k, b, Omega=Om, shift=sigma, precision=prec, ngpus=ng, return_stats=True, **kw)
+        A = matrices.shifted(L, sigma) if sigma is not None else L
+        assert st2.converged
+        assert abs(st2.iterations - st1.iterations) <= 4
+        assert np.max(np.abs(D2 - D1) / np.abs(D1)) < 1e-8
+        assert V2.shape == (n, k)
+        assert np.max(rbl_oracle.ritz_residuals(A, D2, V2)) < 1e-6
+        assert np.min(np.linalg.svd(V1.T @ V2, compute_uv=False)) > 1 - 1e-6      # same invariant subspace
+
+
+def test_multi_gpu_group_handle_one_based_and_device_rng(gpu):
+    _need_gpus(gpu, 2)
+    L = matrices.laplacian_2d(60)
+    D1, V1 = gpu.RBL_gpu(L, 8, 4, shift=8.0, seed=3)
+    D2, V2 = gpu.RBL_gpu(L, 8, 4, shift=8.0, seed=3, ngpus=2, index_base=1)
+    # the counter-based generator draws element (row, col) independently of the partition: same start block
+    assert np.max(np.abs(D2 - D1) / np.abs(D1)) < 1e-10

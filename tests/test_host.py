@@ -24,11 +24,31 @@ def test_library_exports_every_declared_symbol(rbl):
 
 
 def test_struct_sizes_match_header(rbl):
+    """The ctypes mirrors (and therefore the Julia structs of julia/RBL_b200.jl, which list the same fields in the same
+    order) have exactly the compiled sizes."""
     import ctypes as C
-    assert C.sizeof(rbl.RblOptions) == 8 + 8 + 4 * 4 + 8 + 4 * 6 + 4 * 7 + 4  # incl. tail padding to 8
+    a, b = C.c_int64(), C.c_int64()
+    assert rbl.lib().rbl_struct_sizes(C.byref(a), C.byref(b)) == 0
+    assert C.sizeof(rbl.RblOptions) == a.value == 96
+    assert C.sizeof(rbl.RblStats) == b.value
     o = rbl.binding.default_options()
     assert (o.max_kryl_sz, o.tol, o.reorth_period, o.check_period) == (1200, 1e-7, 2, 4)  # RBL_gpu.jl:211,189,164,186
     assert o.precision == 0 and o.op == 0
+    assert (o.ngpus, o.filter_degree, o.restart, o.spill, o.mem_limit_mb, o.seed) == (1, 0, 0, 0, 0, 0)
+    # the Julia wrapper's struct field lists mirror the header's
+    jl = open(os.path.join(ROOT, "gpu-randomized-block-lanczos_b200", "julia", "RBL_b200.jl")).read()
+    hdr = open(os.path.join(ROOT, "include", "rbl_b200.h")).read()
+    for struct_name, jl_name in (("rbl_options", "RblOptions"), ("rbl_stats", "RblStats")):
+        body = hdr[hdr.index("typedef struct {", hdr.index("Options.") if struct_name == "rbl_options" else hdr.index("Per-solve statistics")):]
+        body = body[:body.index("} " + struct_name)]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        c_fields = re.findall(r"\b(?:int64_t|int32_t|double)\s+([a-z_0-9]+)\s*(?:\[\d+\])?;", body)
+        jbody = jl[jl.index("struct " + jl_name):]
+        jbody = jbody[:jbody.index("\nend")]
+        j_fields = re.findall(r"^\s+([a-z_0-9]+)::", jbody, flags=re.M)
+        assert c_fields == j_fields, (struct_name, c_fields, j_fields)
+        py_fields = [f for f, _ in (rbl.RblOptions if struct_name == "rbl_options" else rbl.RblStats)._fields_]
+        assert c_fields == py_fields
 
 
 def test_no_device_is_a_loud_error(rbl):
