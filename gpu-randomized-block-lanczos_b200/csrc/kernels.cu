@@ -329,7 +329,8 @@ void launch_reduce_partials(const double* partials, int nparts, int count, doubl
 // =================================================================================================
 template <int B>
 __global__ void __launch_bounds__(B* B) chol_kernel(const double* __restrict__ G, QrState* st, int pass,
-                                                     double nrows_global, int reset_ref, double defl_rel) {
+                                                     double nrows_global, int reset_ref, double defl_rel,
+                                                     const double* __restrict__ overlap) {
     __shared__ double A[B][B + 1];
     __shared__ double Rm[B][B + 1];
     __shared__ double Ro[B][B + 1];
@@ -413,7 +414,17 @@ __global__ void __launch_bounds__(B* B) chol_kernel(const double* __restrict__ G
     }
     __syncthreads();
     // deflated columns produce an exactly zero Q column
-    st->Rinv[i * B + j] = (defl[j] || defl[i]) ? 0.0 : Ri[i][j];
+    const double rinv_ij = (defl[j] || defl[i]) ? 0.0 : Ri[i][j];
+    st->Rinv[i * B + j] = rinv_ij;
+    if (overlap != nullptr) {
+        // coefficients of the fused local re-orthogonalisation: (Q_i' U) * Rinv, U the block the Gram was taken of
+        __syncthreads();
+        Ri[i][j] = rinv_ij;
+        __syncthreads();
+        double s = 0.0;
+        for (int k = 0; k <= j; ++k) s += overlap[i * B + k] * Ri[k][j];
+        st->Mloc[i * B + j] = s;
+    }
     // accumulated R = Rm * Ro  (pass 1: Rm); rows of deflated columns are zero
     double racc;
     if (pass == 1) {
@@ -437,10 +448,10 @@ __global__ void __launch_bounds__(B* B) chol_kernel(const double* __restrict__ G
 }
 
 void launch_chol(int B, const double* G, QrState* st, int pass, int64_t nrows_global, int reset_ref, double defl_rel,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const double* overlap) {
     dispatch_B(B, [&](auto bc) {
         constexpr int BB = decltype(bc)::value;
-        chol_kernel<BB><<<1, BB * BB, 0, stream>>>(G, st, pass, (double)nrows_global, reset_ref, defl_rel);
+        chol_kernel<BB><<<1, BB * BB, 0, stream>>>(G, st, pass, (double)nrows_global, reset_ref, defl_rel, overlap);
     });
 }
 
@@ -679,7 +690,7 @@ template <int B, typename S>
 __global__ void __launch_bounds__(256) reorth_update_kernel(int64_t n, int64_t m, const S* __restrict__ buf,
                                                             int64_t bstride, const S* __restrict__ Cmat,
                                                             double* __restrict__ w0, double* __restrict__ w1,
-                                                            S* __restrict__ store_w1) {
+                                                            S* __restrict__ store_w1, S* __restrict__ store_w0) {
     using C = UpdCfg<B, S>;
     constexpr int LPR = C::LPR, RPT = C::RPT, ROWS_W = C::ROWS_W, ROWS_CTA = C::ROWS_CTA, SK = C::SK, BLK = C::BLK,
                   JC = C::JC;
@@ -774,7 +785,9 @@ __global__ void __launch_bounds__(256) reorth_update_kernel(int64_t n, int64_t m
         for (int t = 0; t < 2 * B; ++t) {
             if ((t >> 3) == q) {
                 if (t < B) {
-                    w0[ro + t] = w0[ro + t] - (double)acc[u][t];
+                    const double nv = w0[ro + t] - (double)acc[u][t];
+                    w0[ro + t] = nv;
+                    if (store_w0 != nullptr) store_w0[ro + t] = (S)nv;
                 } else {
                     const double nv = w1[ro + (t - B)] - (double)acc[u][t];
                     w1[ro + (t - B)] = nv;
@@ -787,23 +800,23 @@ __global__ void __launch_bounds__(256) reorth_update_kernel(int64_t n, int64_t m
 
 template <int B, typename S>
 static void update_launch_t(const ReorthPlan& p, const void* buf, int64_t bstride, const void* Cmat, double* w0,
-                            double* w1, void* store_w1, cudaStream_t st) {
+                            double* w1, void* store_w1, void* store_w0, cudaStream_t st) {
     using C = UpdCfg<B, S>;
     const size_t smem = (size_t)C::JC * C::BLK * sizeof(S);
     static PerDeviceOnce once;
     if (once.first()) cudaFuncSetAttribute(reorth_update_kernel<B, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     unsigned grid = (unsigned)((p.n + C::ROWS_CTA - 1) / C::ROWS_CTA);
     reorth_update_kernel<B, S><<<grid, 256, smem, st>>>(p.n, p.m, (const S*)buf, bstride, (const S*)Cmat, w0, w1,
-                                                         (S*)store_w1);
+                                                         (S*)store_w1, (S*)store_w0);
 }
 
 void launch_reorth_update(const ReorthPlan& p, const void* buf, int64_t bstride, const void* Cmat, double* w0,
-                          double* w1, void* store_w1, cudaStream_t st) {
+                          double* w1, void* store_w1, cudaStream_t st, void* store_w0) {
     if (p.m <= 0) return;
     dispatch_B(p.B, [&](auto bc) {
         constexpr int BB = decltype(bc)::value;
-        if (p.fp32) update_launch_t<BB, float>(p, buf, bstride, Cmat, w0, w1, store_w1, st);
-        else update_launch_t<BB, double>(p, buf, bstride, Cmat, w0, w1, store_w1, st);
+        if (p.fp32) update_launch_t<BB, float>(p, buf, bstride, Cmat, w0, w1, store_w1, store_w0, st);
+        else update_launch_t<BB, double>(p, buf, bstride, Cmat, w0, w1, store_w1, store_w0, st);
     });
 }
 

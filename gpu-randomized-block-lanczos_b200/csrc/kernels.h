@@ -69,6 +69,29 @@ void launch_rowop(int B, const RowOpArgs& a, int grid, cudaStream_t st);
 // out[e] = sum_p partials[p][e], e < count   (fixed order: deterministic)
 void launch_reduce_partials(const double* partials, int nparts, int count, double* out, cudaStream_t st);
 
+// ---- second-generation fused row kernel (rowops.cu): B = 16, 32 -----------------------------------------------------
+// per row tile:  y <- y*Rinv (optional) ; y <- y - x1*M1 (optional) ; Y <- y ; store <- y ; G0 += y'y ; G1 += z'y
+struct FusedArgs {
+    int64_t n = 0;
+    double* y = nullptr;
+    const double* rinv = nullptr;     // upper triangular B x B (row-major), applied first
+    const double* x1 = nullptr;
+    const double* m1 = nullptr;
+    int m1_transposed = 0;
+    const double* z = nullptr;        // left operand of the second Gram
+    int gram_yy = 0;
+    const int* gram_flag = nullptr;   // device flag: y'y is accumulated only when *gram_flag != 0 (optional 3rd QR pass)
+    const int* skip_flag = nullptr;   // device flag: the kernel is a no-op when *skip_flag == 0
+    int write_y = 1;
+    void* store = nullptr;
+    int store_fp32 = 0;
+    float store_split_scale = 0.f;
+    double* partials = nullptr;       // [grid][2][B*B]: slot 0 = y'y, slot 1 = z'y
+};
+bool fused_rowop_supported(int B);
+int fused_rowop_grid(int B, int64_t n);
+void launch_fused_rowop(int B, const FusedArgs& a, int grid, cudaStream_t st);
+
 // ---- block-QR small step (single CTA) -----------------------------------------------------------
 struct QrState {             // lives in device memory
     double R[32 * 32];       // accumulated R (row-major B x B)
@@ -78,16 +101,19 @@ struct QrState {             // lives in device memory
     int need_more;           // 1: a further re-orthogonalisation pass is required
     int ndeflated;
     int bad;                 // non-finite input seen
+    double Mloc[32 * 32];    // pass 2 with an overlap matrix P = Q_i' U: P * Rinv (coefficients of the fused local reorth)
 };
 // pass 1: shifted Cholesky of G (+ exact-zero column deflation); pass >= 2: plain Cholesky with
 // deflation of columns whose accumulated R_jj <= defl_rel * ref.  `nrows_global` enters the shift.
+// `overlap` (optional, pass 2): B x B matrix P; st->Mloc = P * Rinv of this pass.
 void launch_chol(int B, const double* G, QrState* st, int pass, int64_t nrows_global, int reset_ref, double defl_rel,
-                 cudaStream_t stream);
+                 cudaStream_t stream, const double* overlap = nullptr);
 
 // ---- K5 partial (full) re-orthogonalisation against the Krylov buffer ----------------------------
 // gram:   C[(j*B+c), t] = sum_r buf_j[r,c] * W[r,t],  W = [w0 | w1] (fp64 active blocks), t < 2B
 // update: w0 -= sum_j buf_j * C_j[:, 0:B],  w1 -= sum_j buf_j * C_j[:, B:2B]; optionally refresh the
-//         buffer copy of w1 (copyto!(Qgpu[i-1],Qg1), RBL_gpu.jl:76).
+//         buffer copy of w1 (copyto!(Qgpu[i-1],Qg1), RBL_gpu.jl:76) and, when the newest block is already stored
+//         (fused local reorth, solver.cu), that of w0.
 // C and the partials are float when the buffer is float, else double.
 struct ReorthPlan {
     int B = 0, fp32 = 0;
@@ -101,7 +127,7 @@ void launch_reorth_gram(const ReorthPlan& p, const void* buf, int64_t block_stri
                         const double* w1, void* partials, void* C, cudaStream_t st);
 void launch_reorth_gram_reduce(const ReorthPlan& p, const void* partials, void* C, cudaStream_t st);
 void launch_reorth_update(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, const void* C, double* w0,
-                          double* w1, void* store_w1, cudaStream_t st);
+                          double* w1, void* store_w1, cudaStream_t st, void* store_w0 = nullptr);
 
 // scaled two-term FP16 split on mma.sync m16n8k16 (reorth_tc16.cu): same interface, half the tensor-pipe time.
 // `n_global` fixes the power-of-two operand scale (orthonormal columns of global length n_global).
@@ -115,7 +141,7 @@ void launch_reorth_coeff_h(const ReorthPlan& p, const void* C, float* scratch, i
                            cudaStream_t st);
 void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t block_stride_elems,
                             double* w0, double* w1, void* store_w1, float* scratch, int64_t m_cap, int presplit,
-                            cudaStream_t st);
+                            cudaStream_t st, void* store_w0 = nullptr);
 // `presplit`: buf (and store_w1) hold split16 rows (split16.h) instead of fp32 values
 
 // all-fp64 mode: FP64 tensor-core MMA (mma.sync.m8n8k4.f64) + cp.async rings, B = 16 (reorth_f64.cu)
@@ -123,7 +149,7 @@ bool reorth_d_supported(int B, int fp32);
 void launch_reorth_gram_d(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, const double* w0,
                           const double* w1, void* partials, void* C, cudaStream_t st);
 void launch_reorth_update_d(const ReorthPlan& p, const void* buf, int64_t block_stride_elems, const void* C, double* w0,
-                            double* w1, void* store_w1, cudaStream_t st);
+                            double* w1, void* store_w1, cudaStream_t st, void* store_w0 = nullptr);
 
 // ---- K6 Ritz vectors -----------------------------------------------------------------------------
 // V[:, t] = sum_j buf_j * S[(j*B .. j*B+B), t];  S device, row-major (m*B) x kpad in the buffer's type;

@@ -197,7 +197,7 @@ template <int B>
 __global__ void __launch_bounds__(UpdD<B>::NW * 32, 1)
     reorth_update_d_kernel(int64_t n, int64_t m, const double* __restrict__ buf, int64_t bstride,
                            const double* __restrict__ Cmat, double* __restrict__ w0, double* __restrict__ w1,
-                           double* __restrict__ store_w1) {
+                           double* __restrict__ store_w1, double* __restrict__ store_w0) {
     using C = UpdD<B>;
     constexpr int NW = C::NW, RWP = C::RWP, MT = C::MT, NT = C::NT, PA = C::PA, PC = C::PC, JC = C::JC, NST = C::NST,
                   STAGE = C::STAGE, CBUF = C::CBUF, NCP = C::NCP, NTHR = NW * 32;
@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(UpdD<B>::NW * 32, 1)
                 v.x -= acc[a][x][0];
                 v.y -= acc[a][x][1];
                 *p = v;
+                if (store_w0 != nullptr) *reinterpret_cast<double2*>(store_w0 + (size_t)row * B + tgt) = v;
             } else {
                 double2* p = reinterpret_cast<double2*>(w1 + (size_t)row * B + (tgt - B));
                 double2 v = *p;
@@ -334,14 +335,14 @@ void launch_reorth_gram_d(const ReorthPlan& p, const void* buf, int64_t bstride,
 }
 
 void launch_reorth_update_d(const ReorthPlan& p, const void* buf, int64_t bstride, const void* Cmat, double* w0,
-                            double* w1, void* store_w1, cudaStream_t st) {
+                            double* w1, void* store_w1, cudaStream_t st, void* store_w0) {
     constexpr int B = 16;
     using U = UpdD<B>;
     static PerDeviceOnce once;
     if (once.first()) cudaFuncSetAttribute(reorth_update_d_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::smem_bytes);
     const unsigned grid = (unsigned)((p.n + U::ROWS_CTA - 1) / U::ROWS_CTA);
     reorth_update_d_kernel<B><<<grid, U::NW * 32, U::smem_bytes, st>>>(p.n, p.m, (const double*)buf, bstride,
-                                                                       (const double*)Cmat, w0, w1, (double*)store_w1);
+                                                                       (const double*)Cmat, w0, w1, (double*)store_w1, (double*)store_w0);
 }
 
 }  // namespace rbl

@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(UpdH<B, PS>::NW * 32, 1)
     reorth_update_h_kernel(int64_t n, int64_t m, const float* __restrict__ buf, int64_t bstride,
                            const unsigned* __restrict__ Ch, const unsigned* __restrict__ Cl, float scale_a,
                            const float* __restrict__ scale_c_ptr, double* __restrict__ w0, double* __restrict__ w1,
-                           float* __restrict__ store_w1) {
+                           float* __restrict__ store_w1, float* __restrict__ store_w0) {
     using C = UpdH<B, PS>;
     constexpr int NW = C::NW, MT = C::MT, NT = C::NT, NH = C::NH, KS = C::KS, PA = C::PA, PC = C::PC, JC = C::JC,
                   NST = C::NST, STAGE = C::STAGE, CBUF = C::CBUF, NCP = C::NCP, NTHR = NW * 32;
@@ -588,6 +588,17 @@ __global__ void __launch_bounds__(UpdH<B, PS>::NW * 32, 1)
                     v.x -= (double)d0;
                     v.y -= (double)d1;
                     *p = v;
+                    if (store_w0 != nullptr) {
+                        if constexpr (PS) {
+                            unsigned hi, lo;
+                            split_h2((float)v.x, (float)v.y, scale_a, hi, lo);
+                            unsigned* srow = reinterpret_cast<unsigned*>(store_w0) + (size_t)row * B;
+                            srow[tgt >> 1] = hi;
+                            srow[B / 2 + (tgt >> 1)] = lo;
+                        } else {
+                            *reinterpret_cast<float2*>(store_w0 + (size_t)row * B + tgt) = make_float2((float)v.x, (float)v.y);
+                        }
+                    }
                 } else {
                     double2* p = reinterpret_cast<double2*>(w1 + (size_t)row * B + (tgt - B));
                     double2 v = *p;
@@ -710,24 +721,25 @@ void launch_reorth_coeff_h(const ReorthPlan& p, const void* Cmat, float* scratch
 
 template <int B, bool PS>
 static void update_h_launch(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, double* w0,
-                            double* w1, void* store_w1, float* scratch, int64_t m_cap, cudaStream_t st) {
+                            double* w1, void* store_w1, void* store_w0, float* scratch, int64_t m_cap, cudaStream_t st) {
     using U = UpdH<B, PS>;
     HScratch s = h_layout(scratch, B, p.n, m_cap);
     static PerDeviceOnce once;
     if (once.first()) cudaFuncSetAttribute(reorth_update_h_kernel<B, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::smem_bytes);
     const unsigned grid = (unsigned)((p.n + U::ROWS_CTA - 1) / U::ROWS_CTA);
     reorth_update_h_kernel<B, PS><<<grid, U::NW * 32, U::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.ch, s.cl,
-                                                                 pick_scale(n_global), s.scale_c, w0, w1, (float*)store_w1);
+                                                                 pick_scale(n_global), s.scale_c, w0, w1, (float*)store_w1, (float*)store_w0);
 }
 
 void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, double* w0,
-                            double* w1, void* store_w1, float* scratch, int64_t m_cap, int presplit, cudaStream_t st) {
+                            double* w1, void* store_w1, float* scratch, int64_t m_cap, int presplit, cudaStream_t st,
+                            void* store_w0) {
     if (p.B == 16) {
-        if (presplit) update_h_launch<16, true>(p, n_global, buf, bstride, w0, w1, store_w1, scratch, m_cap, st);
-        else update_h_launch<16, false>(p, n_global, buf, bstride, w0, w1, store_w1, scratch, m_cap, st);
+        if (presplit) update_h_launch<16, true>(p, n_global, buf, bstride, w0, w1, store_w1, store_w0, scratch, m_cap, st);
+        else update_h_launch<16, false>(p, n_global, buf, bstride, w0, w1, store_w1, store_w0, scratch, m_cap, st);
     } else {
-        if (presplit) update_h_launch<32, true>(p, n_global, buf, bstride, w0, w1, store_w1, scratch, m_cap, st);
-        else update_h_launch<32, false>(p, n_global, buf, bstride, w0, w1, store_w1, scratch, m_cap, st);
+        if (presplit) update_h_launch<32, true>(p, n_global, buf, bstride, w0, w1, store_w1, store_w0, scratch, m_cap, st);
+        else update_h_launch<32, false>(p, n_global, buf, bstride, w0, w1, store_w1, store_w0, scratch, m_cap, st);
     }
 }
 

@@ -286,7 +286,7 @@ MemPlan plan_memory(rbl_handle* h, int64_t k, int b, int64_t m_req) {
     if (opt.mem_limit_mb > 0) budget = std::min(budget, (double)opt.mem_limit_mb * 1048576.0);
     const bool extra = opt.restart || opt.filter_degree != 0;
     const int nX = 3 + (opt.filter_degree != 0 ? 1 : 0);
-    const int rgrid = rowop_grid(B, nloc);
+    const int rgrid = std::max(rowop_grid(B, nloc), fused_rowop_supported(B) ? 2 * fused_rowop_grid(B, nloc) : 0);
     const size_t vsz = opt.v_fp32 ? 4 : 8;
     size_t fixed = (size_t)nX * next * B * 8                    // active blocks
                    + (size_t)nloc * 4 * B * 4                    // packed target words of the tensor-core reorth
@@ -404,10 +404,15 @@ struct Run {
         if (tail_event) cudaEventDestroy(tail_event);
     }
 
+    // small device matrices (B x B each): [G | P] are adjacent so that one reduction / all-reduce covers both
     double* G() { return w.small.p; }
-    double* Ai() { return w.small.p + (size_t)B * B; }
-    double* Bp() { return w.small.p + 2 * (size_t)B * B; }
-    double* Gloc() { return w.small.p + 3 * (size_t)B * B; }
+    double* Pov() { return w.small.p + (size_t)B * B; }       // second Gram of a fused pass (A_i, or Q_i'U)
+    double* Ai() { return w.small.p + 2 * (size_t)B * B; }
+    double* Bp() { return w.small.p + 3 * (size_t)B * B; }
+    double* Gloc() { return w.small.p + 4 * (size_t)B * B; }
+    static constexpr int kSmallMats = 6;
+    bool fused = false;
+    int fgrid = 1;
     void* slot(int64_t j) { return w.buf.p + (size_t)j * bstride * ssz; }
 
     void nccl(bool ok, const std::string& err) {
@@ -428,6 +433,122 @@ struct Run {
         launch_rowop(B, a, rgrid, st);
         ++launches;
     }
+    // fused row kernel (rowops.cu) and the reduction of its [grid][2][B*B] partials into G() / Pov()
+    void fpass(const FusedArgs& f) {
+        launch_fused_rowop(B, f, fgrid, st);
+        ++launches;
+    }
+    // which = 1: y'y -> G(); 2: z'y -> Pov(); 3: both
+    void finish_fused(int which) {
+        launch_reduce_partials(w.part.p, fgrid, 2 * B * B, G(), st);
+        ++launches;
+        if (which == 3) allreduce(G(), (size_t)2 * B * B);
+        else if (which == 1) allreduce(G(), (size_t)B * B);
+        else allreduce(Pov(), (size_t)B * B);
+    }
+    // ---- the four block passes of a step.  cur = Q_i, prev = Q_{i-1}, U = op(A) Q_i on entry ----
+    // B: U -= Q_{i-1} B_{i-1}' ; A_i = Q_i' U                                      RBL_gpu.jl:177-178
+    void pass_B(bool have_prev) {
+        if (fused) {
+            FusedArgs f;
+            f.n = nloc; f.y = U; f.z = cur; f.partials = w.part.p; f.write_y = have_prev ? 1 : 0;
+            if (have_prev) { f.x1 = prev; f.m1 = Bp(); f.m1_transposed = 1; }
+            fpass(f);
+            finish_fused(2);
+            RBL_CUDA(cudaMemcpyAsync(Ai(), Pov(), (size_t)B * B * 8, cudaMemcpyDeviceToDevice, st));
+        } else {
+            RowOpArgs a;
+            a.n = nloc; a.y = U; a.gram_z = cur; a.do_gram = 1; a.partials = w.part.p;
+            if (have_prev) { a.x1 = prev; a.m1 = Bp(); a.m1_transposed = 1; a.write_y = 1; }
+            rowop(a);
+            finish_gram(Ai());
+        }
+    }
+    // C: U -= Q_i A_i ; G = U'U                                                     :179 (+ Gram for the QR)
+    void pass_C() {
+        if (fused) {
+            FusedArgs f;
+            f.n = nloc; f.y = U; f.x1 = cur; f.m1 = Ai(); f.gram_yy = 1; f.partials = w.part.p;
+            fpass(f);
+            finish_fused(1);
+        } else {
+            RowOpArgs a;
+            a.n = nloc; a.y = U; a.x1 = cur; a.m1 = Ai(); a.write_y = 1; a.do_gram = 1; a.partials = w.part.p;
+            rowop(a);
+            finish_gram(G());
+        }
+    }
+    // D: U <- U R1^-1 ; G = U'U ; P = Q_i' U                                        CholQR pass 1 (:180-182)
+    void pass_D() {
+        if (fused) {
+            FusedArgs f;
+            f.n = nloc; f.y = U; f.rinv = w.qr.p->Rinv; f.gram_yy = 1; f.z = cur; f.partials = w.part.p;
+            fpass(f);
+            finish_fused(3);
+        } else {
+            RowOpArgs a;
+            a.n = nloc; a.y = U; a.rinv = w.qr.p->Rinv; a.write_y = 1; a.do_gram = 1; a.partials = w.part.p;
+            rowop(a);
+            finish_gram(G());
+            RowOpArgs a2;
+            a2.n = nloc; a2.y = U; a2.gram_z = cur; a2.do_gram = 1; a2.partials = w.part.p;
+            rowop(a2);
+            finish_gram(Pov());
+        }
+    }
+    // E: Q_{i+1} = U R2^-1 - Q_i (P R2^-1): CholQR pass 2 fused with the local re-orthogonalisation of the NEXT step
+    // (loc_reorth_gpu! :83-93,:167) and the copy into the Krylov slab (:168-172); Gram only if a third pass is due
+    void pass_E(void* store_slot) {
+        if (fused) {
+            FusedArgs f;
+            f.n = nloc; f.y = U; f.rinv = w.qr.p->Rinv; f.x1 = cur; f.m1 = w.qr.p->Mloc;
+            f.gram_yy = 1; f.gram_flag = &w.qr.p->need_more; f.partials = w.part.p;
+            f.store = store_slot; f.store_fp32 = fp32; f.store_split_scale = split_scale;
+            fpass(f);
+            finish_fused(1);
+        } else {
+            RowOpArgs a;
+            a.n = nloc; a.y = U; a.rinv = w.qr.p->Rinv; a.write_y = 1;
+            rowop(a);
+            RowOpArgs a2;
+            a2.n = nloc; a2.y = U; a2.x1 = cur; a2.m1 = w.qr.p->Mloc; a2.write_y = 1; a2.do_gram = 1; a2.partials = w.part.p;
+            a2.store = store_slot; a2.store_fp32 = fp32; a2.store_split_scale = split_scale;
+            rowop(a2);
+            finish_gram(G());
+        }
+    }
+    // optional CholQR pass 3 (device flag need_more; no-ops otherwise).  Right-multiplication keeps Q_i' Q_{i+1} = 0.
+    void pass_3(void* store_slot) {
+        launch_chol(B, G(), w.qr.p, 3, h->n, 0, 1e-12, st);
+        ++launches;
+        if (fused) {
+            FusedArgs f;
+            f.n = nloc; f.y = U; f.rinv = w.qr.p->Rinv; f.skip_flag = &w.qr.p->need_more;
+            f.store = store_slot; f.store_fp32 = fp32; f.store_split_scale = split_scale;
+            fpass(f);
+        } else {
+            RowOpArgs a3;
+            a3.n = nloc; a3.y = U; a3.rinv = w.qr.p->Rinv; a3.write_y = 1; a3.skip_flag = &w.qr.p->need_more;
+            a3.store = store_slot; a3.store_fp32 = fp32; a3.store_split_scale = split_scale;
+            rowop(a3);
+        }
+    }
+    // one block step after the operator was applied: U = op(A) Q_i  ->  Q_{i+1} (in U), A_i, B_i
+    void step_after_op(bool have_prev, void* store_slot, int reset_ref) {
+        tm.mark(PH_3TERM);
+        pass_B(have_prev);
+        pass_C();
+        tm.mark(PH_QR);
+        launch_chol(B, G(), w.qr.p, 1, h->n, reset_ref, 1e-12, st);
+        ++launches;
+        pass_D();
+        launch_chol(B, G(), w.qr.p, 2, h->n, 0, 1e-12, st, Pov());
+        ++launches;
+        tm.mark(PH_LOC);
+        pass_E(store_slot);
+        pass_3(store_slot);
+    }
+
     void halo(double* Xblk) {
         if (!h->comm.active()) return;
         std::string err;
@@ -528,22 +649,22 @@ struct Run {
         ++n_rgram;
         bytes_rgram += (double)ssz * (double)nloc * (double)m * B + 8.0 * (double)nloc * 2 * B;
     }
-    void reorth_update(int64_t m, double* w0, double* w1, void* store_w1) {
+    void reorth_update(int64_t m, double* w0, double* w1, void* store_w1, void* store_w0 = nullptr) {
         ReorthPlan p = reorth_plan(B, fp32, nloc, m);
         if (use_d) {
-            launch_reorth_update_d(p, w.buf.p, bstride, w.Cmat.p, w0, w1, store_w1, st);
+            launch_reorth_update_d(p, w.buf.p, bstride, w.Cmat.p, w0, w1, store_w1, st, store_w0);
             ++launches;
         } else if (use_h) {
             launch_reorth_coeff_h(p, w.Cmat.p, w.tc_scratch.p, m_cap, multi ? 1 : 0, st);
-            launch_reorth_update_h(p, h->n, w.buf.p, bstride, w0, w1, store_w1, w.tc_scratch.p, m_cap, split_scale != 0.f, st);
+            launch_reorth_update_h(p, h->n, w.buf.p, bstride, w0, w1, store_w1, w.tc_scratch.p, m_cap, split_scale != 0.f, st, store_w0);
             launches += 2;
         } else {
-            launch_reorth_update(p, w.buf.p, bstride, w.Cmat.p, w0, w1, store_w1, st);
+            launch_reorth_update(p, w.buf.p, bstride, w.Cmat.p, w0, w1, store_w1, st, store_w0);
             ++launches;
         }
         ++n_rupd;
         bytes_rupd += (double)ssz * (double)nloc * (double)m * B + 2 * 8.0 * (double)nloc * 2 * B +
-                      (store_w1 ? (double)ssz * (double)nloc * B : 0.0);
+                      ((store_w1 ? 1.0 : 0.0) + (store_w0 ? 1.0 : 0.0)) * (double)ssz * (double)nloc * B;
     }
 
     // decision shared by all ranks: 0 continue, 1 accept, 2 abort (the root's host check failed)
@@ -734,23 +855,14 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
     };
 
     // ---- first step (i = 1)                                                     RBL_gpu.jl:149-161 ----
+    // Invariant of the loop below: `cur` = Q_i is already locally re-orthogonalised against Q_{i-1} and stored in
+    // slab slot nlb+i-1 (both happen in pass E of the step that produced it).
     tm.mark(PH_LOC);
     launch_store_block(B, nloc, cur, slot(nlb), fp32, split_scale, st);
     ++launches;
     tm.mark(PH_SPMM);
     apply_op(cur, U);
-    tm.mark(PH_3TERM);
-    {
-        RowOpArgs a;
-        a.n = nloc; a.y = U; a.gram_z = cur; a.do_gram = 1; a.partials = w.part.p;
-        rowop(a);
-        finish_gram(Ai());
-        RowOpArgs a2;
-        a2.n = nloc; a2.y = U; a2.x1 = cur; a2.m1 = Ai(); a2.write_y = 1; a2.do_gram = 1; a2.partials = w.part.p;
-        rowop(a2);
-    }
-    tm.mark(PH_QR);
-    block_qr(U, 1);
+    step_after_op(false, (nlb + 1 < m_cap) ? slot(nlb + 1) : nullptr, 1);
     record_step(1);
     tm.mark(PH_NONE);
     { double* t = prev; prev = cur; cur = U; U = t; }
@@ -806,39 +918,16 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         const int64_t m = nlb + i - 2;  // stored blocks the two newest are re-orthogonalised against
         if (i % reorth_period == 0 && m > 0) {
             // hybrid_part_reorth! (+ restart_reorth_gpu! for the locked blocks): project Q_i and Q_{i-1} against
-            // everything stored before them, all at once (block CGS)
+            // everything stored before them, all at once (block CGS); both are already in the slab, so both stored
+            // copies are refreshed (copyto!(Qgpu[i-1],Qg1), RBL_gpu.jl:76)
             tm.mark(PH_RGRAM);
             reorth_gram(m, cur, prev);
             tm.mark(PH_RUPD);
-            reorth_update(m, cur, prev, slot(nlb + i - 2));
-        }
-        // loc_reorth_gpu! (effective): Q_i -= Q_{i-1} (Q_{i-1}' Q_i); then the block joins the buffer (:167-172)
-        tm.mark(PH_LOC);
-        {
-            RowOpArgs a;
-            a.n = nloc; a.y = cur; a.gram_z = prev; a.do_gram = 1; a.partials = w.part.p;
-            rowop(a);
-            finish_gram(Gloc());
-            RowOpArgs a2;
-            a2.n = nloc; a2.y = cur; a2.x1 = prev; a2.m1 = Gloc(); a2.write_y = 1;
-            a2.store = slot(nlb + i - 1); a2.store_fp32 = fp32; a2.store_split_scale = split_scale;
-            rowop(a2);
+            reorth_update(m, cur, prev, slot(nlb + i - 2), slot(nlb + i - 1));
         }
         tm.mark(PH_SPMM);
         apply_op(cur, U);                                                      // :176
-        tm.mark(PH_3TERM);
-        {
-            RowOpArgs a;                                                       // :177-178
-            a.n = nloc; a.y = U; a.x1 = prev; a.m1 = Bp(); a.m1_transposed = 1; a.write_y = 1;
-            a.gram_z = cur; a.do_gram = 1; a.partials = w.part.p;
-            rowop(a);
-            finish_gram(Ai());
-            RowOpArgs a2;                                                      // :179 (+ Gram for the QR)
-            a2.n = nloc; a2.y = U; a2.x1 = cur; a2.m1 = Ai(); a2.write_y = 1; a2.do_gram = 1; a2.partials = w.part.p;
-            rowop(a2);
-        }
-        tm.mark(PH_QR);
-        block_qr(U, 0);                                                        // :180-184
+        step_after_op(true, (nlb + i < m_cap) ? slot(nlb + i) : nullptr, 0);   // :177-184 and :167-172 of the next step
         record_step(i);
         tm.mark(PH_NONE);
         { double* t = prev; prev = cur; cur = U; U = t; }
@@ -1075,11 +1164,13 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
     c.m_cap = m_cap;
     stats.buffer_blocks = m_cap;
     c.rgrid = rowop_grid(B, c.nloc);
+    c.fused = fused_rowop_supported(B);
+    c.fgrid = c.fused ? fused_rowop_grid(B, c.nloc) : 1;
     const int nX = 3 + (filtering ? 1 : 0);
     for (int i = 0; i < nX; ++i) w.X[i].ensure((size_t)c.next * B);
     w.buf.ensure((size_t)m_cap * c.bstride * c.ssz);
-    w.part.ensure((size_t)c.rgrid * B * B);
-    w.small.ensure(4 * (size_t)B * B);
+    w.part.ensure(std::max((size_t)c.rgrid, (size_t)2 * c.fgrid) * B * B);
+    w.small.ensure(Run::kSmallMats * (size_t)B * B);
     w.qr.ensure(1);
     w.Cmat.ensure((size_t)m_cap * B * 2 * B * c.ssz);
     w.rpart.ensure(std::max<size_t>(1, reorth_max_partial_elems(B, c.fp32, c.nloc, m_cap)) * c.ssz);
@@ -1097,7 +1188,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
     if (extra) w.Vacc.ensure((size_t)c.nloc * k);
     const double t_alloc_done = now_s();
     RBL_CUDA(cudaMemsetAsync(w.qr.p, 0, sizeof(QrState), c.st));
-    RBL_CUDA(cudaMemsetAsync(w.small.p, 0, 4 * (size_t)B * B * 8, c.st));
+    RBL_CUDA(cudaMemsetAsync(w.small.p, 0, Run::kSmallMats * (size_t)B * B * 8, c.st));
     for (int i = 0; i < nX; ++i) RBL_CUDA(cudaMemsetAsync(w.X[i].p, 0, (size_t)c.next * B * 8, c.st));
     h->last = KrylovInfo{};
 

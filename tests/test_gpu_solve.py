@@ -178,7 +178,11 @@ def test_multi_gpu_group_handle_equals_single_gpu(gpu, case):
         assert np.max(np.abs(D2 - D1) / np.abs(D1)) < 1e-8
         assert V2.shape == (n, k)
         assert np.max(rbl_oracle.ritz_residuals(A, D2, V2)) < 1e-6
-        assert np.min(np.linalg.svd(V1.T @ V2, compute_uv=False)) > 1 - 1e-6      # same invariant subspace
+        # same invariant subspace - for the pairs above the last eigenvalue cluster (the k-th eigenvalue of a Laplacian
+        # usually cuts a degenerate cluster, whose basis inside the returned set is not unique)
+        sep = np.abs(D1 - D1[-1]) > 1e-6 * np.abs(D1[0])
+        if sep.any():
+            assert np.min(np.linalg.svd(V1[:, sep].T @ V2, compute_uv=False)) > 1 - 1e-6
 
 
 def test_multi_gpu_group_handle_one_based_and_device_rng(gpu):
