@@ -827,7 +827,7 @@ void launch_reorth_update(const ReorthPlan& p, const void* buf, int64_t bstride,
 template <int B, typename S, typename VT, bool SPLIT>
 __global__ void __launch_bounds__(256) ritz_kernel(int64_t n, int64_t m, int k, int kpad, const S* __restrict__ buf,
                                                    int64_t bstride, const S* __restrict__ Smat, VT* __restrict__ V,
-                                                   int64_t ldv, int RL, int JC, float split_inv_scale) {
+                                                   int64_t ldv, int RL, int JC, float split_inv_scale, int accumulate) {
     constexpr int RPT = 2;
     constexpr int TT = 16;
     constexpr int VW = 16 / sizeof(S);
@@ -918,14 +918,17 @@ __global__ void __launch_bounds__(256) ritz_kernel(int64_t n, int64_t m, int k, 
 #pragma unroll
         for (int t = 0; t < TT; ++t) {
             const int col = tg * TT + t;
-            if (col < k) V[(size_t)col * ldv + rows[u]] = (VT)dacc[u][t];
+            if (col < k) {
+                VT* dst = V + (size_t)col * ldv + rows[u];
+                *dst = accumulate ? (VT)((double)*dst + dacc[u][t]) : (VT)dacc[u][t];
+            }
         }
     }
 }
 
 template <int B, typename S, typename VT, bool SPLIT = false>
 static void ritz_launch_t(int64_t n, int64_t m, int k, int kpad, const void* buf, int64_t bstride, const void* Smat,
-                          void* V, int64_t ldv, cudaStream_t st, float split_inv_scale = 0.f) {
+                          void* V, int64_t ldv, cudaStream_t st, int accumulate, float split_inv_scale = 0.f) {
     const int KG = kpad / 16;
     int RL = 256 / KG;
     if (RL > 32) RL = (RL / 32) * 32;   // whole warps share a target group (broadcast smem reads)
@@ -937,26 +940,26 @@ static void ritz_launch_t(int64_t n, int64_t m, int k, int kpad, const void* buf
     cudaFuncSetAttribute(ritz_kernel<B, S, VT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     unsigned grid = (unsigned)((n + (int64_t)RL * 2 - 1) / ((int64_t)RL * 2));
     ritz_kernel<B, S, VT, SPLIT><<<grid, 256, smem, st>>>(n, m, k, kpad, (const S*)buf, bstride, (const S*)Smat, (VT*)V, ldv, RL,
-                                                         JC, split_inv_scale);
+                                                         JC, split_inv_scale, accumulate);
 }
 
 void launch_ritz(int B, int fp32, int64_t n, int64_t m, int k, int kpad, const void* buf, int64_t bstride,
-                 const void* Smat, void* V, int64_t ldv, int v_fp32, float split_scale, cudaStream_t st) {
+                 const void* Smat, void* V, int64_t ldv, int v_fp32, float split_scale, cudaStream_t st, int accumulate) {
     if (kpad / 16 > 256) { std::fprintf(stderr, "rbl: k too large for ritz kernel\n"); std::abort(); }
     dispatch_B(B, [&](auto bc) {
         constexpr int BB = decltype(bc)::value;
         if (fp32 && split_scale != 0.f) {
             if constexpr (BB >= 16) {
                 const float inv = 1.0f / split_scale;
-                if (v_fp32) ritz_launch_t<BB, float, float, true>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st, inv);
-                else ritz_launch_t<BB, float, double, true>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st, inv);
+                if (v_fp32) ritz_launch_t<BB, float, float, true>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st, accumulate, inv);
+                else ritz_launch_t<BB, float, double, true>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st, accumulate, inv);
             }
         } else if (fp32) {
-            if (v_fp32) ritz_launch_t<BB, float, float>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st);
-            else ritz_launch_t<BB, float, double>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st);
+            if (v_fp32) ritz_launch_t<BB, float, float>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st, accumulate);
+            else ritz_launch_t<BB, float, double>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st, accumulate);
         } else {
-            if (v_fp32) ritz_launch_t<BB, double, float>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st);
-            else ritz_launch_t<BB, double, double>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st);
+            if (v_fp32) ritz_launch_t<BB, double, float>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st, accumulate);
+            else ritz_launch_t<BB, double, double>(n, m, k, kpad, buf, bstride, Smat, V, ldv, st, accumulate);
         }
     });
 }

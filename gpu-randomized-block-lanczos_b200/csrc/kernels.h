@@ -141,7 +141,9 @@ void launch_reorth_coeff_h(const ReorthPlan& p, const void* C, float* scratch, i
                            cudaStream_t st);
 void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t block_stride_elems,
                             double* w0, double* w1, void* store_w1, float* scratch, int64_t m_cap, int presplit,
-                            cudaStream_t st, void* store_w0 = nullptr);
+                            cudaStream_t st, void* store_w0 = nullptr, int64_t coef_block0 = 0);
+// coef_block0: `buf` holds stored blocks coef_block0 .. coef_block0+p.m of the coefficient set built by launch_reorth_coeff_h
+// (host-spilled blocks are streamed through a staging buffer chunk by chunk)
 // `presplit`: buf (and store_w1) hold split16 rows (split16.h) instead of fp32 values
 
 // all-fp64 mode: FP64 tensor-core MMA (mma.sync.m8n8k4.f64) + cp.async rings, B = 16 (reorth_f64.cu)
@@ -155,13 +157,13 @@ void launch_reorth_update_d(const ReorthPlan& p, const void* buf, int64_t block_
 // V[:, t] = sum_j buf_j * S[(j*B .. j*B+B), t];  S device, row-major (m*B) x kpad in the buffer's type;
 // V column-major n x k (ldv), float or double as the buffer.                  RBL_gpu.jl:106-132
 void launch_ritz(int B, int fp32, int64_t n, int64_t m, int k, int kpad, const void* buf, int64_t block_stride_elems,
-                 const void* S, void* V, int64_t ldv, int v_fp32, float split_scale, cudaStream_t st);
+                 const void* S, void* V, int64_t ldv, int v_fp32, float split_scale, cudaStream_t st, int accumulate = 0);
 // split_scale != 0: the fp32 buffer holds split16 rows written with that scale
 
 // tensor-core K6 for a split16 buffer (reorth_tc16.cu): B = 16 or 32, S fp32; scratch: ritz_h_scratch_words words
 size_t ritz_h_scratch_words(int B, int64_t m, int kpad);
 void launch_ritz_h(int B, int64_t n, int64_t m, int k, int kpad, const void* buf, int64_t block_stride_elems, const void* S,
-                   void* V, int64_t ldv, int v_fp32, float split_scale, unsigned* scratch, cudaStream_t st);
+                   void* V, int64_t ldv, int v_fp32, float split_scale, unsigned* scratch, cudaStream_t st, int accumulate = 0);
 
 // ---- layout / conversion helpers -------------------------------------------------------------------
 // column-major n x b (ld) fp64  ->  row-major n x B fp64 (zero padded)

@@ -721,25 +721,27 @@ void launch_reorth_coeff_h(const ReorthPlan& p, const void* Cmat, float* scratch
 
 template <int B, bool PS>
 static void update_h_launch(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, double* w0,
-                            double* w1, void* store_w1, void* store_w0, float* scratch, int64_t m_cap, cudaStream_t st) {
+                            double* w1, void* store_w1, void* store_w0, float* scratch, int64_t m_cap, cudaStream_t st,
+                            int64_t coef_block0) {
     using U = UpdH<B, PS>;
     HScratch s = h_layout(scratch, B, p.n, m_cap);
     static PerDeviceOnce once;
     if (once.first()) cudaFuncSetAttribute(reorth_update_h_kernel<B, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U::smem_bytes);
     const unsigned grid = (unsigned)((p.n + U::ROWS_CTA - 1) / U::ROWS_CTA);
-    reorth_update_h_kernel<B, PS><<<grid, U::NW * 32, U::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.ch, s.cl,
+    const size_t coff = (size_t)coef_block0 * (B / 2) * 2 * B;
+    reorth_update_h_kernel<B, PS><<<grid, U::NW * 32, U::smem_bytes, st>>>(p.n, p.m, (const float*)buf, bstride, s.ch + coff, s.cl + coff,
                                                                  pick_scale(n_global), s.scale_c, w0, w1, (float*)store_w1, (float*)store_w0);
 }
 
 void launch_reorth_update_h(const ReorthPlan& p, int64_t n_global, const void* buf, int64_t bstride, double* w0,
                             double* w1, void* store_w1, float* scratch, int64_t m_cap, int presplit, cudaStream_t st,
-                            void* store_w0) {
+                            void* store_w0, int64_t coef_block0) {
     if (p.B == 16) {
-        if (presplit) update_h_launch<16, true>(p, n_global, buf, bstride, w0, w1, store_w1, store_w0, scratch, m_cap, st);
-        else update_h_launch<16, false>(p, n_global, buf, bstride, w0, w1, store_w1, store_w0, scratch, m_cap, st);
+        if (presplit) update_h_launch<16, true>(p, n_global, buf, bstride, w0, w1, store_w1, store_w0, scratch, m_cap, st, coef_block0);
+        else update_h_launch<16, false>(p, n_global, buf, bstride, w0, w1, store_w1, store_w0, scratch, m_cap, st, coef_block0);
     } else {
-        if (presplit) update_h_launch<32, true>(p, n_global, buf, bstride, w0, w1, store_w1, store_w0, scratch, m_cap, st);
-        else update_h_launch<32, false>(p, n_global, buf, bstride, w0, w1, store_w1, store_w0, scratch, m_cap, st);
+        if (presplit) update_h_launch<32, true>(p, n_global, buf, bstride, w0, w1, store_w1, store_w0, scratch, m_cap, st, coef_block0);
+        else update_h_launch<32, false>(p, n_global, buf, bstride, w0, w1, store_w1, store_w0, scratch, m_cap, st, coef_block0);
     }
 }
 
@@ -784,7 +786,8 @@ __global__ void split_ritz_coeff_kernel(size_t nwords, int kpad, int ncols, cons
 template <int B, int NT, typename VT>
 __global__ void __launch_bounds__(RitzH<B, NT>::NW * 32)
     ritz_h_kernel(int64_t n, int64_t m, const float* __restrict__ buf, int64_t bstride, const unsigned* __restrict__ Sh,
-                  const unsigned* __restrict__ Sl, int ncols, float inv_scale, VT* __restrict__ V, int64_t ldv, int k) {
+                  const unsigned* __restrict__ Sl, int ncols, float inv_scale, VT* __restrict__ V, int64_t ldv, int k,
+                  int accumulate) {
     using C = RitzH<B, NT>;
     constexpr int NW = C::NW, KS = C::KS, PA = C::PA, NCOL = C::NCOL, PC = C::PC, JC = C::JC, NST = C::NST,
                   STAGE = C::STAGE, CBUF = C::CBUF, NCP = C::NCP, NTHR = NW * 32;
@@ -911,8 +914,14 @@ __global__ void __launch_bounds__(RitzH<B, NT>::NW * 32)
             const int col = col0 + x * 8 + 2 * t;
             const double v0 = (dacc[x][2 * h] + (double)acc[x][2 * h]) * (double)inv_scale;
             const double v1 = (dacc[x][2 * h + 1] + (double)acc[x][2 * h + 1]) * (double)inv_scale;
-            if (col < k) V[(size_t)col * ldv + row] = (VT)v0;
-            if (col + 1 < k) V[(size_t)(col + 1) * ldv + row] = (VT)v1;
+            if (col < k) {
+                VT* d0 = V + (size_t)col * ldv + row;
+                *d0 = accumulate ? (VT)((double)*d0 + v0) : (VT)v0;
+            }
+            if (col + 1 < k) {
+                VT* d1 = V + (size_t)(col + 1) * ldv + row;
+                *d1 = accumulate ? (VT)((double)*d1 + v1) : (VT)v1;
+            }
         }
     }
 }
@@ -920,12 +929,12 @@ __global__ void __launch_bounds__(RitzH<B, NT>::NW * 32)
 template <int B, int NT, typename VT>
 static void ritz_h_launch_t(int64_t n, int64_t m, int k, const void* buf, int64_t bstride, const unsigned* sh,
                             const unsigned* sl, int ncols, int groups, float inv_scale, void* V, int64_t ldv,
-                            cudaStream_t st) {
+                            cudaStream_t st, int accumulate) {
     using R = RitzH<B, NT>;
     cudaFuncSetAttribute(ritz_h_kernel<B, NT, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::smem_bytes);
     dim3 grid((unsigned)((n + R::ROWS_CTA - 1) / R::ROWS_CTA), (unsigned)groups);
     ritz_h_kernel<B, NT, VT><<<grid, R::NW * 32, R::smem_bytes, st>>>(n, m, (const float*)buf, bstride, sh, sl, ncols, inv_scale,
-                                                                     (VT*)V, ldv, k);
+                                                                     (VT*)V, ldv, k, accumulate);
 }
 
 // column groups of at most 64 Ritz columns; NT n-tiles per group from {2, 4, 6, 7, 8}
@@ -943,7 +952,7 @@ size_t ritz_h_scratch_words(int B, int64_t m, int kpad) {
 }
 
 void launch_ritz_h(int B, int64_t n, int64_t m, int k, int kpad, const void* buf, int64_t bstride, const void* Smat,
-                   void* V, int64_t ldv, int v_fp32, float split_scale, unsigned* scratch, cudaStream_t st) {
+                   void* V, int64_t ldv, int v_fp32, float split_scale, unsigned* scratch, cudaStream_t st, int accumulate) {
     int groups, nt;
     ritz_h_shape(kpad, groups, nt);
     const int ncols = groups * nt * 8;
@@ -956,8 +965,8 @@ void launch_ritz_h(int B, int64_t n, int64_t m, int k, int kpad, const void* buf
     auto go = [&](auto bc, auto ntc) {
         constexpr int BB = decltype(bc)::value;
         constexpr int NN = decltype(ntc)::value;
-        if (v_fp32) ritz_h_launch_t<BB, NN, float>(n, m, k, buf, bstride, sh, sl, ncols, groups, inv, V, ldv, st);
-        else ritz_h_launch_t<BB, NN, double>(n, m, k, buf, bstride, sh, sl, ncols, groups, inv, V, ldv, st);
+        if (v_fp32) ritz_h_launch_t<BB, NN, float>(n, m, k, buf, bstride, sh, sl, ncols, groups, inv, V, ldv, st, accumulate);
+        else ritz_h_launch_t<BB, NN, double>(n, m, k, buf, bstride, sh, sl, ncols, groups, inv, V, ldv, st, accumulate);
     };
     auto by_nt = [&](auto bc) {
         switch (nt) {

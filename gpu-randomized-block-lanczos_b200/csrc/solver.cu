@@ -33,6 +33,7 @@
 #include <mutex>
 #include <numeric>
 #include <thread>
+#include <unistd.h>
 
 #include "partition.h"
 
@@ -45,7 +46,7 @@ std::vector<std::pair<int, Workspace*>> g_parked_ws;  // (device, workspace)
 size_t solve_bytes(const Workspace& w) {
     size_t x = 0;
     for (int i = 0; i < 4; ++i) x += w.X[i].count;
-    return w.buf.count + w.ritzV.count + w.ritzS.count + w.Cmat.count + w.rpart.count + w.tc_scratch.count * 4 +
+    return w.buf.count + w.stage.count + w.ritzV.count + w.ritzS.count + w.Cmat.count + w.rpart.count + w.tc_scratch.count * 4 +
            w.ritz_words.count * 4 + (x + w.omega.count + w.part.count + w.small.count + w.sendbuf.count + w.Vacc.count) * 8;
 }
 size_t ws_bytes(const Workspace& w) {
@@ -414,6 +415,49 @@ struct Run {
     bool fused = false;
     int fgrid = 1;
     void* slot(int64_t j) { return w.buf.p + (size_t)j * bstride * ssz; }
+    // ---- host tier of the Krylov slab (opts.spill; hybrid_part_reorth!, RBL_gpu.jl:59-81,127-130,168-169) ------------
+    // slab slots [0, m_dev) live in HBM, slots [m_dev, m_cap) in pinned host memory.  Spilled blocks are written through
+    // a device staging block and streamed back, kChunk blocks at a time (double-buffered on a copy stream), for every
+    // Gram / update / Ritz pass.
+    static constexpr int kChunk = 4;
+    int64_t m_dev = 0;
+    int64_t spilled_hi = 0;     // highest spilled slot written + 1
+    size_t blk_bytes() const { return (size_t)bstride * ssz; }
+    bool is_spilled(int64_t j) const { return j >= m_dev; }
+    unsigned char* hslot(int64_t j) { return w.hslab.p + (size_t)(j - m_dev) * blk_bytes(); }
+    unsigned char* stage_chunk(int which) { return w.stage.p + (size_t)which * kChunk * blk_bytes(); }
+    unsigned char* stage_store(int which) { return w.stage.p + (size_t)(2 * kChunk + which) * blk_bytes(); }
+    // where a kernel writes slab block j (j < 0: nowhere); flush_store afterwards moves a staged block to the host tier
+    void* store_dst(int64_t j, int which) { return j < 0 ? nullptr : (is_spilled(j) ? (void*)stage_store(which) : slot(j)); }
+    void flush_store(int64_t j, int which) {
+        if (j < 0 || !is_spilled(j)) return;
+        RBL_CUDA(cudaMemcpyAsync(hslot(j), stage_store(which), blk_bytes(), cudaMemcpyDeviceToHost, st));
+        spilled_hi = std::max(spilled_hi, j + 1);
+    }
+    // for every kChunk-block piece [c0, c0+cn) of the spilled range [from, to): f(device pointer, c0, cn); the next
+    // piece is copied in on the copy stream while f works on this one
+    template <typename F>
+    void for_spilled_chunks(int64_t from, int64_t to, F&& f) {
+        if (to <= from) return;
+        cudaStream_t cs = w.copy_stream;
+        RBL_CUDA(cudaEventRecord(w.spill_ev[4], st));          // host tier writes issued so far on the main stream
+        RBL_CUDA(cudaStreamWaitEvent(cs, w.spill_ev[4], 0));
+        auto prefetch = [&](int64_t c0, int which) {
+            const int64_t cn = std::min<int64_t>(kChunk, to - c0);
+            RBL_CUDA(cudaStreamWaitEvent(cs, w.spill_ev[2 + which], 0));   // the kernel that last read this staging chunk
+            RBL_CUDA(cudaMemcpyAsync(stage_chunk(which), hslot(c0), (size_t)cn * blk_bytes(), cudaMemcpyHostToDevice, cs));
+            RBL_CUDA(cudaEventRecord(w.spill_ev[which], cs));
+        };
+        int which = 0;
+        prefetch(from, 0);
+        for (int64_t c0 = from; c0 < to; c0 += kChunk, which ^= 1) {
+            const int64_t cn = std::min<int64_t>(kChunk, to - c0);
+            if (c0 + kChunk < to) prefetch(c0 + kChunk, which ^ 1);
+            RBL_CUDA(cudaStreamWaitEvent(st, w.spill_ev[which], 0));
+            f((void*)stage_chunk(which), c0, cn);
+            RBL_CUDA(cudaEventRecord(w.spill_ev[2 + which], st));
+        }
+    }
 
     void nccl(bool ok, const std::string& err) {
         if (!ok) throw Error(RBL_NCCL_ERROR, err);
@@ -534,7 +578,8 @@ struct Run {
         }
     }
     // one block step after the operator was applied: U = op(A) Q_i  ->  Q_{i+1} (in U), A_i, B_i
-    void step_after_op(bool have_prev, void* store_slot, int reset_ref) {
+    void step_after_op(bool have_prev, int64_t store_j, int reset_ref) {
+        void* store_slot = store_dst(store_j, 0);
         tm.mark(PH_3TERM);
         pass_B(have_prev);
         pass_C();
@@ -547,6 +592,7 @@ struct Run {
         tm.mark(PH_LOC);
         pass_E(store_slot);
         pass_3(store_slot);
+        flush_store(store_j, 0);
     }
 
     void halo(double* Xblk) {
@@ -627,44 +673,62 @@ struct Run {
 
     // K5a: C = Qbuf[0..m)' * [w0 | w1] into w.Cmat (all-reduced over ranks); K5b: w -= Qbuf * C, optional refresh
     // of one slab block with the updated w1.  hybrid_part_reorth! / part_reorth_gpu_async!, RBL_gpu.jl:59-81,29-47
-    void reorth_gram(int64_t m, double* w0, double* w1) {
-        ReorthPlan p = reorth_plan(B, fp32, nloc, m);
+    // Gram of `mc` stored blocks at device address `buf` into rows [row0, row0+mc) of the coefficient matrix
+    void gram_part(const void* buf, int64_t mc, int64_t row0, double* w0, double* w1) {
+        ReorthPlan p = reorth_plan(B, fp32, nloc, mc);
+        unsigned char* Cdst = w.Cmat.p + (size_t)row0 * B * 2 * B * ssz;
         if (use_d) {
-            launch_reorth_gram_d(p, w.buf.p, bstride, w0, w1, w.rpart.p, w.Cmat.p, st);
+            launch_reorth_gram_d(p, buf, bstride, w0, w1, w.rpart.p, Cdst, st);
             launches += 2;
-            if (multi) { std::string err; nccl(h->comm.allreduce_f64((double*)w.Cmat.p, (size_t)m * B * 2 * B, st, err), err); }
         } else if (use_h) {
-            launch_reorth_gram_h(p, h->n, w.buf.p, bstride, w0, w1, w.rpart.p, w.Cmat.p, w.tc_scratch.p, m_cap, split_scale != 0.f, st);
+            launch_reorth_gram_h(p, h->n, buf, bstride, w0, w1, w.rpart.p, Cdst, w.tc_scratch.p, m_cap, split_scale != 0.f, st);
             launches += 4;
-            if (multi) { std::string err; nccl(h->comm.allreduce_f32((float*)w.Cmat.p, (size_t)m * B * 2 * B, st, err), err); }
         } else {
-            launch_reorth_gram(p, w.buf.p, bstride, w0, w1, w.rpart.p, w.Cmat.p, st);
+            launch_reorth_gram(p, buf, bstride, w0, w1, w.rpart.p, Cdst, st);
             launches += 2;
-            if (multi) {
-                std::string err;
-                const size_t cnt = (size_t)m * B * 2 * B;
-                nccl(fp32 ? h->comm.allreduce_f32((float*)w.Cmat.p, cnt, st, err) : h->comm.allreduce_f64((double*)w.Cmat.p, cnt, st, err), err);
-            }
+        }
+    }
+    void reorth_gram(int64_t m, double* w0, double* w1) {
+        const int64_t md = std::min(m, m_dev);
+        if (md > 0) gram_part(w.buf.p, md, 0, w0, w1);
+        for_spilled_chunks(md, m, [&](void* dev, int64_t c0, int64_t cn) { gram_part(dev, cn, c0, w0, w1); });
+        if (multi) {
+            std::string err;
+            const size_t cnt = (size_t)m * B * 2 * B;
+            nccl((fp32 ? h->comm.allreduce_f32((float*)w.Cmat.p, cnt, st, err) : h->comm.allreduce_f64((double*)w.Cmat.p, cnt, st, err)), err);
         }
         ++n_rgram;
         bytes_rgram += (double)ssz * (double)nloc * (double)m * B + 8.0 * (double)nloc * 2 * B;
     }
-    void reorth_update(int64_t m, double* w0, double* w1, void* store_w1, void* store_w0 = nullptr) {
-        ReorthPlan p = reorth_plan(B, fp32, nloc, m);
-        if (use_d) {
-            launch_reorth_update_d(p, w.buf.p, bstride, w.Cmat.p, w0, w1, store_w1, st, store_w0);
-            ++launches;
-        } else if (use_h) {
-            launch_reorth_coeff_h(p, w.Cmat.p, w.tc_scratch.p, m_cap, multi ? 1 : 0, st);
-            launch_reorth_update_h(p, h->n, w.buf.p, bstride, w0, w1, store_w1, w.tc_scratch.p, m_cap, split_scale != 0.f, st, store_w0);
-            launches += 2;
-        } else {
-            launch_reorth_update(p, w.buf.p, bstride, w.Cmat.p, w0, w1, store_w1, st, store_w0);
+    void update_part(const void* buf, int64_t mc, int64_t row0, double* w0, double* w1, void* store_w1, void* store_w0) {
+        ReorthPlan p = reorth_plan(B, fp32, nloc, mc);
+        const unsigned char* Csrc = w.Cmat.p + (size_t)row0 * B * 2 * B * ssz;
+        if (use_d) launch_reorth_update_d(p, buf, bstride, Csrc, w0, w1, store_w1, st, store_w0);
+        else if (use_h) launch_reorth_update_h(p, h->n, buf, bstride, w0, w1, store_w1, w.tc_scratch.p, m_cap, split_scale != 0.f, st, store_w0, row0);
+        else launch_reorth_update(p, buf, bstride, Csrc, w0, w1, store_w1, st, store_w0);
+        ++launches;
+    }
+    // j_w1 / j_w0: slab slots whose stored copies are refreshed with the updated targets (-1: none)
+    void reorth_update(int64_t m, double* w0, double* w1, int64_t j_w1, int64_t j_w0 = -1) {
+        const int64_t md = std::min(m, m_dev);
+        if (use_h) {
+            ReorthPlan p = reorth_plan(B, fp32, nloc, m);
+            launch_reorth_coeff_h(p, w.Cmat.p, w.tc_scratch.p, m_cap, (multi || md < m) ? 1 : 0, st);
             ++launches;
         }
+        // the refresh must see the fully updated targets: it rides on the LAST partial update
+        void* s1 = store_dst(j_w1, 1);
+        void* s0 = store_dst(j_w0, 2);
+        if (md > 0) update_part(w.buf.p, md, 0, w0, w1, md == m ? s1 : nullptr, md == m ? s0 : nullptr);
+        for_spilled_chunks(md, m, [&](void* dev, int64_t c0, int64_t cn) {
+            const bool last = c0 + cn >= m;
+            update_part(dev, cn, c0, w0, w1, last ? s1 : nullptr, last ? s0 : nullptr);
+        });
+        flush_store(j_w1, 1);
+        flush_store(j_w0, 2);
         ++n_rupd;
         bytes_rupd += (double)ssz * (double)nloc * (double)m * B + 2 * 8.0 * (double)nloc * 2 * B +
-                      ((store_w1 ? 1.0 : 0.0) + (store_w0 ? 1.0 : 0.0)) * (double)ssz * (double)nloc * B;
+                      ((j_w1 >= 0 ? 1.0 : 0.0) + (j_w0 >= 0 ? 1.0 : 0.0)) * (double)ssz * (double)nloc * B;
     }
 
     // decision shared by all ranks: 0 continue, 1 accept, 2 abort (the root's host check failed)
@@ -858,11 +922,12 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
     // Invariant of the loop below: `cur` = Q_i is already locally re-orthogonalised against Q_{i-1} and stored in
     // slab slot nlb+i-1 (both happen in pass E of the step that produced it).
     tm.mark(PH_LOC);
-    launch_store_block(B, nloc, cur, slot(nlb), fp32, split_scale, st);
+    launch_store_block(B, nloc, cur, store_dst(nlb, 0), fp32, split_scale, st);
+    flush_store(nlb, 0);
     ++launches;
     tm.mark(PH_SPMM);
     apply_op(cur, U);
-    step_after_op(false, (nlb + 1 < m_cap) ? slot(nlb + 1) : nullptr, 1);
+    step_after_op(false, (nlb + 1 < m_cap) ? nlb + 1 : -1, 1);
     record_step(1);
     tm.mark(PH_NONE);
     { double* t = prev; prev = cur; cur = U; U = t; }
@@ -923,11 +988,11 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
             tm.mark(PH_RGRAM);
             reorth_gram(m, cur, prev);
             tm.mark(PH_RUPD);
-            reorth_update(m, cur, prev, slot(nlb + i - 2), slot(nlb + i - 1));
+            reorth_update(m, cur, prev, nlb + i - 2, nlb + i - 1);
         }
         tm.mark(PH_SPMM);
         apply_op(cur, U);                                                      // :176
-        step_after_op(true, (nlb + i < m_cap) ? slot(nlb + i) : nullptr, 0);   // :177-184 and :167-172 of the next step
+        step_after_op(true, (nlb + i < m_cap) ? nlb + i : -1, 0);   // :177-184 and :167-172 of the next step
         record_step(i);
         tm.mark(PH_NONE);
         { double* t = prev; prev = cur; cur = U; U = t; }
@@ -1024,14 +1089,24 @@ void Run::ritz(int64_t nlb, int64_t mfin, const TopKResult& res, const std::vect
     dS.ensure(Sh.size());
     RBL_CUDA(cudaMemcpyAsync(dS.p, Sh.data(), Sh.size(), cudaMemcpyHostToDevice, st));
     tm.mark(PH_RITZ);
-    if (split_scale != 0.f) {
-        w.ritz_words.ensure(ritz_h_scratch_words(B, mfin, kpad));
-        launch_ritz_h(B, nloc, mfin, (int)kc, kpad, slot(nlb), bstride, dS.p, Vdev, ldv, out_fp32 ? 1 : 0, split_scale, w.ritz_words.p, st);
+    // blocks nlb .. nlb+mfin: the HBM part in one launch, spilled blocks chunk by chunk (accumulating), RBL_gpu.jl:116-130
+    auto ritz_part = [&](const void* bufp, int64_t j0, int64_t mc, int accumulate) {
+        const unsigned char* Sp = dS.p + (size_t)j0 * B * kpad * ssz;
+        if (split_scale != 0.f) {
+            w.ritz_words.ensure(ritz_h_scratch_words(B, mc, kpad));
+            launch_ritz_h(B, nloc, mc, (int)kc, kpad, bufp, bstride, Sp, Vdev, ldv, out_fp32 ? 1 : 0, split_scale, w.ritz_words.p, st, accumulate);
+            ++launches;
+        } else {
+            launch_ritz(B, fp32, nloc, mc, (int)kc, kpad, bufp, bstride, Sp, Vdev, ldv, out_fp32 ? 1 : 0, 0.f, st, accumulate);
+        }
         ++launches;
-    } else {
-        launch_ritz(B, fp32, nloc, mfin, (int)kc, kpad, slot(nlb), bstride, dS.p, Vdev, ldv, out_fp32 ? 1 : 0, 0.f, st);
-    }
-    ++launches;
+    };
+    const int64_t dev_blocks = std::max<int64_t>(0, std::min(nlb + mfin, m_dev) - nlb);
+    if (dev_blocks > 0) ritz_part(slot(nlb), 0, dev_blocks, 0);
+    for_spilled_chunks(nlb + dev_blocks, nlb + mfin, [&](void* dev, int64_t c0, int64_t cn) {
+        ritz_part(dev, c0 - nlb, cn, (c0 - nlb) > 0 ? 1 : 0);
+        if (split_scale != 0.f) RBL_CUDA(cudaStreamSynchronize(st));   // ritz_words is reused by the next piece
+    });
     tm.mark(PH_NONE);
     RBL_CUDA(cudaStreamSynchronize(st));   // Sh goes out of scope
     stats.bytes_ritz += (double)ssz * (double)nloc * (double)mfin * B + (out_fp32 ? 4.0 : 8.0) * (double)nloc * (double)kc;
@@ -1157,18 +1232,39 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
     }
     if (m_fit < 3) throw Error(RBL_OOM, "rbl_solve: problem does not fit device memory (fewer than 3 Krylov blocks)");
     int64_t m_cap = std::min(m_req, m_fit);
+    int64_t m_dev = m_cap;
     const bool mem_capped = m_fit < m_req;
-    if (mem_capped && !opt.restart)
+    if (mem_capped && opt.spill) {
+        // host tier (hybrid_part_reorth!, RBL_gpu.jl:59-81): the staging buffers come out of the device budget, the
+        // blocks that do not fit go to pinned host memory (at most half of the physical RAM)
+        const int64_t stage_blocks = 2 * Run::kChunk + 3;
+        if (m_fit - stage_blocks < 3) throw Error(RBL_OOM, "rbl_solve: device memory too small for the host-spill staging buffers");
+        m_dev = m_fit - stage_blocks;
+        const double host_budget = 0.5 * (double)sysconf(_SC_PHYS_PAGES) * (double)sysconf(_SC_PAGE_SIZE);
+        const int64_t host_blocks = (int64_t)(host_budget / ((double)c.bstride * c.ssz));
+        m_cap = std::min(m_req, m_dev + host_blocks);
+    }
+    if (mem_capped && !opt.restart && m_cap < m_req)
         std::fprintf(stderr, "[rbl] warning: Krylov buffer capped at %lld blocks by device memory (%lld requested); "
                              "set opts.restart to continue past the cap\n", (long long)m_cap, (long long)m_req);
     c.m_cap = m_cap;
-    stats.buffer_blocks = m_cap;
+    c.m_dev = m_dev;
+    stats.buffer_blocks = m_dev;
+    if (m_dev < m_cap) {
+        w.stage.ensure((size_t)(2 * Run::kChunk + 3) * c.bstride * c.ssz);
+        w.hslab.ensure((size_t)(m_cap - m_dev) * c.bstride * c.ssz);
+        if (!w.copy_stream) RBL_CUDA(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
+        for (auto& e : w.spill_ev)
+            if (!e) RBL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (int q = 0; q < 5; ++q) RBL_CUDA(cudaEventRecord(w.spill_ev[q], c.st));
+        if (opt.verbose) std::fprintf(stderr, "[rbl] host spill tier: %lld blocks in HBM, up to %lld in pinned host memory\n", (long long)m_dev, (long long)(m_cap - m_dev));
+    }
     c.rgrid = rowop_grid(B, c.nloc);
     c.fused = fused_rowop_supported(B);
     c.fgrid = c.fused ? fused_rowop_grid(B, c.nloc) : 1;
     const int nX = 3 + (filtering ? 1 : 0);
     for (int i = 0; i < nX; ++i) w.X[i].ensure((size_t)c.next * B);
-    w.buf.ensure((size_t)m_cap * c.bstride * c.ssz);
+    w.buf.ensure((size_t)m_dev * c.bstride * c.ssz);
     w.part.ensure(std::max((size_t)c.rgrid, (size_t)2 * c.fgrid) * B * B);
     w.small.ensure(Run::kSmallMats * (size_t)B * B);
     w.qr.ensure(1);
@@ -1323,7 +1419,8 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
         for (int64_t blk = first_blk; blk < nlb_new; ++blk) {
             const int ncol = (int)std::min<int64_t>(b, nlock - blk * b);
             launch_colmajor_to_block(B, c.nloc, ncol, w.Vacc.p + (size_t)blk * b * c.nloc, c.nloc, c.U, c.st);
-            launch_store_block(B, c.nloc, c.U, c.slot(blk), c.fp32, c.split_scale, c.st);
+            launch_store_block(B, c.nloc, c.U, c.store_dst(blk, 0), c.fp32, c.split_scale, c.st);
+            c.flush_store(blk, 0);
             c.launches += 2;
         }
         nlb = nlb_new;
@@ -1346,7 +1443,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
         RBL_CUDA(cudaMemsetAsync(c.prev, 0, (size_t)c.next * B * 8, c.st));
         if (nlb > 0) {   // restart_reorth_gpu! (restarted.jl:1-21): start block orthogonal to the locked vectors
             c.reorth_gram(nlb, c.cur, c.prev);
-            c.reorth_update(nlb, c.cur, c.prev, nullptr);
+            c.reorth_update(nlb, c.cur, c.prev, -1);
         }
         c.gram_then_qr(c.cur, 1);
     }
@@ -1412,6 +1509,8 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
     RBL_CUDA(cudaMemcpy(w.hqr.p, w.qr.p, sizeof(QrState), cudaMemcpyDeviceToHost));
     h->last.B = B; h->last.b = b; h->last.blocks = nlb + mfin; h->last.fp32 = c.fp32; h->last.split_scale = c.split_scale;
     h->last.bstride = c.bstride; h->last.ssz = c.ssz; h->last.use_h = c.use_h; h->last.use_d = c.use_d; h->last.m_cap = m_cap;
+    h->last.m_dev = m_dev;
+    stats.spilled_blocks = std::max<int64_t>(0, c.spilled_hi - m_dev);
 
     double sec[PH_COUNT];
     c.tm.collect(sec);
@@ -1449,7 +1548,13 @@ void krylov_block(rbl_handle* h, int64_t j, double* out_colmajor) {
     Workspace& w = h->ws_ref();
     const int64_t nloc = h->nloc;
     double* blk = w.X[0].p;
-    launch_decode_block(L.B, nloc, w.buf.p + (size_t)j * L.bstride * L.ssz, L.fp32, L.split_scale, blk, h->stream);
+    const unsigned char* src = w.buf.p + (size_t)j * L.bstride * L.ssz;
+    if (j >= L.m_dev) {   // spilled block: through the staging buffer
+        RBL_CUDA(cudaMemcpyAsync(w.stage.p, w.hslab.p + (size_t)(j - L.m_dev) * L.bstride * L.ssz, (size_t)L.bstride * L.ssz,
+                                 cudaMemcpyHostToDevice, h->stream));
+        src = w.stage.p;
+    }
+    launch_decode_block(L.B, nloc, src, L.fp32, L.split_scale, blk, h->stream);
     DevBuf<double> cm;
     cm.alloc((size_t)nloc * L.b);
     launch_block_to_colmajor(L.B, nloc, L.b, blk, cm.p, nloc, h->stream);
@@ -1461,6 +1566,7 @@ void krylov_block(rbl_handle* h, int64_t j, double* out_colmajor) {
 void orthogonality(rbl_handle* h, double* max_abs, double* fro) {
     const KrylovInfo& L = h->last;
     if (L.blocks <= 0) throw Error(RBL_INVALID, "rbl_orthogonality: no solve has run on this handle");
+    if (L.blocks > L.m_dev) throw Error(RBL_INVALID, "rbl_orthogonality: not available when Krylov blocks were spilled to the host (use rbl_krylov_block)");
     RBL_CUDA(cudaSetDevice(h->device));
     Run c(h);
     Workspace& w = c.w;
@@ -1468,6 +1574,7 @@ void orthogonality(rbl_handle* h, double* max_abs, double* fro) {
     c.bstride = L.bstride; c.split_scale = L.split_scale; c.use_h = L.use_h; c.use_d = L.use_d; c.m_cap = L.m_cap;
     c.multi = h->comm.active();
     c.is_root = h->rank == 0;
+    c.m_dev = L.m_dev;
     c.tm.enabled = false;
     c.tm.h = h; c.tm.st = c.st;
     DevBuf<double> acc;

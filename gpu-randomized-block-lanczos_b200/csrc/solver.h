@@ -94,6 +94,10 @@ struct Workspace {
     DevBuf<unsigned char> ritzS, ritzV;   // Ritz coefficient matrix and (host-output solves) the device copy of V
     DevBuf<unsigned> ritz_words;          // f16 hi/lo words of S for the tensor-core Ritz kernel
     DevBuf<double> omega;
+    PinnedBuf<unsigned char> hslab;       // host tier of the Krylov slab (opts.spill)
+    DevBuf<unsigned char> stage;          // 2 staging chunks + 3 staging store blocks of the host tier
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t spill_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf<double> Vacc;                  // restarted / filtered solves: fp64 locked + final Ritz vectors (nloc x k)
     DevBuf<double> ctrl, share;           // row-sharded runs: decision flag and the shared (D, S) of the accepting check
     PinnedBuf<double> h_ctrl;
@@ -107,6 +111,9 @@ struct Workspace {
     std::vector<cudaEvent_t> event_pool;
     ~Workspace() {
         for (auto e : event_pool) cudaEventDestroy(e);
+        for (auto e : spill_ev)
+            if (e) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -121,7 +128,7 @@ namespace rbl {
 // what the last solve left in the Krylov slab (debug / parity exports rbl_krylov_block, rbl_orthogonality)
 struct KrylovInfo {
     int B = 0, b = 0;
-    int64_t blocks = 0, bstride = 0, m_cap = 0;
+    int64_t blocks = 0, bstride = 0, m_cap = 0, m_dev = 0;
     bool fp32 = false, use_h = false, use_d = false;
     float split_scale = 0.f;
     size_t ssz = 8;
