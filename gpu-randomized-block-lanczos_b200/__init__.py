@@ -6,5 +6,5 @@ Host-side mirror (Python, ctypes) of the Julia interface of Iasonaspg/GPU-Random
 """
 from .binding import (RblError, RblOptions, RblStats, Solver, lib, lib_path, load_library,  # noqa: F401
                       band_eig_topk, band_count_below, Checker, halo_plan, partition_rows, microbench,
-                      k_spmm, k_gram, k_block_qr, k_reorth, k_ritz)
+                      k_spmm, k_gram, k_block_qr, k_reorth, k_ritz, load_matrix_market, load_matrix)
 from .rbl import RBL, RBL_gpu, rbl_solve_sharded  # noqa: F401

@@ -94,6 +94,9 @@ SIGNATURES = {
     "rbl_partition_rows": (C.c_int, [C.c_int64, C.c_int, _P64]),
     "rbl_halo_plan": (C.c_int, [C.c_int64, C.c_int, _P64, C.c_int, C.c_int64, C.c_int64, _P64, _P64, _P64, _P64, _P64,
                                 _P32]),
+    "rbl_matrix_market_read": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p), _P64, _P64]),
+    "rbl_matrix_arrays": (C.c_int, [C.c_void_p, C.POINTER(_P64), C.POINTER(_P64), C.POINTER(_PD)]),
+    "rbl_matrix_free": (C.c_int, [C.c_void_p]),
     "rbl_microbench": (C.c_int, [C.c_int, C.c_int64, C.c_int, _PD]),
 }
 
@@ -388,3 +391,33 @@ def microbench(which: int, size: int = 1 << 30, iters: int = 10) -> float:
     out = C.c_double()
     _check(lib().rbl_microbench(which, size, iters, C.byref(out)))
     return out.value
+
+
+# ---- loaders (benchmark.jl:3-4,12-28: MatrixMarket.jl / MAT.jl) -----------------------------------------------------------
+def load_matrix_market(path: str):
+    """`mmread(path)` through the library's native reader -> scipy.sparse.csc_matrix (symmetric storage expanded)."""
+    import scipy.sparse as sp
+    h = C.c_void_p()
+    n, nnz = C.c_int64(), C.c_int64()
+    _check(lib().rbl_matrix_market_read(os.fsencode(path), 0, C.byref(h), C.byref(n), C.byref(nnz)))
+    try:
+        cp, rv, nz = _P64(), _P64(), _PD()
+        _check(lib().rbl_matrix_arrays(h, C.byref(cp), C.byref(rv), C.byref(nz)))
+        colptr = np.ctypeslib.as_array(cp, shape=(n.value + 1,)).copy()
+        rowval = np.ctypeslib.as_array(rv, shape=(max(nnz.value, 1),))[:nnz.value].copy()
+        nzval = np.ctypeslib.as_array(nz, shape=(max(nnz.value, 1),))[:nnz.value].copy()
+    finally:
+        lib().rbl_matrix_free(h)
+    return sp.csc_matrix((nzval, rowval, colptr), shape=(n.value, n.value))
+
+
+def load_matrix(path: str):
+    """SuiteSparse downloads as the reference's driver reads them: `.mtx` (Matrix Market, native reader) or `.mat`
+    (MATLAB v5 `Problem.A`, benchmark.jl:25-27, through scipy.io.loadmat; v7.3 / HDF5 files are not supported)."""
+    if path.lower().endswith(".mat"):
+        import scipy.io
+        import scipy.sparse as sp
+        d = scipy.io.loadmat(path)
+        A = d["Problem"]["A"][0, 0] if "Problem" in d else next(v for v in d.values() if sp.issparse(v))
+        return sp.csc_matrix(A, dtype=np.float64)
+    return load_matrix_market(path)

@@ -8,6 +8,7 @@
 #include <thread>
 #include <vector>
 
+#include "mmio.h"
 #include "partition.h"
 #include "solver.h"
 
@@ -652,6 +653,34 @@ int rbl_halo_plan(int64_t n, int world, const int64_t* row_starts, int rank, int
         if (colidx_local_out) std::memcpy(colidx_local_out, p.colidx_local.data(), p.colidx_local.size() * 4);
         return (int)RBL_OK;
     });
+}
+
+// ---- Matrix Market loader (benchmark.jl:21,28 mmread) ---------------------------------------------------------------
+struct rbl_matrix {
+    MmMatrix m;
+};
+int rbl_matrix_market_read(const char* path, int index_base, rbl_matrix** out, int64_t* n_out, int64_t* nnz_out) {
+    return guarded([&] {
+        if (!path || !out || (index_base != 0 && index_base != 1)) throw Error(RBL_INVALID, "rbl_matrix_market_read: bad arguments");
+        std::unique_ptr<rbl_matrix> M(new rbl_matrix());
+        std::string err;
+        if (!read_matrix_market(path, index_base, M->m, err)) throw Error(RBL_INVALID, "rbl_matrix_market_read: " + err);
+        if (n_out) *n_out = M->m.n;
+        if (nnz_out) *nnz_out = (int64_t)M->m.nzval.size();
+        *out = M.release();
+        return (int)RBL_OK;
+    });
+}
+int rbl_matrix_arrays(rbl_matrix* m, const int64_t** colptr, const int64_t** rowval, const double** nzval) {
+    if (!m) return RBL_INVALID;
+    if (colptr) *colptr = m->m.colptr.data();
+    if (rowval) *rowval = m->m.rowval.data();
+    if (nzval) *nzval = m->m.nzval.data();
+    return RBL_OK;
+}
+int rbl_matrix_free(rbl_matrix* m) {
+    delete m;
+    return RBL_OK;
 }
 
 int rbl_microbench(int which, int64_t size, int iters, double* result_out) {

@@ -267,6 +267,15 @@ int rbl_halo_plan(int64_t n, int world, const int64_t* row_starts, int rank, int
                   const int64_t* rowptr, const int64_t* colidx_global, int64_t* n_halo_out, int64_t* halo_cols_out,
                   int64_t* halo_owner_ptr_out, int32_t* colidx_local_out);
 
+/* Matrix Market loader (host only) - what `mmread` gives the reference's benchmark driver (benchmark.jl:3,21,28): reads a
+ * square `coordinate` file (real / integer / pattern; general / symmetric / skew-symmetric) into the CSC arrays rbl_create
+ * takes (full matrix, symmetric storage expanded, duplicates summed, row indices sorted, index_base 0 or 1).
+ * The arrays returned by rbl_matrix_arrays stay valid until rbl_matrix_free. */
+typedef struct rbl_matrix rbl_matrix;
+int rbl_matrix_market_read(const char* path, int index_base, rbl_matrix** out, int64_t* n_out, int64_t* nnz_out);
+int rbl_matrix_arrays(rbl_matrix* m, const int64_t** colptr, const int64_t** rowval, const double** nzval);
+int rbl_matrix_free(rbl_matrix* m);
+
 /* Micro-benchmarks used by bench.py / profiles (device): achieved copy GB/s and pipe rates. */
 int rbl_microbench(int which, int64_t size, int iters, double* result_out);
 

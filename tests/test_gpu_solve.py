@@ -192,3 +192,35 @@ def test_multi_gpu_group_handle_one_based_and_device_rng(gpu):
     D2, V2 = gpu.RBL_gpu(L, 8, 4, shift=8.0, seed=3, ngpus=2, index_base=1)
     # the counter-based generator draws element (row, col) independently of the partition: same start block
     assert np.max(np.abs(D2 - D1) / np.abs(D1)) < 1e-10
+
+
+# ---- N4: the reference's drivers on top of the drop-in (benchmark.jl, images.jl) ------------------------------------
+def test_benchmark_driver_with_matrix_market_file_and_arpack(gpu, tmp_path):
+    """benchmark.jl:21-45: mmread -> RBL_gpu(A, nd, 4) -> compare with ARPACK eigs(A, nev=nd, tol=1e-7, which=:LM)."""
+    import io
+    import os
+    import scipy.io
+    import scipy.sparse as sp
+    from tools import benchmark
+    A = matrices.erdos_renyi_sym(3000, 12, seed=8)
+    path = os.path.join(tmp_path, "er.mtx")
+    scipy.io.mmwrite(path, sp.coo_matrix(A), symmetry="symmetric", precision=17)
+    M = gpu.load_matrix(path)
+    buf = io.StringIO()
+    r = benchmark.run(M, 10, 4, precision="fp64", arpack=True, out=buf)
+    assert r["stats"].converged
+    assert np.max(np.abs(r["d"] - r["d_arpack"]) / np.abs(r["d_arpack"])) < 1e-6      # ARPACK's own tol is 1e-7
+    assert "Largest:" in buf.getvalue() and "part reorth" in buf.getvalue()
+
+
+def test_images_driver_low_rank_approximation(gpu):
+    """images.jl:28-32: eigenpairs of the dense B'B with b = 1 give the optimal rank-k approximation of B."""
+    from tools import images
+    Bm = images.synthetic_image(120, 80)
+    k = 12
+    U, s, V, st = images.low_rank(Bm, k)
+    sv = np.linalg.svd(Bm, compute_uv=False)
+    assert st.converged
+    assert np.max(np.abs(s - sv[:k]) / sv[:k]) < 1e-8
+    Blr = (U * s[None, :]) @ V.T
+    assert np.linalg.norm(Bm - Blr) <= np.sqrt(np.sum(sv[k:] ** 2)) * (1 + 1e-6)
