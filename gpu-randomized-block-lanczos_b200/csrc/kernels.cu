@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t nrows, const int* __r
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;
     const int rsel = lane / LPR;
+    // (A blocked assignment - every CTA walking a contiguous row range so that L1 would serve the +-1 / +-N stencil
+    // neighbours - was measured and is slower: 117-222 us against 105 us at 2-16 CTAs per SM on config 2.)
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const double2* __restrict__ Q2 = reinterpret_cast<const double2*>(Q);

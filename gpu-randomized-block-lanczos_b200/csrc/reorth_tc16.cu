@@ -65,10 +65,13 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], const unsigned (&a)[4], c
 // ---- tensor memory (TMEM) as the second accumulation level of the Gram kernel --------------------------------
 // mma.sync accumulates in fp32 with truncation, so the error of an accumulator grows linearly with the length of its
 // chain (measured, tools/reorth_accuracy.py: 256-row chains 1.4x, 1024-row chains 4.9x the error of an fp32 sgemm).
-// Every GRAM_FLUSH k-steps each warp therefore adds its MMA accumulators, with round-to-nearest FADDs, to running sums
-// and restarts the chain from zero.  The sums live in TMEM (256 KB per SM, otherwise unused by this kernel): neither the
-// register file (106 of 128 registers in use) nor shared memory (180 KB of stages) has room for a second accumulator set.
-// A warp reaches lanes [32 (warp % 4), +32) of TMEM; the four warps that share a lane quarter use different columns.
+// Every FLUSH k-steps each warp therefore adds its MMA accumulators, with round-to-nearest FADDs, to running sums
+// and restarts the chain from zero.  The register file has no room for a second accumulator set (106 of 128 registers).
+// B = 16: the sums live in shared memory (64 KB, one pipeline stage fewer).  B = 32: 128 KB of sums do not fit next to
+// the stages, they live in tensor memory (256 KB per SM, otherwise unused by this kernel): a warp reaches lanes
+// [32 (warp % 4), +32) of TMEM, the four warps that share a lane quarter use different columns.  (TMEM sums were
+// measured for B = 16 too: the LDTM / STTM traffic shares the tensor datapath with the MMAs and cost 10% of the
+// kernel's bandwidth; the shared-memory sums cost 3%.)
 __device__ __forceinline__ void tmem_alloc(unsigned* smem_dst, unsigned ncols) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(d), "r"(ncols) : "memory");
@@ -131,14 +134,15 @@ struct GramH {
     static constexpr int NH = NT / 4;            // n-tiles are processed four at a time (register budget)
     static constexpr int PA = B;                 // unpadded rows, permuted + swizzled (see gram_slot)
     static constexpr int PW = 2 * B + 8;         // words per staged target row-pair
-    static constexpr int NST = 5;
+    static constexpr bool SUM_SMEM = (B == 16);  // second-level sums: shared memory (B = 16) or tensor memory (B = 32)
+    static constexpr int NST = SUM_SMEM ? 4 : 5;
     static constexpr int RS = 16;                // rows per stage
     static constexpr int RW = 64;                // rows per shared target chunk (32 row pairs)
     static constexpr int STAGE = WB * RS * PA;   // floats
     static constexpr int WBUF = (RW / 2) * PW;   // words per target buffer (hi or lo)
     static constexpr int NCP = (WB * RS * (B / 4)) / 32;  // cp.async per lane per stage
-    static constexpr size_t smem_bytes = (size_t)(NW * NST * STAGE + 4 * WBUF) * sizeof(float);
     static constexpr int NACC = WB * MT * NT * 4;   // fp32 accumulators per thread
+    static constexpr size_t smem_bytes = (size_t)(NW * NST * STAGE + 4 * WBUF + (SUM_SMEM ? NW * NACC * 32 : 0)) * sizeof(float);
     static constexpr int TCOLS = 4 * NACC;          // TMEM columns: four warps per lane quarter
     static constexpr int FLUSH = 8;                 // k-steps (of RS rows) per tensor-core accumulation chain
 };
@@ -185,46 +189,68 @@ __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
 #pragma unroll
                 for (int y = 0; y < 4; ++y) acc[b][a][x][y] = 0.f;
 
-    // second-level sums in tensor memory (see tmem_* above)
+    // second-level sums (see the note above tmem_alloc)
     constexpr int NACC = C::NACC;
     static_assert(NACC % 16 == 0 && (C::TCOLS & (C::TCOLS - 1)) == 0 && C::TCOLS >= 32 && C::TCOLS <= 512, "TMEM slice shape");
     __shared__ unsigned tmem_base_sh;
-    if (warp == 0) tmem_alloc(&tmem_base_sh, C::TCOLS);
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const unsigned tsum = tmem_base_sh + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * NACC;
-    {
+    unsigned tsum = 0;
+    float4* ssum = nullptr;
+    if constexpr (C::SUM_SMEM) {
+        // [warp][NACC/4][lane] float4: consecutive lanes read consecutive 16-byte words (conflict-free)
+        ssum = reinterpret_cast<float4*>(smem + (size_t)NW * NST * STAGE + 4 * WBUF) + (size_t)warp * (NACC / 4) * 32 + lane;
+#pragma unroll
+        for (int q = 0; q < NACC / 4; ++q) ssum[q * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        if (warp == 0) tmem_alloc(&tmem_base_sh, C::TCOLS);
+        tcgen05_fence_before();
+        __syncthreads();
+        tcgen05_fence_after();
+        tsum = tmem_base_sh + (((unsigned)(warp & 3) * 32u) << 16) + (unsigned)(warp >> 2) * NACC;
         const unsigned z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
         for (int c0 = 0; c0 < NACC; c0 += 8) tmem_st8(tsum + c0, z);
         tmem_wait_st();
     }
-    // sums += acc (round to nearest); acc = 0, or (last) acc = sums.  16 sums are in flight per TMEM round trip.
+    // sums += acc (round to nearest); acc = 0, or (last) acc = sums
     auto flush = [&](bool last) {
         float* af = &acc[0][0][0][0];
+        if constexpr (C::SUM_SMEM) {
 #pragma unroll
-        for (int c0 = 0; c0 < NACC; c0 += 16) {
-            unsigned sa[8], sb[8];
-            tmem_ld8(tsum + c0, sa);
-            tmem_ld8(tsum + c0 + 8, sb);
-            tmem_wait_ld();
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                sa[e] = __float_as_uint(__uint_as_float(sa[e]) + af[c0 + e]);
-                sb[e] = __float_as_uint(__uint_as_float(sb[e]) + af[c0 + 8 + e]);
+            for (int q = 0; q < NACC / 4; ++q) {
+                float4 v = ssum[q * 32];
+                v.x += af[4 * q]; v.y += af[4 * q + 1]; v.z += af[4 * q + 2]; v.w += af[4 * q + 3];
+                if (last) {
+                    af[4 * q] = v.x; af[4 * q + 1] = v.y; af[4 * q + 2] = v.z; af[4 * q + 3] = v.w;
+                } else {
+                    ssum[q * 32] = v;
+                    af[4 * q] = af[4 * q + 1] = af[4 * q + 2] = af[4 * q + 3] = 0.f;
+                }
             }
-            if (last) {
+        } else {
+            tmem_wait_st();   // the stores of this warp's previous flush (issued FLUSH k-steps ago)
+#pragma unroll
+            for (int c0 = 0; c0 < NACC; c0 += 16) {
+                unsigned sa[8], sb[8];
+                tmem_ld8(tsum + c0, sa);
+                tmem_ld8(tsum + c0 + 8, sb);
+                tmem_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    af[c0 + e] = __uint_as_float(sa[e]);
-                    af[c0 + 8 + e] = __uint_as_float(sb[e]);
+                    sa[e] = __float_as_uint(__uint_as_float(sa[e]) + af[c0 + e]);
+                    sb[e] = __float_as_uint(__uint_as_float(sb[e]) + af[c0 + 8 + e]);
                 }
-            } else {
-                tmem_st8(tsum + c0, sa);
-                tmem_st8(tsum + c0 + 8, sb);
+                if (last) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) af[c0 + e] = 0.f;
+                    for (int e = 0; e < 8; ++e) {
+                        af[c0 + e] = __uint_as_float(sa[e]);
+                        af[c0 + 8 + e] = __uint_as_float(sb[e]);
+                    }
+                } else {
+                    tmem_st8(tsum + c0, sa);
+                    tmem_st8(tsum + c0 + 8, sb);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) af[c0 + e] = 0.f;
+                }
             }
         }
     };
@@ -344,18 +370,16 @@ __global__ void __launch_bounds__(GramH<B>::NW * 32, 1)
                 }
             }
             // the warps flush in turn (two per k-step): the TMEM round trips of one warp hide behind the MMAs of the others
-            if ((ks + 1 + warp) % C::FLUSH == 0 && ks + 1 < nks) {
-                tmem_wait_st();   // the stores of this warp's previous flush (issued FLUSH k-steps ago)
-                flush(false);
-            }
+            if ((ks + 1 + warp) % C::FLUSH == 0 && ks + 1 < nks) flush(false);
         }
         cp_async_wait<0>();
-        tmem_wait_st();
         flush(true);
     }
-    tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base_sh, C::TCOLS);
+    if constexpr (!C::SUM_SMEM) {
+        tcgen05_fence_before();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc(tmem_base_sh, C::TCOLS);
+    }
 #pragma unroll
     for (int b = 0; b < WB; ++b) {
         const int64_t j = jbase + b;
