@@ -334,7 +334,12 @@ int rbl_spmm(rbl_handle* h, int64_t b, const double* q, double* u) {
         du.alloc(up.size());
         RBL_CUDA(cudaMemcpy(dq.p, qp.data(), qp.size() * 8, cudaMemcpyHostToDevice));
         const SpmmCoef cf = (h->opt.op == RBL_OP_SHIFT_MINUS_A) ? SpmmCoef{-1.0, h->opt.sigma, 0.0} : SpmmCoef{1.0, 0.0, 0.0};
-        launch_spmm(B, n, h->wsp->d_rowptr.p, h->wsp->d_colidx.p, h->wsp->d_vals.p, dq.p, du.p, cf, nullptr, h->stream);
+        SpmmWindows wtmp = h->spmm_wt;
+        size_t wsm = 0;
+        if (wtmp.nwin > 0 && spmm_window_supported(B) && spmm_window_stages(wtmp, B, &wsm) > 0)
+            launch_spmm_window(B, n, n, h->wsp->d_rowptr.p, h->wsp->d_rel.p, h->wsp->d_vals.p, dq.p, du.p, cf, nullptr, h->spmm_wt, h->stream);
+        else
+            launch_spmm(B, n, h->wsp->d_rowptr.p, h->wsp->d_colidx.p, h->wsp->d_vals.p, dq.p, du.p, cf, nullptr, h->stream);
         RBL_CUDA(cudaStreamSynchronize(h->stream));
         RBL_CUDA(cudaMemcpy(up.data(), du.p, up.size() * 8, cudaMemcpyDeviceToHost));
         for (int64_t r = 0; r < n; ++r)

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t nrows, const int* __r
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const double2* __restrict__ Q2 = reinterpret_cast<const double2*>(Q);
+    // (Two rows per thread and iteration - more loads in flight per thread - was measured too: 120 us against 96 us.)
     for (int64_t row = warp * RPW + rsel; row < nrows; row += nwarps * RPW) {
         int p = __ldg(rowptr + row);
         const int p1 = __ldg(rowptr + row + 1);

@@ -38,6 +38,29 @@ struct SpmmCoef {
 void launch_spmm(int B, int64_t nrows, const int* rowptr, const int* colidx, const double* vals, const double* Q,
                  double* U, SpmmCoef cf, const double* Z, cudaStream_t st);
 
+// second generation for banded / stencil matrices (spmm.cu): Q and the CSR stream staged in shared memory by TMA bulk copies
+struct SpmmWindows {
+    static constexpr int kMax = 8;         // windows
+    static constexpr int kTileRows = 64;   // rows per tile
+    static constexpr int kMaxStages = 8;   // tiles in flight
+    int nwin = 0;            // 0: no window structure (use launch_spmm)
+    int lo[kMax], hi[kMax];  // offset range col - row of every window
+    int base[kMax];          // first ring row of the window in shared memory (filled by spmm_window_stages)
+    int diag_w = -1;         // window that holds offset 0 (-1: none)
+    int max_tile_nnz = 0;    // most nonzeros in an aligned 64-row tile
+};
+// window table from a sample of the (host) CSR rows; columns >= nown (halo) are never part of a window
+SpmmWindows spmm_plan_windows(int64_t nrows, int64_t nown, const int* rowptr, const int* colidx);
+// number of pipeline stages that fit shared memory for block size B (0: none), ring bases, total bytes
+int spmm_window_stages(SpmmWindows& wt, int B, size_t* smem_bytes_out);
+// rel[p] = (window << 24) | (col - row - lo[window]) or -1 - col for entries outside every window; *irregular += their count
+void launch_spmm_build_rel(int64_t nrows, int64_t nown, const int* rowptr, const int* colidx, const SpmmWindows& wt, int* rel,
+                           unsigned long long* irregular, cudaStream_t st);
+bool spmm_window_supported(int B);
+// rowptr / rel / vals need 8 elements of slack behind their last entry (16-byte rounded bulk copies)
+void launch_spmm_window(int B, int64_t nrows, int64_t nown, const int* rowptr, const int* rel, const double* vals, const double* Q,
+                        double* U, SpmmCoef cf, const double* Z, const SpmmWindows& wt, cudaStream_t st);
+
 // ---- K2/K3/K4 fused row-wise block operations on fp64 blocks --------------------------------------
 // For every row r of Y (n x B, fp64):
 //     y <- y - x1[r,:] * M1 - x2[r,:] * M2        (either may be absent; M row-major B x B, device)

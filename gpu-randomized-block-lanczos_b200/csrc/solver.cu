@@ -258,13 +258,35 @@ rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, co
     }
     h->gersh_lo = glo;
     h->gersh_hi = ghi;
-    h->wsp->d_rowptr.ensure((size_t)nloc + 1);
+    h->wsp->d_rowptr.ensure((size_t)nloc + 1 + 8);     // slack: the TMA SpMM copies 16-byte rounded slices
     h->wsp->d_colidx.ensure(std::max<int64_t>(1, nnz));
-    h->wsp->d_vals.ensure(std::max<int64_t>(1, nnz));
+    h->wsp->d_vals.ensure(std::max<int64_t>(1, nnz) + 8);
     RBL_CUDA(cudaMemcpy(h->wsp->d_rowptr.p, rp.data(), ((size_t)nloc + 1) * sizeof(int), cudaMemcpyHostToDevice));
     if (nnz) {
         RBL_CUDA(cudaMemcpy(h->wsp->d_colidx.p, ci.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice));
         RBL_CUDA(cudaMemcpy(h->wsp->d_vals.p, vals, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    // band structure?  then SpMM stages Q through shared-memory rings filled by the TMA engine (spmm.cu)
+    h->spmm_wt = SpmmWindows{};
+    {
+        const char* env = std::getenv("RBL_SPMM_WINDOW");
+        // opt-in (RBL_SPMM_WINDOW=1): correct and at its designed L2 traffic (3Q + A), but instruction-bound - 189 us per
+        // config-2 launch against 96 us for the gather kernel (profiles/r02_ncu_spmm_window.txt)
+        SpmmWindows wt = (env && env[0] == '1') ? spmm_plan_windows(nloc, nloc, rp.data(), ci.data()) : SpmmWindows{};
+        if (wt.nwin > 0) {
+            h->wsp->d_rel.ensure(std::max<int64_t>(1, nnz) + 8);
+            DevBuf<unsigned long long> d_bad;
+            d_bad.alloc(1);
+            RBL_CUDA(cudaMemsetAsync(d_bad.p, 0, 8, h->stream));
+            launch_spmm_build_rel(nloc, nloc, h->wsp->d_rowptr.p, h->wsp->d_colidx.p, wt, h->wsp->d_rel.p, d_bad.p, h->stream);
+            unsigned long long bad = 0;
+            RBL_CUDA(cudaMemcpyAsync(&bad, d_bad.p, 8, cudaMemcpyDeviceToHost, h->stream));
+            RBL_CUDA(cudaStreamSynchronize(h->stream));
+            if ((double)bad <= 0.10 * (double)nnz) h->spmm_wt = wt;
+            if (h->opt.verbose)
+                std::fprintf(stderr, "[rbl] SpMM: %d offset windows, %llu of %lld entries outside them -> %s\n", wt.nwin, bad, (long long)nnz,
+                             h->spmm_wt.nwin ? "TMA-staged window kernel" : "gather kernel");
+        }
     }
     h->t_h2d_create = now_s() - t0;
     return h.release();
@@ -414,6 +436,7 @@ struct Run {
     static constexpr int kSmallMats = 6;
     bool fused = false;
     int fgrid = 1;
+    bool spmm_use_window = false;
     void* slot(int64_t j) { return w.buf.p + (size_t)j * bstride * ssz; }
     // ---- host tier of the Krylov slab (opts.spill; hybrid_part_reorth!, RBL_gpu.jl:59-81,127-130,168-169) ------------
     // slab slots [0, m_dev) live in HBM, slots [m_dev, m_cap) in pinned host memory.  Spilled blocks are written through
@@ -614,7 +637,10 @@ struct Run {
     // U = cf.alpha * A Q + cf.beta * Q + cf.gamma * Z
     void spmm(double* Q, double* Uo, SpmmCoef cf, const double* Z) {
         halo(Q);
-        launch_spmm(B, nloc, w.d_rowptr.p, w.d_colidx.p, w.d_vals.p, Q, Uo, cf, Z, st);
+        if (spmm_use_window)
+            launch_spmm_window(B, nloc, nloc, w.d_rowptr.p, w.d_rel.p, w.d_vals.p, Q, Uo, cf, Z, h->spmm_wt, st);
+        else
+            launch_spmm(B, nloc, w.d_rowptr.p, w.d_colidx.p, w.d_vals.p, Q, Uo, cf, Z, st);
         ++launches;
         ++n_spmm;
         bytes_spmm += 12.0 * (double)h->nnz + 4.0 * (double)(nloc + 1) + 16.0 * (double)nloc * B +
@@ -1260,6 +1286,11 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
         if (opt.verbose) std::fprintf(stderr, "[rbl] host spill tier: %lld blocks in HBM, up to %lld in pinned host memory\n", (long long)m_dev, (long long)(m_cap - m_dev));
     }
     c.rgrid = rowop_grid(B, c.nloc);
+    {
+        SpmmWindows wtmp = h->spmm_wt;
+        size_t wsm = 0;
+        c.spmm_use_window = wtmp.nwin > 0 && spmm_window_supported(B) && spmm_window_stages(wtmp, B, &wsm) > 0;
+    }
     c.fused = fused_rowop_supported(B);
     c.fgrid = c.fused ? fused_rowop_grid(B, c.nloc) : 1;
     const int nX = 3 + (filtering ? 1 : 0);

@@ -105,7 +105,7 @@ struct Workspace {
     PinnedBuf<QrState> hqr;
     // what a handle needs besides the solve buffers: parked with the workspace so that a create / destroy cycle does
     // no cudaFree / cudaStreamDestroy / cudaEventDestroy (measured: sporadic 0.4-1.8 s stalls in rbl_destroy)
-    DevBuf<int> d_rowptr, d_colidx, d_send_rows;
+    DevBuf<int> d_rowptr, d_colidx, d_send_rows, d_rel;   // d_rel: window-relative column encoding of the TMA SpMM
     DevBuf<double> d_vals;
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> event_pool;
@@ -141,6 +141,7 @@ struct rbl_handle {
     std::vector<rbl_handle*> parts;
     std::vector<int64_t> part_rows;       // parts.size()+1 global row offsets
     double gersh_lo = 0.0, gersh_hi = 0.0;  // Gershgorin interval of A (global)
+    rbl::SpmmWindows spmm_wt;              // nwin > 0: the matrix has band structure, SpMM stages Q through shared memory
     rbl::KrylovInfo last;
     rbl::Workspace* wsp = nullptr;   // adopted from / returned to the process-wide cache
     rbl::Workspace& ws_ref() { return *wsp; }

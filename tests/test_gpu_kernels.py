@@ -166,3 +166,31 @@ def _ritz_case(gpu, n, b, m, k, fp32, impl):
     ref = blocks.astype(dt).astype(np.float64).transpose(1, 0, 2).reshape(n, m * b) @ S.astype(dt).astype(np.float64)
     tol = (2e-5 if fp32 else 1e-12) * np.max(np.abs(ref))
     assert np.max(np.abs(V.astype(np.float64) - ref)) < tol
+
+
+@pytest.mark.parametrize("b", [16, 13, 32])
+@pytest.mark.parametrize("case", ["lap3d-30", "lap2d-150", "lap3d-30 shifted", "banded+stray"])
+def test_spmm_tma_window_kernel(gpu, case, b):
+    """K1 second generation (spmm.cu): banded / stencil matrices large enough for the window plan (n >= 4096, B = 16 / 32) go
+    through the TMA-staged shared-memory rings; entries outside every window are gathered from global memory."""
+    kw = {}
+    if case.startswith("lap3d"):
+        A = matrices.laplacian_3d(30).tocsr()
+        if "shifted" in case:
+            kw = dict(op=1, sigma=12.0)
+    elif case == "lap2d-150":
+        A = matrices.laplacian_2d(150).tocsr()
+    else:
+        n = 20000
+        rng = np.random.default_rng(5)
+        A = sp.diags([rng.standard_normal(n - abs(o)) for o in (-700, -3, -1, 0, 1, 3, 700)], (-700, -3, -1, 0, 1, 3, 700), format="lil")
+        for _ in range(300):                      # stray entries far from the bands (plus long rows)
+            i, j = rng.integers(0, n, 2)
+            A[i, j] = rng.standard_normal()
+        A[5, :40] = 1.0
+        A = sp.csr_matrix(A)
+    Q = np.random.default_rng(b).standard_normal((A.shape[0], b))
+    U = gpu.k_spmm(A, Q, **kw)
+    ref = (12.0 * Q - A @ Q) if kw else A @ Q
+    bound = 16 * np.finfo(float).eps * ((abs(A) @ np.abs(Q)) + (12.0 * np.abs(Q) if kw else 0))
+    assert np.all(np.abs(U - ref) <= bound + 1e-300)

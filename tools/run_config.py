@@ -112,6 +112,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("config", type=int, choices=[3, 4, 5])
     ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--pairs-per-row", type=int, default=64, help="config 3: n*this/2 (i,j) draws; triu keeps half -> ~this/2 nnz per row")
     ap.add_argument("--side", type=int, default=4096)
     ap.add_argument("--grid", type=int, default=400)
     ap.add_argument("--k", type=int, default=0)
@@ -130,7 +131,7 @@ def main():
     t_gen = time.perf_counter()
     if a.config == 3:
         k, b = a.k or 50, a.b or 32
-        A = er_sym_fast(a.n, 32, seed=3)
+        A = er_sym_fast(a.n, a.pairs_per_row, seed=3)
         n = A.shape[0]
         out.update(workload=f"configs[2]: symmetric Erdos-Renyi n={n}, nnz={A.nnz}, {k} extreme eigenpairs, b={b}, 1 GPU", n=n, nnz=int(A.nnz))
         opts = B.default_options(max_kryl_sz=a.max_kryl or 100000, precision=prec, restart=1, filter_degree=a.degree if a.degree >= 0 else 9,
