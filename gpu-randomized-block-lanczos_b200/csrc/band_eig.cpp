@@ -960,6 +960,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         wit_.assign(1, x);
         wit_theta_.assign(1, th);
         R.witness_rho = rho;
+        R.witness_theta = th;
         if (verbose > 1)
             std::fprintf(stderr, "[rbl] check N=%lld %s theta=%.12g rho=%.3e (nfac=%d)\n", (long long)N, how, th, rho, wk.nfac);
         return finish(false);

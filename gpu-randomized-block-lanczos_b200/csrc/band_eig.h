@@ -76,6 +76,7 @@ struct TopKResult {
     std::vector<double> resid;  // k residual bounds ||B_i s_last||
     bool have_all = false;      // d/s/resid hold all k pairs (full check ran)
     double witness_rho = -1.0;  // residual bound of the pair that proved non-convergence (stages 1-2), else -1
+    double witness_theta = 0.0; // its Ritz value
     int factorizations = 0;
 };
 

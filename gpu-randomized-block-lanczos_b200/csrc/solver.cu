@@ -384,6 +384,17 @@ struct FilterPlan {
                              : std::cosh(degree * std::acosh(ax)) * ((x < 0 && (degree & 1)) ? -1.0 : 1.0);
         return rho * t;
     }
+    // eigenvalue estimate of op(A) from a Ritz value theta of p(op(A)) (the wanted side of the filter); `side`: +1 wanted
+    // above the damped interval, -1 below, 0 two-sided (odd degree keeps the sign).  Returns false inside the interval.
+    bool invert(double theta, int side, double* lam) const {
+        if (degree == 0) { *lam = theta; return true; }
+        const double y = theta / rho, ay = std::fabs(y);
+        if (!(ay > 1.0)) return false;
+        const double x = std::cosh(std::acosh(ay) / degree);
+        const double sgn = side != 0 ? (double)side : (y < 0 ? -1.0 : 1.0);
+        *lam = c() + e() * sgn * x;
+        return true;
+    }
 };
 
 struct CycleOut {
@@ -965,6 +976,29 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
     int64_t pending_i = 0;
     bool check_in_flight = false;
     std::string root_error;
+    // Adaptive check cadence.  The reference tests convergence every check_period-th step (RBL_gpu.jl:186); most of those
+    // checks happen while the slowest wanted pair is orders of magnitude away from the tolerance.  From the residual
+    // bound rho of the witness pair at two consecutive checks the root estimates its decay per step and postpones the
+    // next check by at most HALF the steps that witness still needs (and at most 8 periods): the witness cannot have
+    // converged by then, so no accepting check is skipped unless the convergence rate more than doubles.  The
+    // acceptance rule itself is unchanged.  RBL_CHECK_ADAPTIVE=0 restores a check at every period.
+    static const bool adaptive_checks = [] { const char* e = std::getenv("RBL_CHECK_ADAPTIVE"); return !(e && e[0] == '0'); }();
+    double w_rho = -1.0, w_theta = 0.0;
+    int64_t w_it = 0, next_check_i = 0;
+    auto extra_periods = [&](const TopKResult& r, int64_t it) -> int {
+        int extra = 0;
+        if (adaptive_checks && r.witness_rho > 0 && w_rho > 0 && it > w_it && r.witness_rho < w_rho &&
+            std::fabs(r.witness_theta - w_theta) <= 1e-6 * std::max(std::fabs(w_theta), 1e-300)) {
+            const double rate = std::log(w_rho / r.witness_rho) / (double)(it - w_it);      // decay of log(rho) per step
+            if (rate > 0 && r.witness_rho > opt.tol) {
+                const double steps_left = std::log(r.witness_rho / opt.tol) / rate;
+                extra = (int)std::floor(0.5 * steps_left / check_period) - 1;
+                extra = std::max(0, std::min(extra, 7));
+            }
+        }
+        w_rho = r.witness_rho; w_theta = r.witness_theta; w_it = it;
+        return extra;
+    };
     // waits for the in-flight check; true when it accepted.  Row-sharded runs: only rank 0 evaluates the host
     // check; the decision code (and, on acceptance, D, S and the bounds) is summed over ranks with every other
     // rank contributing zeros, so all ranks follow the same control flow and use the same Ritz basis; a failure
@@ -981,7 +1015,7 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
                 while (pending.wait_for(std::chrono::microseconds(200)) != std::future_status::ready)
                     if (idle_from < 0 && cudaEventQuery(tail_event) == cudaSuccess) idle_from = now_s();
                 r = pending.get();
-                code = r.converged ? 1 : 0;
+                code = r.converged ? 1 : 4 * extra_periods(r, pending_i);   // 0 / 1 / 2 in the low bits, postponement above
             } catch (const std::exception& e) {
                 root_error = e.what();
                 code = 2;
@@ -993,6 +1027,9 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         }
         ++checks;
         code = agree(code);
+        const int extra = code / 4;
+        code %= 4;
+        next_check_i = pending_i + (int64_t)(1 + extra) * check_period;
         if (code >= 2) throw Error(RBL_BREAKDOWN, "rbl_solve: host eigen-check failed: " + (root_error.empty() ? std::string("(on rank 0)") : root_error));
         if (code == 1) {
             converged = true;
@@ -1026,6 +1063,7 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         if (!probe && i * b > k_rem && i % check_period == 0) {                 // :186
             RBL_CUDA(cudaEventRecord(tail_event, st));
             if (harvest()) break;
+            if (i < next_check_i) continue;      // postponed (adaptive cadence): no check at this step
             mark_event(i);
             pending_i = i;
             check_in_flight = true;
@@ -1233,6 +1271,8 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
     // checks fall on reorth steps and the refresh of slot(i-2) stays behind them (reorth_period >= 2)
     c.async_ok = opt.async_check && c.reorth_period >= 2 && (c.check_period % c.reorth_period == 0);
     int fdeg = opt.filter_degree < 0 ? 8 : opt.filter_degree;
+    int filt_side = 0;          // +1 / -1: wanted pairs above / below the damped interval; 0: both ends
+    double filt_norm = 0.0;     // |lambda_1| estimate: the filter is scaled so that p(lambda_k) ~ ||op(A)||
     const bool filtering = fdeg > 0;
     const bool extra = filtering || opt.restart;
     c.base = (opt.op == RBL_OP_SHIFT_MINUS_A) ? SpmmCoef{-1.0, opt.sigma, 0.0} : SpmmCoef{1.0, 0.0, 0.0};
@@ -1389,6 +1429,8 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
         const double xk = std::fabs((r.d[kq - 1] - f.c()) / f.e());
         f.rho = (tk > 0 && xk > 1.0) ? std::fabs(r.d[0]) / tk : 1.0;
         c.flt = f;
+        filt_side = allpos ? 1 : (allneg ? -1 : 0);
+        filt_norm = std::fabs(r.d[0]);
         stats.filter_cut = cut;
         stats.filter_degree = f.degree;
         stats.filter_two_sided = f.two_sided ? 1 : 0;
@@ -1428,6 +1470,30 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
         for (int64_t j = 0; j < have; ++j) {
             if (j < k_rem && r.resid[j] <= opt.tol) lock.push_back(j);
             else if ((int64_t)rest.size() < b) rest.push_back(j);
+        }
+        if (filtering && have > 0) {
+            // Re-place the filter: this cycle's Ritz values, mapped back through p, estimate the wanted eigenvalues far
+            // better than the short probe did; a tighter damped interval separates the wanted end more per degree.
+            double lam_last = 0.0, lam_k = 0.0;
+            const int64_t kq = std::min<int64_t>(k_rem, have);
+            if (c.flt.invert(r.d[have - 1], filt_side, &lam_last) && c.flt.invert(r.d[kq - 1], filt_side, &lam_k)) {
+                FilterPlan f = c.flt;
+                const double cut_old = f.two_sided ? f.b : (filt_side > 0 ? f.b : -f.a);
+                const double cut_new = std::fabs(lam_last);
+                if (cut_new > cut_old) {
+                    if (f.two_sided) { f.a = -cut_new; f.b = cut_new; }
+                    else if (filt_side > 0) f.b = cut_new;
+                    else f.a = -cut_new;
+                    f.rho = 1.0;
+                    const double tk = std::fabs(f.eval(lam_k));
+                    const double xk = std::fabs((lam_k - f.c()) / f.e());
+                    f.rho = (tk > 0 && xk > 1.0) ? filt_norm / tk : 1.0;
+                    if (opt.verbose)
+                        std::fprintf(stderr, "[rbl] filter re-placed: damped [%.8g, %.8g] (cut %.8g -> %.8g), rho %.3e\n", f.a, f.b, cut_old, cut_new, f.rho);
+                    c.flt = f;
+                    stats.filter_cut = cut_new;
+                }
+            }
         }
         {   // is there room for another cycle once these are locked?  If not: best effort from this cycle, as at the cap
             const int64_t nlb_next = (nlock + (int64_t)lock.size() + b - 1) / b;

@@ -60,6 +60,18 @@ class ChebFilter:
                        np.cosh(self.degree * np.arccosh(np.maximum(ax, 1.0))) * np.where((x < 0) & (self.degree % 2 == 1), -1.0, 1.0))
         return self.rho * out
 
+    def invert(self, theta, side):
+        """Eigenvalue estimate of A from a Ritz value theta of p(A) on the wanted side (side: +1 above the damped
+        interval, -1 below, 0 two-sided); None inside the interval."""
+        if self.degree == 0:
+            return float(theta)
+        y = theta / self.rho
+        if not abs(y) > 1.0:
+            return None
+        x = np.cosh(np.arccosh(abs(y)) / self.degree)
+        sgn = float(side) if side != 0 else (-1.0 if y < 0 else 1.0)
+        return float(self.c + self.e * sgn * x)
+
     def apply(self, A, Q):
         """p(A) Q by the three-term recurrence t_{j+1} = 2 (A - c)/e t_j - t_{j-1}; rho folded into the last step."""
         if self.degree == 0:
@@ -206,6 +218,7 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
     st = RestartStats()
     Q1 = np.linalg.qr(np.asarray(A @ np.asarray(Omega, dtype=DOUBLE), dtype=DOUBLE))[0]      # RBL.jl:137
     flt = ChebFilter(degree=0)
+    side, norm_a = 0, 0.0
     if filter_degree != 0:
         d = filter_degree if filter_degree > 0 else 8
         kk = k + b
@@ -216,6 +229,8 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
         st.probe_steps = pr.iterations
         glo, ghi = gershgorin(A)
         flt = place_filter(pr.D, min(k, len(pr.D)), len(pr.D), d, glo, ghi)
+        side = 0 if flt.two_sided else (1 if pr.D[0] > 0 else -1)
+        norm_a = abs(pr.D[0])
         st.operator_applications += pr.iterations
     st.filter = flt
     Y = np.zeros((n, 0))
@@ -238,6 +253,26 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
             final = res
             st.converged = res.converged
             break
+        if flt.degree > 0 and len(res.D) > 0:
+            # re-place the filter from this cycle's Ritz values mapped back through p (tighter damped interval)
+            kq = min(k_rem, len(res.D))
+            lam_last, lam_k = flt.invert(res.D[-1], side), flt.invert(res.D[kq - 1], side)
+            if lam_last is not None and lam_k is not None:
+                cut_old = flt.b if (flt.two_sided or side > 0) else -flt.a
+                cut_new = abs(lam_last)
+                if cut_new > cut_old:
+                    f2 = ChebFilter(degree=flt.degree, a=flt.a, b=flt.b, rho=1.0, two_sided=flt.two_sided)
+                    if f2.two_sided:
+                        f2.a, f2.b = -cut_new, cut_new
+                    elif side > 0:
+                        f2.b = cut_new
+                    else:
+                        f2.a = -cut_new
+                    tk = abs(float(f2.scalar(lam_k)))
+                    xk = abs((lam_k - f2.c) / f2.e)
+                    f2.rho = norm_a / tk if tk > 0 and xk > 1.0 else 1.0
+                    flt = f2
+                    st.filter = flt
         # lock every wanted pair whose bound passed (restarted.jl:122-131), restart from the best b others (:133-135)
         nb = res.iterations
         Qm = np.hstack(res.Q[:nb])
