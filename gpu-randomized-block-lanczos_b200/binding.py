@@ -94,9 +94,11 @@ SIGNATURES = {
     "rbl_partition_rows": (C.c_int, [C.c_int64, C.c_int, _P64]),
     "rbl_halo_plan": (C.c_int, [C.c_int64, C.c_int, _P64, C.c_int, C.c_int64, C.c_int64, _P64, _P64, _P64, _P64, _P64,
                                 _P32]),
+    "rbl_spmm_schedule": (C.c_int, [C.c_int64, C.c_int64, _P32, _P32, C.c_int, _P64, _P32, _P64]),
     "rbl_matrix_market_read": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p), _P64, _P64]),
     "rbl_matrix_arrays": (C.c_int, [C.c_void_p, C.POINTER(_P64), C.POINTER(_P64), C.POINTER(_PD)]),
     "rbl_matrix_free": (C.c_int, [C.c_void_p]),
+    "rbl_spmm_bench": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _PD, _P64]),
     "rbl_microbench": (C.c_int, [C.c_int, C.c_int64, C.c_int, _PD]),
 }
 
@@ -385,6 +387,24 @@ def halo_plan(n: int, world: int, row_starts, rank: int, rowptr, colidx):
     _check(lib().rbl_halo_plan(n, world, _p64(rs), rank, nloc, nnz, _p64(rp), _p64(ci), C.byref(nh), _p64(halo),
                                _p64(optr), loc.ctypes.data_as(_P32)))
     return halo, optr, loc
+
+
+def spmm_schedule(rowptr, colidx, nown=None, slots: int = 0):
+    """Row schedule of the patch-scheduled SpMM for 0-based CSR arrays: (order, info) or (None, None) when the matrix has
+    no stencil structure.  info: dims, stride1, stride2, ext0..2, patch0..2, slots, npatch, halo0."""
+    rp = np.ascontiguousarray(rowptr, dtype=np.int32)
+    ci = np.ascontiguousarray(colidx, dtype=np.int32)
+    n = len(rp) - 1
+    cnt = C.c_int64()
+    args = (n, n if nown is None else nown, rp.ctypes.data_as(_P32), ci.ctypes.data_as(_P32), slots)
+    _check(lib().rbl_spmm_schedule(*args, C.byref(cnt), None, None))
+    if cnt.value == 0:
+        return None, None
+    order = np.zeros(cnt.value, dtype=np.int32)
+    info = np.zeros(12, dtype=np.int64)
+    _check(lib().rbl_spmm_schedule(*args, C.byref(cnt), order.ctypes.data_as(_P32), _p64(info)))
+    keys = ("dims", "stride1", "stride2", "ext0", "ext1", "ext2", "patch0", "patch1", "patch2", "slots", "npatch", "halo0")
+    return order, dict(zip(keys, (int(v) for v in info)))
 
 
 def microbench(which: int, size: int = 1 << 30, iters: int = 10) -> float:

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "librbl_b200.so")
-SOURCES = ["kernels.cu", "rowops.cu", "spmm.cu", "reorth_tc16.cu", "reorth_f64.cu", "microbench.cu", "solver.cu", "capi.cu",
+SOURCES = ["kernels.cu", "rowops.cu", "spmm.cu", "spmm_sched.cu", "spmm_lab.cu", "reorth_tc16.cu", "reorth_f64.cu", "microbench.cu", "solver.cu", "capi.cu",
            "band_eig.cpp", "comm.cpp", "partition.cpp", "mmio.cpp"]
 SOURCES = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 HEADERS = [f for f in os.listdir(CSRC) if f.endswith(".h")] + [os.path.join("..", "..", "include", "rbl_b200.h")]

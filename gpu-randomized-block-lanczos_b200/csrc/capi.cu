@@ -660,6 +660,24 @@ int rbl_halo_plan(int64_t n, int world, const int64_t* row_starts, int rank, int
     });
 }
 
+int rbl_spmm_schedule(int64_t nrows, int64_t nown, const int32_t* rowptr, const int32_t* colidx, int slots,
+                      int64_t* entries_out, int32_t* order_out, int64_t* info_out) {
+    return guarded([&] {
+        if (!rowptr || !colidx || !entries_out || nrows < 0) throw Error(RBL_INVALID, "rbl_spmm_schedule: bad arguments");
+        std::vector<int> order;
+        SpmmSchedule sc;
+        const bool ok = spmm_plan_schedule(nrows, nown, rowptr, colidx, slots > 0 ? slots : spmm_sched_default_slots(16), order, &sc);
+        *entries_out = ok ? (int64_t)order.size() : 0;
+        if (ok && order_out) std::memcpy(order_out, order.data(), order.size() * sizeof(int));
+        if (ok && info_out) {
+            const int64_t v[12] = {sc.dims, sc.stride[1], sc.stride[2], sc.ext[0], sc.ext[1], sc.ext[2],
+                                   sc.patch[0], sc.patch[1], sc.patch[2], sc.slots, sc.npatch, sc.halo[0]};
+            std::memcpy(info_out, v, sizeof(v));
+        }
+        return (int)RBL_OK;
+    });
+}
+
 // ---- Matrix Market loader (benchmark.jl:21,28 mmread) ---------------------------------------------------------------
 struct rbl_matrix {
     MmMatrix m;
@@ -686,6 +704,20 @@ int rbl_matrix_arrays(rbl_matrix* m, const int64_t** colptr, const int64_t** row
 int rbl_matrix_free(rbl_matrix* m) {
     delete m;
     return RBL_OK;
+}
+
+int rbl_spmm_bench(rbl_handle* h, int64_t b, int variant, int grid_mult, int iters, int flush, int with_z, double* us_out,
+                   int64_t* mismatch_out) {
+    return guarded([&] {
+        if (!h || !us_out || iters < 1) throw Error(RBL_INVALID, "rbl_spmm_bench: bad arguments");
+        if (h->world != 1 || !h->parts.empty()) throw Error(RBL_INVALID, "rbl_spmm_bench: single-GPU handles only");
+        RBL_CUDA(cudaSetDevice(h->device));
+        unsigned long long bad = 0;
+        *us_out = spmm_lab_run(h, (int)b, variant, grid_mult, iters, flush, with_z, &bad);
+        if (mismatch_out) *mismatch_out = (int64_t)bad;
+        if (*us_out < 0) throw Error(RBL_INVALID, "rbl_spmm_bench: variant not available for this matrix / block size");
+        return (int)RBL_OK;
+    });
 }
 
 int rbl_microbench(int which, int64_t size, int iters, double* result_out) {

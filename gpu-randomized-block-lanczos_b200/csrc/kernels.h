@@ -61,6 +61,25 @@ bool spmm_window_supported(int B);
 void launch_spmm_window(int B, int64_t nrows, int64_t nown, const int* rowptr, const int* rel, const double* vals, const double* Q,
                         double* U, SpmmCoef cf, const double* Z, const SpmmWindows& wt, cudaStream_t st);
 
+// row schedule for stencil / banded matrices (spmm_sched.cu; used by the SpMM laboratory only): rows grouped into compact
+// patches of the grid the stencil offsets imply
+struct SpmmSchedule {
+    int dims = 0;                 // 0: no schedule (use launch_spmm)
+    int64_t stride[3] = {1, 0, 0};   // row = x + stride[1] * y + stride[2] * z
+    int64_t ext[3] = {1, 1, 1};      // grid extents
+    int halo[3] = {0, 0, 0};      // stencil reach per dimension
+    int patch[3] = {1, 1, 1};     // patch shape (points)
+    int slots = 0;                // schedule entries per patch (>= patch volume, padded with -1)
+    int64_t npatch = 0;
+    double fetch_model = 0.0;     // modelled rows of Q crossing L2->SM per row (x padding penalty)
+};
+}  // namespace rbl
+#include <vector>
+namespace rbl {
+bool spmm_plan_schedule(int64_t nrows, int64_t nown, const int* rowptr, const int* colidx, int slots, std::vector<int>& order,
+                        SpmmSchedule* info);
+int spmm_sched_default_slots(int B);
+
 // ---- K2/K3/K4 fused row-wise block operations on fp64 blocks --------------------------------------
 // For every row r of Y (n x B, fp64):
 //     y <- y - x1[r,:] * M1 - x2[r,:] * M2        (either may be absent; M row-major B x B, device)

@@ -288,6 +288,26 @@ rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, co
                              h->spmm_wt.nwin ? "TMA-staged window kernel" : "gather kernel");
         }
     }
+    // stencil structure?  the SpMM laboratory can visit the rows patch by patch of the implied grid (spmm_sched.cu)
+    h->spmm_sched = SpmmSchedule{};
+    {
+        const char* env = std::getenv("RBL_SPMM_SCHED");      // laboratory only (tools/spmm_lab.py sets it)
+        if (env && env[0] == '1' && h->spmm_wt.nwin == 0) {
+            std::vector<int> order;
+            SpmmSchedule sc;
+            // the schedule does not depend on the block size except through the patch volume: one for all B
+            if (spmm_plan_schedule(nloc, nloc, rp.data(), ci.data(), spmm_sched_default_slots(16), order, &sc)) {
+                h->wsp->d_order.ensure(order.size());
+                RBL_CUDA(cudaMemcpy(h->wsp->d_order.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+                h->spmm_sched = sc;
+            }
+            if (h->opt.verbose)
+                std::fprintf(stderr, "[rbl] SpMM: %s (grid %lld x %lld x %lld, strides 1/%lld/%lld, patch %d x %d x %d in %d slots, %lld patches, model %.2f Q rows per row)\n",
+                             h->spmm_sched.dims ? "row schedule planned (laboratory)" : "no stencil structure",
+                             (long long)sc.ext[0], (long long)sc.ext[1], (long long)sc.ext[2], (long long)sc.stride[1], (long long)sc.stride[2],
+                             sc.patch[0], sc.patch[1], sc.patch[2], sc.slots, (long long)sc.npatch, sc.fetch_model);
+        }
+    }
     h->t_h2d_create = now_s() - t0;
     return h.release();
 }

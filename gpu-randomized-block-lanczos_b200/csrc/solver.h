@@ -106,6 +106,7 @@ struct Workspace {
     // what a handle needs besides the solve buffers: parked with the workspace so that a create / destroy cycle does
     // no cudaFree / cudaStreamDestroy / cudaEventDestroy (measured: sporadic 0.4-1.8 s stalls in rbl_destroy)
     DevBuf<int> d_rowptr, d_colidx, d_send_rows, d_rel;   // d_rel: window-relative column encoding of the TMA SpMM
+    DevBuf<int> d_order;                  // patch-ordered row schedule of the SpMM (spmm_sched.cu)
     DevBuf<double> d_vals;
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> event_pool;
@@ -141,6 +142,7 @@ struct rbl_handle {
     std::vector<rbl_handle*> parts;
     std::vector<int64_t> part_rows;       // parts.size()+1 global row offsets
     double gersh_lo = 0.0, gersh_hi = 0.0;  // Gershgorin interval of A (global)
+    rbl::SpmmSchedule spmm_sched;          // dims > 0: patch-scheduled gather SpMM (default for stencil matrices)
     rbl::SpmmWindows spmm_wt;              // nwin > 0: the matrix has band structure, SpMM stages Q through shared memory
     rbl::KrylovInfo last;
     rbl::Workspace* wsp = nullptr;   // adopted from / returned to the process-wide cache
@@ -186,5 +188,8 @@ MemPlan plan_memory(rbl_handle* h, int64_t k, int b, int64_t m_req);
 void krylov_block(rbl_handle* h, int64_t j, double* out_colmajor);
 void orthogonality(rbl_handle* h, double* max_abs, double* fro);
 void default_options(rbl_options* o);
+
+// spmm_lab.cu
+double spmm_lab_run(rbl_handle* h, int b, int variant, int grid_mult, int iters, int flush, int with_z, unsigned long long* mismatch_out);
 
 }  // namespace rbl

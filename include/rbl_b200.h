@@ -267,6 +267,14 @@ int rbl_halo_plan(int64_t n, int world, const int64_t* row_starts, int rank, int
                   const int64_t* rowptr, const int64_t* colidx_global, int64_t* n_halo_out, int64_t* halo_cols_out,
                   int64_t* halo_owner_ptr_out, int32_t* colidx_local_out);
 
+/* Row schedule of the patch-scheduled SpMM (host only; new - the reference leaves the SpMM to cuSPARSE, RBL_gpu.jl:152).
+ * From 0-based int32 CSR arrays of the local rows (columns >= nown are halo columns) it detects the grid a stencil matrix
+ * lives on and returns the rows patch by patch: `slots` entries per patch, -1 = padding.  Two-call protocol: with
+ * order_out NULL it returns the number of entries (0: no stencil structure, the plain gather kernel is used).
+ *   info_out[12]: dims, stride1, stride2, ext0, ext1, ext2, patch0, patch1, patch2, slots, npatch, halo0 */
+int rbl_spmm_schedule(int64_t nrows, int64_t nown, const int32_t* rowptr, const int32_t* colidx, int slots,
+                      int64_t* entries_out, int32_t* order_out, int64_t* info_out);
+
 /* Matrix Market loader (host only) - what `mmread` gives the reference's benchmark driver (benchmark.jl:3,21,28): reads a
  * square `coordinate` file (real / integer / pattern; general / symmetric / skew-symmetric) into the CSC arrays rbl_create
  * takes (full matrix, symmetric storage expanded, duplicates summed, row indices sorted, index_base 0 or 1).
@@ -277,6 +285,10 @@ int rbl_matrix_arrays(rbl_matrix* m, const int64_t** colptr, const int64_t** row
 int rbl_matrix_free(rbl_matrix* m);
 
 /* Micro-benchmarks used by bench.py / profiles (device): achieved copy GB/s and pipe rates. */
+/* K1 laboratory (spmm_lab.cu): mean launch time in microseconds of SpMM variant `variant` on the handle's matrix, Q resident,
+ * L2 flushed before every launch when flush != 0; *mismatch_out = elements that differ from the default kernel's result. */
+int rbl_spmm_bench(rbl_handle* h, int64_t b, int variant, int grid_mult, int iters, int flush, int with_z, double* us_out,
+                   int64_t* mismatch_out);
 int rbl_microbench(int which, int64_t size, int iters, double* result_out);
 
 #ifdef __cplusplus

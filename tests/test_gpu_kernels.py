@@ -168,11 +168,7 @@ def _ritz_case(gpu, n, b, m, k, fp32, impl):
     assert np.max(np.abs(V.astype(np.float64) - ref)) < tol
 
 
-@pytest.mark.parametrize("b", [16, 13, 32])
-@pytest.mark.parametrize("case", ["lap3d-30", "lap2d-150", "lap3d-30 shifted", "banded+stray"])
-def test_spmm_tma_window_kernel(gpu, case, b):
-    """K1 second generation (spmm.cu): banded / stencil matrices large enough for the window plan (n >= 4096, B = 16 / 32) go
-    through the TMA-staged shared-memory rings; entries outside every window are gathered from global memory."""
+def _spmm_case(case):
     kw = {}
     if case.startswith("lap3d"):
         A = matrices.laplacian_3d(30).tocsr()
@@ -180,6 +176,8 @@ def test_spmm_tma_window_kernel(gpu, case, b):
             kw = dict(op=1, sigma=12.0)
     elif case == "lap2d-150":
         A = matrices.laplacian_2d(150).tocsr()
+    elif case == "image-140":
+        A = matrices.image_graph_laplacian(140, 140, seed=1).tocsr()
     else:
         n = 20000
         rng = np.random.default_rng(5)
@@ -189,8 +187,39 @@ def test_spmm_tma_window_kernel(gpu, case, b):
             A[i, j] = rng.standard_normal()
         A[5, :40] = 1.0
         A = sp.csr_matrix(A)
+    A.sort_indices()
+    return A, kw
+
+
+@pytest.mark.parametrize("b", [16, 13, 32, 4])
+@pytest.mark.parametrize("case", ["lap3d-30", "lap2d-150", "lap3d-30 shifted", "banded+stray", "image-140"])
+def test_spmm_structured_paths(gpu, case, b, monkeypatch):
+    """K1 on stencil / banded matrices large enough for the structure planners: the gather kernel (default) and the TMA-staged
+    window kernel (spmm.cu, RBL_SPMM_WINDOW=1, B = 16 / 32) against SciPy."""
+    A, kw = _spmm_case(case)
     Q = np.random.default_rng(b).standard_normal((A.shape[0], b))
-    U = gpu.k_spmm(A, Q, **kw)
     ref = (12.0 * Q - A @ Q) if kw else A @ Q
     bound = 16 * np.finfo(float).eps * ((abs(A) @ np.abs(Q)) + (12.0 * np.abs(Q) if kw else 0))
-    assert np.all(np.abs(U - ref) <= bound + 1e-300)
+    for path, env in (("gather", {}), ("window", {"RBL_SPMM_WINDOW": "1"})):
+        monkeypatch.delenv("RBL_SPMM_WINDOW", raising=False)
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        U = gpu.k_spmm(A, Q, **kw)
+        assert np.all(np.abs(U - ref) <= bound + 1e-300), path
+
+
+@pytest.mark.parametrize("case", ["lap3d-30", "image-140"])
+def test_spmm_laboratory_variants_are_bit_identical(gpu, case, monkeypatch):
+    """csrc/spmm_lab.cu: the candidate K1 kernels (software-pipelined CSR, ELL, both also in patch-schedule order) repeat the
+    product kernel's per-row arithmetic: every element equal bit for bit, with and without the Chebyshev Z term."""
+    import ctypes as C
+    from rbl_b200 import binding as B
+    A, _ = _spmm_case(case)
+    monkeypatch.setenv("RBL_SPMM_SCHED", "1")
+    with B.Solver(A, options=B.default_options(precision=B.PRECISION_MIXED)) as s:
+        for with_z in (0, 1):
+            for variant in (0, 1, 1 | 256, 1 | 512, 2, 2 | 256, 16 | 1, 16 | 2, 16 | 2 | 256):
+                us, bad = C.c_double(), C.c_int64(-1)
+                rc = gpu.lib().rbl_spmm_bench(s._h, 16, variant, 16, 1, 0, with_z, C.byref(us), C.byref(bad))
+                assert rc == 0, (variant, gpu.lib().rbl_last_error())
+                assert bad.value == 0 and us.value > 0, (variant, with_z, bad.value)
