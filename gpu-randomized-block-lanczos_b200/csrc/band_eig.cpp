@@ -232,9 +232,22 @@ int64_t band_count_below(const BandSym& T, double x) {
 // ------------------------------------------------------------------------------------------------ helpers
 namespace {
 
+// (four independent AVX2 accumulators: a plain `s += a[i]*b[i]` loop cannot be vectorised without reassociation and ran
+// at one fma per 4 cycles - the k^2/2 dot products of finalize_pairs alone took 40 ms of the accepting check)
 inline double dot(const double* a, const double* b, int64_t n) {
-    double s = 0;
-    for (int64_t i = 0; i < n; ++i) s += a[i] * b[i];
+    __m256d s0 = _mm256_setzero_pd(), s1 = s0, s2 = s0, s3 = s0;
+    int64_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+        s0 = _mm256_fmadd_pd(_mm256_loadu_pd(a + i), _mm256_loadu_pd(b + i), s0);
+        s1 = _mm256_fmadd_pd(_mm256_loadu_pd(a + i + 4), _mm256_loadu_pd(b + i + 4), s1);
+        s2 = _mm256_fmadd_pd(_mm256_loadu_pd(a + i + 8), _mm256_loadu_pd(b + i + 8), s2);
+        s3 = _mm256_fmadd_pd(_mm256_loadu_pd(a + i + 12), _mm256_loadu_pd(b + i + 12), s3);
+    }
+    for (; i + 4 <= n; i += 4) s0 = _mm256_fmadd_pd(_mm256_loadu_pd(a + i), _mm256_loadu_pd(b + i), s0);
+    alignas(32) double t[4];
+    _mm256_store_pd(t, _mm256_add_pd(_mm256_add_pd(s0, s1), _mm256_add_pd(s2, s3)));
+    double s = (t[0] + t[1]) + (t[2] + t[3]);
+    for (; i < n; ++i) s += a[i] * b[i];
     return s;
 }
 inline double nrm2(const double* a, int64_t n) { return std::sqrt(dot(a, a, n)); }
@@ -434,68 +447,176 @@ void extract_cluster(const BandSym& T, Work& wk, double mu, int m, const std::ve
 // independently converged vectors of eigenvalues closer than 1e-3 ||T|| get their eps/gap cross-components
 // removed (like LAPACK dstein's ortol).  *dup is set when a vector of the loose pass vanishes (two inputs were
 // the same eigenvector).
-void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, bool* dup) {
+void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, bool* dup, int threads) {
     const double tn = std::max(T.norm_inf, 1e-300);
     const double ctol = 2e-11 * tn;
+    const auto t_fin0 = std::chrono::steady_clock::now();
     // final pass: neighbouring eigenvalues closer than a few ctol must have orthogonal vectors
     std::sort(out.begin(), out.end(), [](const Pair& a, const Pair& b) { return a.theta < b.theta; });
-    size_t g0 = 0;
-    Work wk2;
-    while (g0 < out.size()) {
+    // clusters are independent of each other: one task per cluster, spread over the host threads (the 100 lowest
+    // eigenvalues of a 3-D Laplacian form ~25 degenerate clusters; one after the other they took 27 ms)
+    struct Cluster { size_t g0, g1; std::vector<Pair> repl; bool dup = false; int nfac = 0; };
+    std::vector<Cluster> cls;
+    for (size_t g0 = 0; g0 < out.size();) {
         size_t g1 = g0 + 1;
         while (g1 < out.size() && out[g1].theta - out[g1 - 1].theta <= 4 * ctol) ++g1;
-        if (g1 - g0 >= 2) {
-            std::vector<std::vector<double>> X;
-            for (size_t j = g0; j < g1; ++j) X.push_back(out[j].v);
-            std::vector<const std::vector<double>*> none;
-            // duplicate detection: a vector that (nearly) vanishes under MGS is regenerated
-            for (size_t j = 0; j < X.size(); ++j) {
-                std::vector<std::vector<double>> head(X.begin(), X.begin() + j + 1);
-                double keep = mgs(head, j, none, T.N);
-                if (keep < 0.5 && dup) {  // seeded mode: two seeds collapsed onto one eigenvector - drop the second
-                    *dup = true;
-                    X.erase(X.begin() + j);
-                    out.erase(out.begin() + g0 + j);
-                    --g1;
-                    --j;
-                    continue;
-                } else if (keep < 0.5) {
-                    double mu_c = 0.5 * (out[g0].theta + out[g1 - 1].theta);
-                    wk2.lu.factor(T, mu_c + 5e-15 * tn);
-                    ++wk2.nfac;
-                    std::vector<const std::vector<double>*> ag;
-                    for (size_t i = 0; i < j; ++i) ag.push_back(&X[i]);
-                    std::vector<std::vector<double>> one(1);
-                    wk2.random_unit(one[0], T.N);
-                    for (int it = 0; it < 4; ++it) {
-                        mgs(one, 0, ag, T.N);
-                        wk2.lu.solve(one[0].data());
-                        scal(one[0].data(), 1.0 / nrm2(one[0].data(), T.N), T.N);
-                    }
+        if (g1 - g0 >= 2) { cls.emplace_back(); cls.back().g0 = g0; cls.back().g1 = g1; }
+        g0 = g1;
+    }
+    auto do_cluster = [&](Cluster& c) {
+        const bool erase_dups = dup != nullptr;
+        std::vector<Pair> loc(out.begin() + c.g0, out.begin() + c.g1);
+        const double mu_c = 0.5 * (loc.front().theta + loc.back().theta);
+        std::vector<std::vector<double>> X;
+        for (auto& p : loc) X.push_back(p.v);
+        std::vector<const std::vector<double>*> none;
+        // duplicate detection: a vector that (nearly) vanishes under MGS is regenerated
+        for (size_t j = 0; j < X.size(); ++j) {
+            std::vector<std::vector<double>> head(X.begin(), X.begin() + j + 1);
+            double keep = mgs(head, j, none, T.N);
+            if (keep < 0.5 && erase_dups) {  // seeded mode: two seeds collapsed onto one eigenvector - drop the second
+                c.dup = true;
+                X.erase(X.begin() + j);
+                loc.erase(loc.begin() + j);
+                --j;
+                continue;
+            } else if (keep < 0.5) {
+                Work wk2;
+                wk2.lu.factor(T, mu_c + 5e-15 * tn);
+                ++c.nfac;
+                std::vector<const std::vector<double>*> ag;
+                for (size_t i = 0; i < j; ++i) ag.push_back(&X[i]);
+                std::vector<std::vector<double>> one(1);
+                wk2.random_unit(one[0], T.N);
+                for (int it = 0; it < 4; ++it) {
                     mgs(one, 0, ag, T.N);
-                    X[j] = one[0];
-                } else {
-                    X[j] = head[j];
+                    wk2.lu.solve(one[0].data());
+                    scal(one[0].data(), 1.0 / nrm2(one[0].data(), T.N), T.N);
                 }
-            }
-            std::vector<double> theta, res;
-            rayleigh_ritz(T, X, theta, res);
-            std::vector<size_t> ord(X.size());
-            for (size_t j = 0; j < ord.size(); ++j) ord[j] = j;
-            std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return theta[a] < theta[b]; });
-            for (size_t j = 0; j < ord.size(); ++j) {
-                out[g0 + j].theta = theta[ord[j]];
-                out[g0 + j].res = res[ord[j]];
-                out[g0 + j].v = X[ord[j]];
+                mgs(one, 0, ag, T.N);
+                X[j] = one[0];
+            } else {
+                X[j] = head[j];
             }
         }
-        g0 = g1;
+        std::vector<double> theta, res;
+        rayleigh_ritz(T, X, theta, res);
+        std::vector<size_t> ord(X.size());
+        for (size_t j = 0; j < ord.size(); ++j) ord[j] = j;
+        std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return theta[a] < theta[b]; });
+        c.repl.resize(X.size());
+        for (size_t j = 0; j < ord.size(); ++j) {
+            c.repl[j].theta = theta[ord[j]];
+            c.repl[j].res = res[ord[j]];
+            c.repl[j].v.swap(X[ord[j]]);
+        }
+    };
+    {
+        std::atomic<size_t> next{0};
+        std::exception_ptr err;
+        std::mutex emu;
+        auto run = [&]() {
+            for (;;) {
+                const size_t ci = next.fetch_add(1);
+                if (ci >= cls.size()) break;
+                try {
+                    do_cluster(cls[ci]);
+                } catch (...) {
+                    std::lock_guard<std::mutex> lk(emu);
+                    if (!err) err = std::current_exception();
+                }
+            }
+        };
+        const int ntc = (int)std::min<size_t>((size_t)std::max(1, threads), cls.size());
+        std::vector<std::thread> th;
+        for (int t = 1; t < ntc; ++t) th.emplace_back(run);
+        run();
+        for (auto& t : th) t.join();
+        if (err) std::rethrow_exception(err);
+    }
+    if (!cls.empty()) {
+        std::vector<Pair> merged;
+        merged.reserve(out.size());
+        size_t pos = 0;
+        int nf_cl = 0;
+        for (auto& c : cls) {
+            for (; pos < c.g0; ++pos) merged.push_back(std::move(out[pos]));
+            for (auto& p : c.repl) merged.push_back(std::move(p));
+            pos = c.g1;
+            if (c.dup && dup) *dup = true;
+            nf_cl += c.nfac;
+        }
+        for (; pos < out.size(); ++pos) merged.push_back(std::move(out[pos]));
+        out.swap(merged);
+        nfac += nf_cl;
     }
     // loose pass (like LAPACK dstein's ortol): independently converged vectors of eigenvalues closer than
     // 1e-3 ||T|| carry a residual/gap component of each other (refined seeds are accepted at residuals up to
-    // 1e-12 ||T||); remove it by Gram-Schmidt in eigenvalue order
+    // 1e-12 ||T||); remove it by Gram-Schmidt in eigenvalue order.
+    // The wanted eigenvalues of the BASELINE Laplacians all lie within that distance of each other, so this is k^2/2
+    // dot + axpy pairs over N-vectors - 60 ms of the accepting check of config 2 when done one after the other.  The
+    // overlaps are tiny, so Gram-Schmidt is applied as threaded sweeps over all vectors at once: G_ij = v_i'v_j (i < j in
+    // the window, all from the same snapshot), v_j <- v_j - sum_i G_ij v_i, normalise; the sweep differs from sequential
+    // Gram-Schmidt at second order in max|G| and is repeated until max|G| <= 1e-14.  Anything unusual (an overlap above
+    // 1e-3, which is what two copies of one eigenvector look like) takes the sequential path below.
     const double otol = 1e-3 * tn;
-    for (size_t j = 1; j < out.size(); ++j) {
+    bool swept = false;
+    const auto t_loose = std::chrono::steady_clock::now();
+    int sweeps = 0;
+    if (threads > 1 && out.size() >= 8) {
+        const size_t m = out.size();
+        const int64_t N = T.N;
+        std::vector<size_t> lo(m, 0);
+        for (size_t j = 1; j < m; ++j) {
+            size_t i = lo[j - 1];
+            while (out[j].theta - out[i].theta > otol) ++i;
+            lo[j] = i;
+        }
+        std::vector<std::vector<double>> G(m), Wn(m);
+        const int nt = (int)std::min<size_t>((size_t)threads, m);
+        auto par = [&](auto&& body) {
+            std::atomic<size_t> next{1};
+            auto run = [&]() {
+                for (;;) {
+                    const size_t j = next.fetch_add(1);
+                    if (j >= m) break;
+                    body(j);
+                }
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) th.emplace_back(run);
+            run();
+            for (auto& t : th) t.join();
+        };
+        swept = true;
+        for (int pass = 0; pass < 4; ++pass) {
+            ++sweeps;
+            std::vector<double> mx(m, 0.0);
+            par([&](size_t j) {
+                G[j].assign(j - lo[j], 0.0);
+                double mj = 0.0;
+                for (size_t i = lo[j]; i < j; ++i) {
+                    const double g = dot(out[i].v.data(), out[j].v.data(), N);
+                    G[j][i - lo[j]] = g;
+                    mj = std::max(mj, std::fabs(g));
+                }
+                mx[j] = mj;
+            });
+            const double maxg = *std::max_element(mx.begin(), mx.end());
+            if (!(maxg <= 1e-3)) { swept = false; break; }      // (also NaN)
+            if (maxg <= 1e-14) break;
+            par([&](size_t j) {
+                if (mx[j] == 0.0) { Wn[j].clear(); return; }
+                Wn[j] = out[j].v;
+                for (size_t i = lo[j]; i < j; ++i) axpy(Wn[j].data(), -G[j][i - lo[j]], out[i].v.data(), N);
+                const double nn = nrm2(Wn[j].data(), N);
+                if (nn > 0) scal(Wn[j].data(), 1.0 / nn, N);
+            });
+            for (size_t j = 1; j < m; ++j)
+                if (!Wn[j].empty()) out[j].v.swap(Wn[j]);
+        }
+    }
+    for (size_t j = 1; j < out.size() && !swept; ++j) {
         bool touched = false;
         for (size_t i = j; i-- > 0;) {
             if (out[j].theta - out[i].theta > otol) break;
@@ -513,7 +634,10 @@ void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, boo
             if (nn > 0) scal(out[j].v.data(), 1.0 / nn, T.N);
         }
     }
-    nfac += wk2.nfac;
+    if (std::getenv("RBL_FINALIZE_TIMING"))
+        std::fprintf(stderr, "[rbl]   finalize_pairs: tight pass %.1f ms, loose pass %.1f ms (%d sweeps, swept %d, %zu pairs)\n",
+                     std::chrono::duration<double>(t_loose - t_fin0).count() * 1e3,
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loose).count() * 1e3, sweeps, (int)swept, out.size());
 }
 
 struct Interval {
@@ -702,7 +826,7 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
 
     {
         int64_t nf2 = 0;
-        finalize_pairs(T, out, nf2, nullptr);
+        finalize_pairs(T, out, nf2, nullptr, threads);
         fac += nf2;
     }
     nfac += fac.load();
@@ -747,6 +871,7 @@ static double seed_min_frac() {
 }
 
 bool BandTopK::refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pairs, int64_t& nfac) {
+    const auto t_ref0 = std::chrono::steady_clock::now();
     const int64_t N = T.N;
     const double tn = std::max(T.norm_inf, 1e-300);
     pairs.assign(k, Pair());
@@ -810,12 +935,17 @@ bool BandTopK::refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pair
     }
     if (rcancel) throw Cancelled{};
     nfac += fac.load();
+    const auto t_ref = std::chrono::steady_clock::now();
     pairs.erase(std::remove_if(pairs.begin(), pairs.end(), [](const Pair& p) { return p.v.empty(); }), pairs.end());
     if ((int64_t)pairs.size() * 4 < k * 3) return false;  // too little survived: slicing from scratch is cheaper
     bool dup = false;
     int64_t nf2 = 0;
-    finalize_pairs(T, pairs, nf2, &dup);  // seeded mode: duplicates are erased, not regenerated
+    finalize_pairs(T, pairs, nf2, &dup, threads);  // seeded mode: duplicates are erased, not regenerated
     nfac += nf2;
+    if (verbose > 1)
+        std::fprintf(stderr, "[rbl]   refine_seeds: inverse iterations %.1f ms (%lld factorisations, %d threads), finalize %.1f ms\n",
+                     std::chrono::duration<double>(t_ref - t_ref0).count() * 1e3, (long long)fac.load(), nt,
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ref).count() * 1e3);
     return (int64_t)pairs.size() * 4 >= k * 3;
 }
 
@@ -962,7 +1092,8 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         R.witness_rho = rho;
         R.witness_theta = th;
         if (verbose > 1)
-            std::fprintf(stderr, "[rbl] check N=%lld %s theta=%.12g rho=%.3e (nfac=%d)\n", (long long)N, how, th, rho, wk.nfac);
+            std::fprintf(stderr, "[rbl] check N=%lld %s theta=%.12g rho=%.3e (nfac=%d, %.2f ms)\n", (long long)N, how, th, rho, wk.nfac,
+                         std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() * 1e3);
         return finish(false);
     };
 
@@ -989,7 +1120,12 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     // The eigenvalue nearest to such an x has rank <= hi+1 <= k on either side of x, so whatever inverse
     // iteration at x converges to is one of the k wanted pairs.  First a target a little inside the wanted
     // set (robust while Ritz values still enter it), then the boundary itself.
-    if (!force_full && bi && k >= 1) {
+    // With FRESH seeds (all k pairs of a T at least 95% of this size, from the tracker or from the last full check) the
+    // refinement of stage 3 costs about what a failed stage 2 costs (and runs on all threads): when the witnesses of stage 1
+    // have converged - which is the situation of the accepting check - go there directly.
+    const bool seeds_fresh = (int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N &&
+                             (double)seeds_[0].v.size() >= 0.95 * (double)N;
+    if (!force_full && bi && k >= 1 && !seeds_fresh) {
         const int64_t margin = std::max<int64_t>(1, std::min<int64_t>(k / 6, k - 1));
         struct Target { int64_t lo, hi; double* x; double* step; };
         Target targets[2] = {{std::max<int64_t>(0, k - 1 - 2 * margin), k - 1 - margin, &xA_, &stepA_},

@@ -456,6 +456,8 @@ struct Run {
     Run(rbl_handle* hh) : h(hh), opt(hh->opt), st(hh->stream), w(hh->ws_ref()) {}
     ~Run() {
         if (tail_event) cudaEventDestroy(tail_event);
+        for (auto e : post_event)
+            if (e) cudaEventDestroy(e);
     }
 
     // small device matrices (B x B each): [G | P] are adjacent so that one reduction / all-reduce covers both
@@ -788,17 +790,47 @@ struct Run {
                       ((j_w1 >= 0 ? 1.0 : 0.0) + (j_w0 >= 0 ? 1.0 : 0.0)) * (double)ssz * (double)nloc * B;
     }
 
-    // decision shared by all ranks: 0 continue, 1 accept, 2 abort (the root's host check failed)
-    int agree(int local_code) {
+    // decision shared by all ranks: 0 continue, 1 accept, 2 abort (the root's host check failed); `step` rides along (the
+    // block step the accepted check belongs to).  Slots [0,4) of the control buffers; the posted form uses [4, 4 + 4*kPostSlots).
+    int agree(int local_code, int64_t* step = nullptr) {
         if (!multi) return local_code;
         DevBuf<double>& d_ctrl = w.ctrl;
         PinnedBuf<double>& h_ctrl = w.h_ctrl;
         h_ctrl.p[0] = is_root ? (double)local_code : 0.0;
-        RBL_CUDA(cudaMemcpyAsync(d_ctrl.p, h_ctrl.p, 8, cudaMemcpyHostToDevice, st));
-        allreduce(d_ctrl.p, 1);
-        RBL_CUDA(cudaMemcpyAsync(h_ctrl.p + 1, d_ctrl.p, 8, cudaMemcpyDeviceToHost, st));
+        h_ctrl.p[1] = (is_root && step) ? (double)*step : 0.0;
+        RBL_CUDA(cudaMemcpyAsync(d_ctrl.p, h_ctrl.p, 16, cudaMemcpyHostToDevice, st));
+        allreduce(d_ctrl.p, 2);
+        RBL_CUDA(cudaMemcpyAsync(h_ctrl.p + 2, d_ctrl.p, 16, cudaMemcpyDeviceToHost, st));
         RBL_CUDA(cudaStreamSynchronize(st));
-        return (int)std::lround(h_ctrl.p[1]);
+        if (step) *step = (int64_t)std::llround(h_ctrl.p[3]);
+        return (int)std::lround(h_ctrl.p[2]);
+    }
+    // The same agreement without draining the stream: posted now (the all-reduce is stream-ordered behind the steps issued
+    // so far), read at the next check point, when it has long completed.
+    static constexpr int kPostSlots = 4;
+    cudaEvent_t post_event[kPostSlots] = {nullptr, nullptr, nullptr, nullptr};
+    int post_next = 0, post_pending = -1;
+    void post_agreement(int local_code, int64_t step) {
+        const int slot = post_next;
+        post_next = (post_next + 1) % kPostSlots;
+        double* hsend = w.h_ctrl.p + 4 + 4 * slot;
+        double* dbuf = w.ctrl.p + 4 + 2 * slot;
+        hsend[0] = is_root ? (double)local_code : 0.0;
+        hsend[1] = is_root ? (double)step : 0.0;
+        RBL_CUDA(cudaMemcpyAsync(dbuf, hsend, 16, cudaMemcpyHostToDevice, st));
+        allreduce(dbuf, 2);
+        RBL_CUDA(cudaMemcpyAsync(hsend + 2, dbuf, 16, cudaMemcpyDeviceToHost, st));
+        if (!post_event[slot]) RBL_CUDA(cudaEventCreateWithFlags(&post_event[slot], cudaEventDisableTiming));
+        RBL_CUDA(cudaEventRecord(post_event[slot], st));
+        post_pending = slot;
+    }
+    int read_agreement(int64_t* step) {
+        const int slot = post_pending;
+        post_pending = -1;
+        RBL_CUDA(cudaEventSynchronize(post_event[slot]));
+        const double* h = w.h_ctrl.p + 4 + 4 * slot;
+        *step = (int64_t)std::llround(h[3]);
+        return (int)std::lround(h[2]);
     }
     // the root's (d, s, resid) of `cols` pairs over Nrows rows of T, made identical on every rank
     void share_result(TopKResult& r, int64_t Nrows, int64_t cols) {
@@ -1008,7 +1040,7 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
     auto extra_periods = [&](const TopKResult& r, int64_t it) -> int {
         int extra = 0;
         if (adaptive_checks && r.witness_rho > 0 && w_rho > 0 && it > w_it && r.witness_rho < w_rho &&
-            std::fabs(r.witness_theta - w_theta) <= 1e-6 * std::max(std::fabs(w_theta), 1e-300)) {
+            std::fabs(r.witness_theta - w_theta) <= 1e-3 * std::max(std::fabs(w_theta), 1e-300)) {   // (the same pair: Ritz values still drift early on)
             const double rate = std::log(w_rho / r.witness_rho) / (double)(it - w_it);      // decay of log(rho) per step
             if (rate > 0 && r.witness_rho > opt.tol) {
                 const double steps_left = std::log(r.witness_rho / opt.tol) / rate;
@@ -1061,6 +1093,110 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         return false;
     };
 
+    // ---- non-blocking form (row-sharded runs, or async_check = 2) ---------------------------------------------------
+    // With several GPUs a block step takes a fraction of a millisecond while a host check takes several: waiting for every
+    // check (harvest) made the device idle for a third of an 8-GPU solve.  Here a check point never waits: the root polls
+    // its worker; while a check is still running no new one is started; the outcome travels to the other ranks through an
+    // agreement POSTED on the stream and read one check period later.  The device runs ahead of the accepting check by
+    // however long that check takes; those speculative steps are discarded exactly like the blocking form's.  The step at
+    // which a solve is accepted can therefore vary by a few check periods from run to run (never earlier than the
+    // blocking form's); every accepted result passed the same test.
+    const bool nb_mode = async_ok && !probe && (multi || opt.async_check >= 2);
+    bool have_accept = false;
+    int64_t accept_i = 0;
+    TopKResult accept_res;
+    auto nb_accept = [&](int64_t step) {
+        converged = true;
+        out.final_i = step;
+        if (is_root) out.res = std::move(accept_res);
+        share_result(out.res, out.final_i * b, k_rem);
+    };
+    // root: collect a finished check / start a new one; returns the code to publish (0 nothing, 1 accepted, 2 failed)
+    auto nb_poll = [&](int64_t it, bool may_start, bool block) -> int {
+        if (!is_root) return 0;
+        if (have_accept) return 1;
+        if (check_in_flight && (block || pending.wait_for(std::chrono::seconds(0)) == std::future_status::ready)) {
+            check_in_flight = false;
+            try {
+                const double t0 = now_s();
+                TopKResult r = pending.get();
+                if (block) { t_blocked += now_s() - t0; t_idle += now_s() - t0; }
+                ++checks;
+                if (r.converged) {
+                    have_accept = true;
+                    accept_i = pending_i;
+                    accept_res = std::move(r);
+                    return 1;
+                }
+                next_check_i = pending_i + (int64_t)(1 + extra_periods(r, pending_i)) * check_period;
+            } catch (const std::exception& e) {
+                root_error = e.what();
+                return 2;
+            }
+        }
+        if (may_start && !check_in_flight && it >= next_check_i) {
+            mark_event(it);
+            pending_i = it;
+            check_in_flight = true;
+            pending = std::async(std::launch::async, [&, it]() { return run_check(it, false, k_rem); });
+        }
+        return 0;
+    };
+    auto nb_fail = [&]() { throw Error(RBL_BREAKDOWN, "rbl_solve: host eigen-check failed: " + (root_error.empty() ? std::string("(on rank 0)") : root_error)); };
+    // check point of step `it`: true when the solve was accepted (by a check of an earlier step)
+    auto nb_checkpoint = [&](int64_t it) -> bool {
+        if (multi && post_pending >= 0) {
+            int64_t step = 0;
+            const int code = read_agreement(&step);
+            if (code >= 2) nb_fail();
+            if (code == 1) { nb_accept(step); return true; }
+        }
+        const int code = nb_poll(it, true, false);
+        if (!multi) {
+            if (code >= 2) nb_fail();
+            if (code == 1) { nb_accept(accept_i); return true; }
+            return false;
+        }
+        post_agreement(code, accept_i);
+        return false;
+    };
+    // the loop ended at the cap without an acceptance seen so far: collect what is still in flight, this time waiting
+    auto nb_drain = [&]() {
+        if (multi && post_pending >= 0) {
+            int64_t step = 0;
+            const int code = read_agreement(&step);
+            if (code >= 2) nb_fail();
+            if (code == 1) { nb_accept(step); return; }
+        }
+        int code = nb_poll(i, false, true);
+        // the check in flight belonged to an earlier step: the last check point of the cycle gets its own check (the waiting
+        // form would have tested it), otherwise a solve that converged just before the cap would be reported as not converged
+        const int64_t last = (i / check_period) * check_period;
+        if (code == 0 && is_root && last > pending_i && last * b > k_rem) {
+            try {
+                mark_event(last);
+                pending_i = last;
+                const double t0 = now_s();
+                TopKResult r = run_check(last, false, k_rem);
+                t_idle += now_s() - t0;
+                ++checks;
+                if (r.converged) {
+                    have_accept = true;
+                    accept_i = last;
+                    accept_res = std::move(r);
+                    code = 1;
+                }
+            } catch (const std::exception& e) {
+                root_error = e.what();
+                code = 2;
+            }
+        }
+        int64_t step = accept_i;
+        code = agree(code, &step);
+        if (code >= 2) nb_fail();
+        if (code == 1) nb_accept(step);
+    };
+
     while (i < max_steps && nlb + i < m_cap) {
         ++i;
         const int64_t m = nlb + i - 2;  // stored blocks the two newest are re-orthogonalised against
@@ -1082,6 +1218,10 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
 
         if (!probe && i * b > k_rem && i % check_period == 0) {                 // :186
             RBL_CUDA(cudaEventRecord(tail_event, st));
+            if (nb_mode) {
+                if (nb_checkpoint(i)) break;
+                continue;
+            }
             if (harvest()) break;
             if (i < next_check_i) continue;      // postponed (adaptive cadence): no check at this step
             mark_event(i);
@@ -1107,7 +1247,10 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         }
     }
     RBL_CUDA(cudaEventRecord(tail_event, st));
-    if (!converged) harvest();
+    if (!converged) {
+        if (nb_mode) nb_drain();
+        else harvest();
+    }
     out.iterations_run = i;
     out.converged = converged;
     RBL_CUDA(cudaStreamSynchronize(st));
@@ -1297,8 +1440,8 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
     const bool extra = filtering || opt.restart;
     c.base = (opt.op == RBL_OP_SHIFT_MINUS_A) ? SpmmCoef{-1.0, opt.sigma, 0.0} : SpmmCoef{1.0, 0.0, 0.0};
     RBL_CUDA(cudaEventCreateWithFlags(&c.tail_event, cudaEventDisableTiming));
-    w.ctrl.ensure(4);
-    w.h_ctrl.ensure(4);
+    w.ctrl.ensure(4 + 2 * Run::kPostSlots);
+    w.h_ctrl.ensure(4 + 4 * Run::kPostSlots);
 
     // ---- memory plan (gpu_buffer_size, RBL_gpu.jl:95-104: how many Krylov blocks fit) ---------------
     MemPlan plan = plan_memory(h, k, b, m_req);

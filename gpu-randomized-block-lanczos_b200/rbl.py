@@ -32,7 +32,7 @@ def RBL_gpu(A, k: int, b: int, *, Omega=None, max_kryl_sz: int = 1200, tol: floa
                               precision=_b.PRECISION_MIXED if precision in ("mixed", "fp32") else _b.PRECISION_FP64,
                               op=_b.OP_SHIFT_MINUS_A if shift is not None else _b.OP_A,
                               sigma=float(shift) if shift is not None else 0.0, device=int(device),
-                              async_check=int(bool(async_check)), host_threads=int(host_threads),
+                              async_check=int(async_check), host_threads=int(host_threads),
                               v_fp32=int(bool(v_fp32)), verbose=int(verbose), ngpus=int(ngpus),
                               filter_degree=int(filter_degree), restart=int(bool(restart)), spill=int(bool(spill)),
                               probe_steps=int(probe_steps), mem_limit_mb=int(mem_limit_mb), seed=int(seed),

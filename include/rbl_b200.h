@@ -55,7 +55,11 @@ typedef struct {
     double sigma;          /* shift for RBL_OP_SHIFT_MINUS_A                                      */
     int32_t device;        /* CUDA device ordinal (-1: current)                                   */
     int32_t async_check;   /* 1: run the host T eigen-check on a worker thread while the device
-                              keeps iterating (results identical to the synchronous order)        */
+                              keeps iterating (results identical to the synchronous order); row-
+                              sharded solves never wait at a check point (a check that is still
+                              running postpones the next one: the accepted step may vary by a few
+                              check periods between runs).  2: that non-waiting form on one GPU too.
+                              0: synchronous, as the reference (RBL_gpu.jl:186-193)               */
     int32_t host_threads;  /* worker threads for the final host eigensolve (0: hardware)          */
     int32_t v_fp32;        /* 1: V_out is float (reference's FLOAT=Float32 build), else double    */
     int32_t verbose;

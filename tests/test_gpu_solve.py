@@ -174,7 +174,8 @@ def test_multi_gpu_group_handle_equals_single_gpu(gpu, case):
         D2, V2, st2 = gpu.RBL_gpu(L, k, b, Omega=Om, shift=sigma, precision=prec, ngpus=ng, return_stats=True, **kw)
         A = matrices.shifted(L, sigma) if sigma is not None else L
         assert st2.converged
-        assert abs(st2.iterations - st1.iterations) <= 4
+        # row-sharded solves never wait at a check point: the accepting check may belong to a slightly later step
+        assert -4 <= st2.iterations - st1.iterations <= 24
         assert np.max(np.abs(D2 - D1) / np.abs(D1)) < 1e-8
         assert V2.shape == (n, k)
         assert np.max(rbl_oracle.ritz_residuals(A, D2, V2)) < 1e-6
@@ -183,6 +184,19 @@ def test_multi_gpu_group_handle_equals_single_gpu(gpu, case):
         sep = np.abs(D1 - D1[-1]) > 1e-6 * np.abs(D1[0])
         if sep.any():
             assert np.min(np.linalg.svd(V1[:, sep].T @ V2, compute_uv=False)) > 1 - 1e-6
+
+
+def test_non_waiting_check_points_accept_the_same_solution(gpu):
+    """async_check=2: a check point never waits for the host; the accepted step is never earlier than the waiting form's and
+    the results agree far below the tolerances."""
+    L = matrices.laplacian_3d(20)
+    Om = np.random.default_rng(2).standard_normal((8000, 16))
+    D1, V1, st1 = gpu.RBL_gpu(L, 20, 16, Omega=Om, shift=12.0, precision="mixed", async_check=1, return_stats=True)
+    D2, V2, st2 = gpu.RBL_gpu(L, 20, 16, Omega=Om, shift=12.0, precision="mixed", async_check=2, return_stats=True)
+    assert st2.converged and st1.iterations <= st2.iterations <= st1.iterations + 40
+    assert st2.iterations % 4 == 0 and st2.iterations_run >= st2.iterations
+    assert np.max(np.abs(D2 - D1) / np.abs(D1)) < 1e-10
+    assert np.max(rbl_oracle.ritz_residuals(matrices.shifted(L, 12.0), D2, V2, norm_a=12.0)) < 1e-6
 
 
 def test_multi_gpu_group_handle_one_based_and_device_rng(gpu):
