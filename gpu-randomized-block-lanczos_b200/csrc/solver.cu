@@ -1100,7 +1100,7 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
     // agreement POSTED on the stream and read one check period later.  The device runs ahead of the accepting check by
     // however long that check takes; those speculative steps are discarded exactly like the blocking form's.  The step at
     // which a solve is accepted can therefore vary by a few check periods from run to run (never earlier than the
-    // blocking form's); every accepted result passed the same test.
+    // blocking form's, at most kMaxAhead + check_period later); every accepted result passed the same test.
     const bool nb_mode = async_ok && !probe && (multi || opt.async_check >= 2);
     bool have_accept = false;
     int64_t accept_i = 0;
@@ -1151,7 +1151,10 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
             if (code >= 2) nb_fail();
             if (code == 1) { nb_accept(step); return true; }
         }
-        const int code = nb_poll(it, true, false);
+        // bounded speculation: a check that started kMaxAhead steps ago is waited for (an accepting full check takes the
+        // time of a hundred 8-GPU steps; running on would only burn slab slots and power on steps that get discarded)
+        constexpr int64_t kMaxAhead = 16;
+        const int code = nb_poll(it, true, check_in_flight && it - pending_i >= kMaxAhead);
         if (!multi) {
             if (code >= 2) nb_fail();
             if (code == 1) { nb_accept(accept_i); return true; }
