@@ -410,10 +410,33 @@ struct FilterPlan {
         if (degree == 0) { *lam = theta; return true; }
         const double y = theta / rho, ay = std::fabs(y);
         if (!(ay > 1.0)) return false;
+        if (side > 0 && y < 0) return false;                            // a Ritz value of the other side (not yet converged)
+        if (side < 0 && ((y < 0) != ((degree & 1) == 1))) return false;
         const double x = std::cosh(std::acosh(ay) / degree);
         const double sgn = side != 0 ? (double)side : (y < 0 ? -1.0 : 1.0);
         *lam = c() + e() * sgn * x;
         return true;
+    }
+    // Largest degree <= `want` for which p(lam1) / p(edge of the damped interval) stays below kMaxDynamicRange (lam1: the
+    // eigenvalue of largest magnitude).  A one-sided Chebyshev filter of high degree over a WIDE wanted interval makes
+    // ||p(A)|| exceed the last wanted Ritz value by many orders of magnitude; those Ritz values are then computed with an
+    // absolute error relative to ||p(A)|| and the absolute tolerance of check_convergence (common.jl:56-65) loses its
+    // meaning.  A wide wanted interval does not need a high degree.  (oracle: cap_degree)
+    static constexpr double kMaxDynamicRange = 1e3;
+    int cap_degree(double lam1, int want) const {
+        const double x1 = e() > 0 ? std::fabs((lam1 - c()) / e()) : 1.0;
+        int d = want;
+        if (x1 > 1.0) d = std::min(d, (int)std::floor(std::acosh(kMaxDynamicRange) / std::acosh(x1)));
+        d = std::max(d, 2);
+        if (two_sided && !(d & 1)) ++d;
+        return d;
+    }
+    // rho such that p(lam_k) = norm (the Ritz value of the last wanted pair gets the magnitude of ||op(A)||)
+    void scale_to(double lam_k, double norm) {
+        rho = 1.0;
+        const double tk = std::fabs(eval(lam_k));
+        const double xk = std::fabs((lam_k - c()) / e());
+        rho = (tk > 0 && xk > 1.0) ? norm / tk : 1.0;
     }
 };
 
@@ -1439,6 +1462,8 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
     int fdeg = opt.filter_degree < 0 ? 8 : opt.filter_degree;
     int filt_side = 0;          // +1 / -1: wanted pairs above / below the damped interval; 0: both ends
     double filt_norm = 0.0;     // |lambda_1| estimate: the filter is scaled so that p(lambda_k) ~ ||op(A)||
+    double filt_lam1 = 0.0;     // lambda_1 estimate (signed)
+    bool filt_settled = false;  // the cut has stopped moving: cycles get the whole buffer
     const bool filtering = fdeg > 0;
     const bool extra = filtering || opt.restart;
     c.base = (opt.op == RBL_OP_SHIFT_MINUS_A) ? SpmmCoef{-1.0, opt.sigma, 0.0} : SpmmCoef{1.0, 0.0, 0.0};
@@ -1590,13 +1615,12 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
         else if (allneg) { f.a = -cut; f.b = s_hi > -cut ? s_hi : -cut + std::fabs(cut); }
         else { f.two_sided = true; f.a = -cut; f.b = cut; if (!(f.degree & 1)) ++f.degree; }
         if (!(f.e() > 0)) throw Error(RBL_BREAKDOWN, "rbl_solve: filter probe found a degenerate spectrum interval");
-        f.rho = 1.0;
-        const double tk = std::fabs(f.eval(r.d[kq - 1]));
-        const double xk = std::fabs((r.d[kq - 1] - f.c()) / f.e());
-        f.rho = (tk > 0 && xk > 1.0) ? std::fabs(r.d[0]) / tk : 1.0;
+        f.degree = f.cap_degree(r.d[0], f.degree);
+        f.scale_to(r.d[kq - 1], std::fabs(r.d[0]));
         c.flt = f;
         filt_side = allpos ? 1 : (allneg ? -1 : 0);
         filt_norm = std::fabs(r.d[0]);
+        filt_lam1 = r.d[0];
         stats.filter_cut = cut;
         stats.filter_degree = f.degree;
         stats.filter_two_sided = f.two_sided ? 1 : 0;
@@ -1623,7 +1647,9 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
         ++cycles;
         const int64_t k_rem = k - nlock;
         const int64_t kk_end = opt.restart ? k_rem + b : k_rem;
-        const int64_t max_steps = std::max<int64_t>(1, (c.kryl_sz + b - 1) / b - nlb);
+        int64_t max_steps = std::max<int64_t>(1, (c.kryl_sz + b - 1) / b - nlb);
+        // filtered restarts: short "settling" cycles while the filter is still being re-placed (below)
+        if (filtering && opt.restart && !filt_settled) max_steps = std::min<int64_t>(max_steps, std::max<int64_t>(8, 3 * ((kk_end + b - 1) / b)));
         last = c.cycle(nlb, k_rem, kk_end, false, max_steps);
         c.total_steps += last.final_i;
         c.total_steps_run += last.iterations_run;
@@ -1637,28 +1663,60 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
             if (j < k_rem && r.resid[j] <= opt.tol) lock.push_back(j);
             else if ((int64_t)rest.size() < b) rest.push_back(j);
         }
-        if (filtering && have > 0) {
-            // Re-place the filter: this cycle's Ritz values, mapped back through p, estimate the wanted eigenvalues far
-            // better than the short probe did; a tighter damped interval separates the wanted end more per degree.
+        if (filtering) {
+            // Filtered restarts never lock.  p amplifies the leading (first converged) eigenvalues far more than the last
+            // wanted ones - by 1e4 per application for a well placed degree-32 filter - so any imperfection of locked vectors
+            // re-grows inside the cycle and comes back as ghost Ritz pairs (observed on 8 GPUs: BASELINE config 5 returned
+            // pairs with residual 2e-5 ||A||; the CPU twin reproduces it on small grids).  Instead the cycle is repeated with
+            // a better filter from the leading b unconverged Ritz vectors: the filter is re-placed from this cycle's Ritz
+            // values mapped back through p (short settling cycles until the cut stops moving - a full-length cycle behind a
+            // badly placed filter is wasted), then, if a full-length cycle still does not converge, the degree doubles
+            // (within the dynamic-range cap).  oracle/rbl_restart_oracle.py RBL_restarted is the same procedure.
+            lock.clear();
+            rest.clear();
+            for (int64_t j = 0; j < have && (int64_t)rest.size() < b; ++j)
+                if (!(j < k_rem && r.resid[j] <= opt.tol)) rest.push_back(j);
             double lam_last = 0.0, lam_k = 0.0;
             const int64_t kq = std::min<int64_t>(k_rem, have);
-            if (c.flt.invert(r.d[have - 1], filt_side, &lam_last) && c.flt.invert(r.d[kq - 1], filt_side, &lam_k)) {
-                FilterPlan f = c.flt;
-                const double cut_old = f.two_sided ? f.b : (filt_side > 0 ? f.b : -f.a);
+            const bool ok_last = have > 0 && c.flt.invert(r.d[have - 1], filt_side, &lam_last);
+            bool ok_k = have > 0 && c.flt.invert(r.d[kq - 1], filt_side, &lam_k);
+            FilterPlan f = c.flt;
+            const double cut_old = f.two_sided ? f.b : (filt_side > 0 ? f.b : -f.a);
+            bool moved = false;
+            if (ok_last && ok_k) {
                 const double cut_new = std::fabs(lam_last);
-                if (cut_new > cut_old) {
+                if (cut_new > cut_old + 1e-2 * std::max(filt_norm - cut_old, 0.0)) {
                     if (f.two_sided) { f.a = -cut_new; f.b = cut_new; }
                     else if (filt_side > 0) f.b = cut_new;
                     else f.a = -cut_new;
-                    f.rho = 1.0;
-                    const double tk = std::fabs(f.eval(lam_k));
-                    const double xk = std::fabs((lam_k - f.c()) / f.e());
-                    f.rho = (tk > 0 && xk > 1.0) ? filt_norm / tk : 1.0;
-                    if (opt.verbose)
-                        std::fprintf(stderr, "[rbl] filter re-placed: damped [%.8g, %.8g] (cut %.8g -> %.8g), rho %.3e\n", f.a, f.b, cut_old, cut_new, f.rho);
-                    c.flt = f;
-                    stats.filter_cut = cut_new;
+                    moved = true;
                 }
+            }
+            bool changed = moved;
+            if (!moved && !filt_settled) {
+                filt_settled = true;          // same filter, whole buffer
+            } else if (!moved) {
+                int d2 = std::min(2 * f.degree, 256);
+                if (f.two_sided && !(d2 & 1)) ++d2;
+                f.degree = d2;
+                changed = true;
+            }
+            if (changed) {
+                f.degree = f.cap_degree(filt_lam1, f.degree);
+                if (f.degree == c.flt.degree && f.a == c.flt.a && f.b == c.flt.b) {
+                    status = RBL_NOT_CONVERGED;        // neither the cut nor the degree can move any more: best effort
+                    break;
+                }
+                if (!ok_k) lam_k = f.c() + f.e() * (1.0 + 1e-3) * (filt_side >= 0 ? 1.0 : -1.0);
+                f.scale_to(lam_k, filt_norm);
+                if (opt.verbose)
+                    std::fprintf(stderr, "[rbl] filter %s: degree %d, damped [%.8g, %.8g] (cut %.8g -> %.8g), rho %.3e\n", moved ? "re-placed" : "degree raised",
+                                 f.degree, f.a, f.b, cut_old, f.two_sided ? f.b : (filt_side > 0 ? f.b : -f.a), f.rho);
+                c.flt = f;
+                stats.filter_cut = f.two_sided ? f.b : (filt_side > 0 ? f.b : -f.a);
+                stats.filter_degree = f.degree;
+            } else if (opt.verbose) {
+                std::fprintf(stderr, "[rbl] filter settled: degree %d, damped [%.8g, %.8g]; the next cycle gets the whole buffer\n", f.degree, f.a, f.b);
             }
         }
         {   // is there room for another cycle once these are locked?  If not: best effort from this cycle, as at the cap

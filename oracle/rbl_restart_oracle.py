@@ -62,11 +62,15 @@ class ChebFilter:
 
     def invert(self, theta, side):
         """Eigenvalue estimate of A from a Ritz value theta of p(A) on the wanted side (side: +1 above the damped
-        interval, -1 below, 0 two-sided); None inside the interval."""
+        interval, -1 below, 0 two-sided); None inside the interval or when the sign of theta belongs to the other side."""
         if self.degree == 0:
             return float(theta)
         y = theta / self.rho
         if not abs(y) > 1.0:
+            return None
+        if side > 0 and y < 0:
+            return None
+        if side < 0 and (y < 0) != (self.degree % 2 == 1):
             return None
         x = np.cosh(np.arccosh(abs(y)) / self.degree)
         sgn = float(side) if side != 0 else (-1.0 if y < 0 else 1.0)
@@ -194,6 +198,33 @@ def lanczos_cycle(A, flt: ChebFilter, k_rem: int, kk: int, b: int, max_blocks: i
     return out
 
 
+MAX_FILTER_DEGREE = 256
+
+
+MAX_DYNAMIC_RANGE = 1e3
+
+
+def cap_degree(f: "ChebFilter", lam1: float, degree: int) -> int:
+    """Largest degree <= `degree` for which p(lam1) / p(edge of the damped interval) stays below MAX_DYNAMIC_RANGE (lam1:
+    estimate of the eigenvalue of largest magnitude).  A one-sided Chebyshev filter of high degree over a WIDE wanted
+    interval makes ||p(A)|| exceed the last wanted Ritz value by many orders of magnitude; those Ritz values are then
+    computed with an absolute error relative to ||p(A)|| and the absolute tolerance of the convergence test loses its
+    meaning.  A wide wanted interval does not need a high degree."""
+    x1 = abs((lam1 - f.c) / f.e) if f.e > 0 else 1.0
+    d = degree
+    if x1 > 1.0:
+        d = min(d, int(np.floor(np.arccosh(MAX_DYNAMIC_RANGE) / np.arccosh(x1))))
+    d = max(d, 2)
+    if f.two_sided and d % 2 == 0:
+        d += 1
+    return d
+
+
+def settle_steps(kk: int, b: int) -> int:
+    """Length of a settling cycle of the filtered restart: enough blocks for rough Ritz values of all kk pairs."""
+    return max(8, 3 * -(-kk // b))
+
+
 # --------------------------------------------------------------------------- driver
 @dataclass
 class RestartStats:
@@ -209,7 +240,7 @@ class RestartStats:
 
 def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol: float = 1e-7, filter_degree: int = 0,
                   probe_steps: int = 0, restart: bool = True, max_cycles: int = 50, reorth_period: int = 2,
-                  check_period: int = 4, return_details: bool = False):
+                  check_period: int = 4, return_details: bool = False, replace_filter: bool = True):
     """Generalised RBL_restarted / RBL_gpu_restarted (restarted.jl:98-146,196-246).
 
     Returns (D, V): the k eigenvalues of A of largest magnitude (descending |lambda|) and their vectors.
@@ -218,7 +249,7 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
     st = RestartStats()
     Q1 = np.linalg.qr(np.asarray(A @ np.asarray(Omega, dtype=DOUBLE), dtype=DOUBLE))[0]      # RBL.jl:137
     flt = ChebFilter(degree=0)
-    side, norm_a = 0, 0.0
+    side, norm_a, lam1_est = 0, 0.0, 0.0
     if filter_degree != 0:
         d = filter_degree if filter_degree > 0 else 8
         kk = k + b
@@ -231,11 +262,21 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
         flt = place_filter(pr.D, min(k, len(pr.D)), len(pr.D), d, glo, ghi)
         side = 0 if flt.two_sided else (1 if pr.D[0] > 0 else -1)
         norm_a = abs(pr.D[0])
+        lam1_est = float(pr.D[0])
+        dc = cap_degree(flt, lam1_est, flt.degree)
+        if dc != flt.degree:
+            flt.degree = dc
+            flt.rho = 1.0
+            kq0 = min(k, len(pr.D))
+            tk = abs(float(flt.scalar(pr.D[kq0 - 1])))
+            xk = abs((pr.D[kq0 - 1] - flt.c) / flt.e)
+            flt.rho = norm_a / tk if tk > 0 and xk > 1.0 else 1.0
         st.operator_applications += pr.iterations
     st.filter = flt
     Y = np.zeros((n, 0))
     Dlock = np.zeros(0)
     start = Q1
+    settled = not replace_filter
     final = None
     while True:
         st.cycles += 1
@@ -245,7 +286,10 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
         if room < 3:
             break
         kk = k_rem + b
-        res = lanczos_cycle(A, flt, k_rem, kk, b, room, start, Y, tol=tol, reorth_period=reorth_period,
+        steps = room
+        if flt.degree > 0 and restart and not settled:
+            steps = min(room, settle_steps(kk, b))
+        res = lanczos_cycle(A, flt, k_rem, kk, b, steps, start, Y, tol=tol, reorth_period=reorth_period,
                             check_period=check_period)
         st.block_steps += res.iterations
         st.operator_applications += res.iterations * max(1, flt.degree)
@@ -253,14 +297,25 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
             final = res
             st.converged = res.converged
             break
-        if flt.degree > 0 and len(res.D) > 0:
-            # re-place the filter from this cycle's Ritz values mapped back through p (tighter damped interval)
-            kq = min(k_rem, len(res.D))
-            lam_last, lam_k = flt.invert(res.D[-1], side), flt.invert(res.D[kq - 1], side)
-            if lam_last is not None and lam_k is not None:
-                cut_old = flt.b if (flt.two_sided or side > 0) else -flt.a
+        if flt.degree > 0:
+            # Filtered restarts never lock.  p amplifies the leading (first converged) eigenvalues far more than the last
+            # wanted ones - by 1e4 per application for a well placed degree-32 filter - so any imperfection of locked vectors
+            # re-grows inside the cycle and comes back as ghost Ritz pairs (observed: BASELINE config 5 returned pairs with
+            # residual 2e-5 ||A||, smaller cases garbage).  Instead the cycle is repeated with a better filter from the
+            # leading b unconverged Ritz vectors: the filter is re-placed from this cycle's Ritz values mapped back through p
+            # (short "settling" cycles until the cut stops moving - a full-length cycle behind a badly placed filter is
+            # wasted), then, if a full-length cycle still does not converge, the degree doubles.
+            nb = res.iterations
+            Qm = np.hstack(res.Q[:nb])
+            have = len(res.D)
+            kq = min(k_rem, have)
+            lam_last = flt.invert(res.D[-1], side) if have else None
+            lam_k = flt.invert(res.D[kq - 1], side) if have else None
+            cut_old = flt.b if (flt.two_sided or side > 0) else -flt.a
+            f2 = None
+            if replace_filter and lam_last is not None and lam_k is not None:
                 cut_new = abs(lam_last)
-                if cut_new > cut_old:
+                if cut_new > cut_old + 1e-2 * max(norm_a - cut_old, 0.0):
                     f2 = ChebFilter(degree=flt.degree, a=flt.a, b=flt.b, rho=1.0, two_sided=flt.two_sided)
                     if f2.two_sided:
                         f2.a, f2.b = -cut_new, cut_new
@@ -268,11 +323,34 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
                         f2.b = cut_new
                     else:
                         f2.a = -cut_new
-                    tk = abs(float(f2.scalar(lam_k)))
-                    xk = abs((lam_k - f2.c) / f2.e)
-                    f2.rho = norm_a / tk if tk > 0 and xk > 1.0 else 1.0
-                    flt = f2
-                    st.filter = flt
+            if f2 is None and not settled:
+                settled = True                      # the cut has stopped moving: the next cycle gets the whole buffer
+                f2 = flt
+            elif f2 is None:
+                d2 = min(2 * flt.degree, MAX_FILTER_DEGREE)
+                if flt.two_sided and d2 % 2 == 0:
+                    d2 += 1
+                f2 = ChebFilter(degree=d2, a=flt.a, b=flt.b, rho=1.0, two_sided=flt.two_sided)
+            if f2 is not flt:
+                want_degree = f2.degree
+                f2.degree = cap_degree(f2, lam1_est, f2.degree)
+                if f2.degree == flt.degree and f2.a == flt.a and f2.b == flt.b:
+                    final = res                   # neither the cut nor the degree can move any more: best effort
+                    break
+                if lam_k is None:
+                    lam_k = f2.c + f2.e * (1.0 + 1e-3) * (1.0 if side >= 0 else -1.0)
+                f2.rho = 1.0
+                tk = abs(float(f2.scalar(lam_k)))
+                xk = abs((lam_k - f2.c) / f2.e)
+                f2.rho = norm_a / tk if tk > 0 and xk > 1.0 else 1.0
+                flt = f2
+                st.filter = flt
+            rest = [j for j in range(have) if not (j < k_rem and res.bounds[j] <= tol)][:b]
+            start = Qm @ res.S[:, rest]
+            if start.shape[1] < b:
+                start = np.hstack([start, np.random.default_rng(st.cycles).standard_normal((n, b - start.shape[1]))])
+            start = np.linalg.qr(start)[0]
+            continue
         # lock every wanted pair whose bound passed (restarted.jl:122-131), restart from the best b others (:133-135)
         nb = res.iterations
         Qm = np.hstack(res.Q[:nb])

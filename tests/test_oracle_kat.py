@@ -56,3 +56,36 @@ def test_oracle_residuals_config1_small():
     assert np.max(rbl_oracle.ritz_residuals(A, D, V, norm_a=8.0)) < 1e-6
     nb = det["S"].shape[0] // b
     assert rbl_oracle.orthogonality_loss(det["Q"][:nb]) < 1e-10
+
+
+# ---- the restart / filter twin (oracle/rbl_restart_oracle.py) pinned against the analytic spectrum -----------------------
+def test_restart_oracle_filtered_restarts_do_not_return_ghost_pairs():
+    """Regression for the filtered restart: with locking behind a re-placed high-degree filter the twin (and the device
+    solver, on BASELINE config 5) returned ghost copies of locked eigenvalues - 'converged' pairs with residuals of order
+    one.  Filtered restarts now re-place the filter / raise its degree and never lock; the dynamic range of p is capped."""
+    from oracle import rbl_restart_oracle as rr
+    N, k, b = 24, 40, 16
+    A = matrices.shifted(matrices.laplacian_3d(N), 12.0)
+    Om = np.random.default_rng(1).standard_normal((N ** 3, b))
+    lam, V, st = rr.RBL_restarted(A, k, b, Om, max_blocks=16, filter_degree=16, return_details=True)
+    exact = 12.0 - matrices.laplacian_eigs(N, 3, k)
+    assert st.converged and st.locked == 0
+    assert np.max(np.abs(lam - exact) / exact) < 1e-12
+    assert st.max_residual < 1e-7
+    assert np.linalg.norm(V.T @ V - np.eye(k), 2) < 1e-10
+    f = st.filter
+    assert f.b < exact[-1]                                   # every wanted eigenvalue stays outside the damped interval
+    x1 = (exact[0] - f.c) / f.e
+    assert np.cosh(f.degree * np.arccosh(x1)) <= 1.01 * rr.MAX_DYNAMIC_RANGE
+
+
+def test_chebyshev_filter_inverse_map_rejects_the_wrong_side():
+    from oracle import rbl_restart_oracle as rr
+    f = rr.ChebFilter(degree=8, a=0.0, b=10.0, rho=2.0)
+    lam = 11.3
+    th = float(f.scalar(lam))
+    assert abs(f.invert(th, 1) - lam) < 1e-12
+    assert f.invert(-th, 1) is None and f.invert(1.5, 1) is None      # other side / inside the damped interval
+    g = rr.ChebFilter(degree=7, a=-10.0, b=0.0, rho=1.0)
+    thn = float(g.scalar(-11.0))
+    assert thn < 0 and abs(g.invert(thn, -1) + 11.0) < 1e-12 and g.invert(-thn, -1) is None
