@@ -1464,6 +1464,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
     double filt_norm = 0.0;     // |lambda_1| estimate: the filter is scaled so that p(lambda_k) ~ ||op(A)||
     double filt_lam1 = 0.0;     // lambda_1 estimate (signed)
     bool filt_settled = false;  // the cut has stopped moving: cycles get the whole buffer
+    int filt_want_degree = 0;   // requested degree (the dynamic-range cap may hold the actual one below it)
     const bool filtering = fdeg > 0;
     const bool extra = filtering || opt.restart;
     c.base = (opt.op == RBL_OP_SHIFT_MINUS_A) ? SpmmCoef{-1.0, opt.sigma, 0.0} : SpmmCoef{1.0, 0.0, 0.0};
@@ -1615,6 +1616,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
         else if (allneg) { f.a = -cut; f.b = s_hi > -cut ? s_hi : -cut + std::fabs(cut); }
         else { f.two_sided = true; f.a = -cut; f.b = cut; if (!(f.degree & 1)) ++f.degree; }
         if (!(f.e() > 0)) throw Error(RBL_BREAKDOWN, "rbl_solve: filter probe found a degenerate spectrum interval");
+        filt_want_degree = f.degree;
         f.degree = f.cap_degree(r.d[0], f.degree);
         f.scale_to(r.d[kq - 1], std::fabs(r.d[0]));
         c.flt = f;
@@ -1689,6 +1691,7 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
                     if (f.two_sided) { f.a = -cut_new; f.b = cut_new; }
                     else if (filt_side > 0) f.b = cut_new;
                     else f.a = -cut_new;
+                    f.degree = filt_want_degree;
                     moved = true;
                 }
             }
@@ -1696,9 +1699,8 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
             if (!moved && !filt_settled) {
                 filt_settled = true;          // same filter, whole buffer
             } else if (!moved) {
-                int d2 = std::min(2 * f.degree, 256);
-                if (f.two_sided && !(d2 & 1)) ++d2;
-                f.degree = d2;
+                filt_want_degree = std::min(2 * f.degree, 256);
+                f.degree = filt_want_degree;
                 changed = true;
             }
             if (changed) {

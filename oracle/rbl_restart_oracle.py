@@ -249,7 +249,7 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
     st = RestartStats()
     Q1 = np.linalg.qr(np.asarray(A @ np.asarray(Omega, dtype=DOUBLE), dtype=DOUBLE))[0]      # RBL.jl:137
     flt = ChebFilter(degree=0)
-    side, norm_a, lam1_est = 0, 0.0, 0.0
+    side, norm_a, lam1_est, want_degree = 0, 0.0, 0.0, 0
     if filter_degree != 0:
         d = filter_degree if filter_degree > 0 else 8
         kk = k + b
@@ -263,6 +263,7 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
         side = 0 if flt.two_sided else (1 if pr.D[0] > 0 else -1)
         norm_a = abs(pr.D[0])
         lam1_est = float(pr.D[0])
+        want_degree = flt.degree
         dc = cap_degree(flt, lam1_est, flt.degree)
         if dc != flt.degree:
             flt.degree = dc
@@ -316,7 +317,7 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
             if replace_filter and lam_last is not None and lam_k is not None:
                 cut_new = abs(lam_last)
                 if cut_new > cut_old + 1e-2 * max(norm_a - cut_old, 0.0):
-                    f2 = ChebFilter(degree=flt.degree, a=flt.a, b=flt.b, rho=1.0, two_sided=flt.two_sided)
+                    f2 = ChebFilter(degree=want_degree, a=flt.a, b=flt.b, rho=1.0, two_sided=flt.two_sided)
                     if f2.two_sided:
                         f2.a, f2.b = -cut_new, cut_new
                     elif side > 0:
@@ -327,13 +328,10 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
                 settled = True                      # the cut has stopped moving: the next cycle gets the whole buffer
                 f2 = flt
             elif f2 is None:
-                d2 = min(2 * flt.degree, MAX_FILTER_DEGREE)
-                if flt.two_sided and d2 % 2 == 0:
-                    d2 += 1
-                f2 = ChebFilter(degree=d2, a=flt.a, b=flt.b, rho=1.0, two_sided=flt.two_sided)
+                want_degree = min(2 * flt.degree, MAX_FILTER_DEGREE)
+                f2 = ChebFilter(degree=want_degree, a=flt.a, b=flt.b, rho=1.0, two_sided=flt.two_sided)
             if f2 is not flt:
-                want_degree = f2.degree
-                f2.degree = cap_degree(f2, lam1_est, f2.degree)
+                f2.degree = cap_degree(f2, lam1_est, f2.degree)      # (the requested degree, as far as the dynamic range allows)
                 if f2.degree == flt.degree and f2.a == flt.a and f2.b == flt.b:
                     final = res                   # neither the cut nor the degree can move any more: best effort
                     break
