@@ -47,7 +47,8 @@ template <int B>
 __global__ void __launch_bounds__(256) spmm_kernel(int64_t nrows, const int* __restrict__ rowptr,
                                                    const int* __restrict__ colidx, const double* __restrict__ vals,
                                                    const double* __restrict__ Q, double* U, SpmmCoef cf,
-                                                   const double* Z) {
+                                                   const double* Z, const int* __restrict__ rowlist,
+                                                   const unsigned char* __restrict__ skip) {
     constexpr int LPR = B / 2;
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31;
@@ -59,7 +60,11 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t nrows, const int* __r
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const double2* __restrict__ Q2 = reinterpret_cast<const double2*>(Q);
     // (Two rows per thread and iteration - more loads in flight per thread - was measured too: 120 us against 96 us.)
-    for (int64_t row = warp * RPW + rsel; row < nrows; row += nwarps * RPW) {
+    // rowlist != nullptr: the nrows rows listed there (row-sharded runs: the rows that reference halo columns, computed once
+    // the halo has arrived); skip != nullptr: rows flagged there are left alone (the same rows, while the halo is in flight)
+    for (int64_t idx = warp * RPW + rsel; idx < nrows; idx += nwarps * RPW) {
+        const int64_t row = rowlist ? (int64_t)__ldg(rowlist + idx) : idx;
+        if (skip && skip[row]) continue;
         int p = __ldg(rowptr + row);
         const int p1 = __ldg(rowptr + row + 1);
         double2 acc = make_double2(0.0, 0.0);
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t nrows, const int* __r
 }
 
 void launch_spmm(int B, int64_t nrows, const int* rowptr, const int* colidx, const double* vals, const double* Q,
-                 double* U, SpmmCoef cf, const double* Z, cudaStream_t st) {
+                 double* U, SpmmCoef cf, const double* Z, cudaStream_t st, const int* rowlist, const unsigned char* skip) {
     if (nrows <= 0) return;
     dispatch_B(B, [&](auto bc) {
         constexpr int BB = decltype(bc)::value;
@@ -108,7 +113,7 @@ void launch_spmm(int B, int64_t nrows, const int* rowptr, const int* colidx, con
         int64_t rows_per_cta = (int64_t)RPW * 8;
         int64_t want = (nrows + rows_per_cta - 1) / rows_per_cta;
         int grid = (int)std::min<int64_t>(want, (int64_t)num_sms() * 16);
-        spmm_kernel<BB><<<grid, 256, 0, st>>>(nrows, rowptr, colidx, vals, Q, U, cf, Z);
+        spmm_kernel<BB><<<grid, 256, 0, st>>>(nrows, rowptr, colidx, vals, Q, U, cf, Z, rowlist, skip);
     });
 }
 

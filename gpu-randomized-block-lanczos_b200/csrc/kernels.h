@@ -35,8 +35,10 @@ inline int padded_block(int b) { return b <= 4 ? 4 : (b <= 8 ? 8 : (b <= 16 ? 16
 struct SpmmCoef {
     double alpha = 1.0, beta = 0.0, gamma = 0.0;
 };
+// rowlist: compute only the `nrows` rows listed; skip: leave the rows flagged there untouched (halo overlap, solver.cu)
 void launch_spmm(int B, int64_t nrows, const int* rowptr, const int* colidx, const double* vals, const double* Q,
-                 double* U, SpmmCoef cf, const double* Z, cudaStream_t st);
+                 double* U, SpmmCoef cf, const double* Z, cudaStream_t st, const int* rowlist = nullptr,
+                 const unsigned char* skip = nullptr);
 
 // second generation for banded / stencil matrices (spmm.cu): Q and the CSR stream staged in shared memory by TMA bulk copies
 struct SpmmWindows {

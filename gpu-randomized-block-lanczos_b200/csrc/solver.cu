@@ -266,6 +266,30 @@ rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, co
         RBL_CUDA(cudaMemcpy(h->wsp->d_colidx.p, ci.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice));
         RBL_CUDA(cudaMemcpy(h->wsp->d_vals.p, vals, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice));
     }
+    // row-sharded: the rows that reference halo columns.  The SpMM computes all other rows while the halo exchange is in
+    // flight on a second stream and these rows once it has arrived (Run::spmm).
+    h->n_bnd_rows = 0;
+    if (world > 1 && h->n_halo > 0) {
+        std::vector<int> bnd;
+        std::vector<unsigned char> flag((size_t)nloc, 0);
+        for (int64_t r = 0; r < nloc; ++r)
+            for (int p = rp[r]; p < rp[r + 1]; ++p)
+                if (ci[p] >= nloc) { flag[r] = 1; bnd.push_back((int)r); break; }
+        const char* env = std::getenv("RBL_HALO_OVERLAP");
+        if (!(env && env[0] == '0') && !bnd.empty() && (int64_t)bnd.size() * 4 <= nloc) {
+            h->wsp->d_bnd_rows.ensure(bnd.size());
+            h->wsp->d_bnd_flag.ensure((size_t)nloc);
+            RBL_CUDA(cudaMemcpy(h->wsp->d_bnd_rows.p, bnd.data(), bnd.size() * sizeof(int), cudaMemcpyHostToDevice));
+            RBL_CUDA(cudaMemcpy(h->wsp->d_bnd_flag.p, flag.data(), flag.size(), cudaMemcpyHostToDevice));
+            if (!h->wsp->comm_stream) RBL_CUDA(cudaStreamCreateWithFlags(&h->wsp->comm_stream, cudaStreamNonBlocking));
+            if (!h->wsp->ev_q) RBL_CUDA(cudaEventCreateWithFlags(&h->wsp->ev_q, cudaEventDisableTiming));
+            if (!h->wsp->ev_halo) RBL_CUDA(cudaEventCreateWithFlags(&h->wsp->ev_halo, cudaEventDisableTiming));
+            h->n_bnd_rows = (int64_t)bnd.size();
+        }
+        if (h->opt.verbose)
+            std::fprintf(stderr, "[rbl] rank %d: %zu of %lld rows reference halo columns -> halo exchange %s\n", rank, bnd.size(), (long long)nloc,
+                         h->n_bnd_rows ? "overlapped with the interior rows" : "before the SpMM");
+    }
     // band structure?  then SpMM stages Q through shared-memory rings filled by the TMA engine (spmm.cu)
     h->spmm_wt = SpmmWindows{};
     {
@@ -674,24 +698,41 @@ struct Run {
         flush_store(store_j, 0);
     }
 
-    void halo(double* Xblk) {
+    void halo(double* Xblk, cudaStream_t hs = nullptr) {
         if (!h->comm.active()) return;
+        if (!hs) hs = st;
         std::string err;
         const int64_t nsend = h->send_ptr[h->world];
-        launch_gather_rows(B, nsend, w.d_send_rows.p, Xblk, w.sendbuf.p, st);
+        launch_gather_rows(B, nsend, w.d_send_rows.p, Xblk, w.sendbuf.p, hs);
         ++launches;
         nccl(h->comm.group_start(err), err);
         for (int p = 0; p < h->world; ++p) {
             if (p == h->rank) continue;
             const size_t sb = (size_t)(h->send_ptr[p + 1] - h->send_ptr[p]) * B * sizeof(double);
             const size_t rb = (size_t)(h->halo_owner_ptr[p + 1] - h->halo_owner_ptr[p]) * B * sizeof(double);
-            nccl(h->comm.send_bytes(w.sendbuf.p + (size_t)h->send_ptr[p] * B, sb, p, st, err), err);
-            nccl(h->comm.recv_bytes(Xblk + (size_t)(nloc + h->halo_owner_ptr[p]) * B, rb, p, st, err), err);
+            nccl(h->comm.send_bytes(w.sendbuf.p + (size_t)h->send_ptr[p] * B, sb, p, hs, err), err);
+            nccl(h->comm.recv_bytes(Xblk + (size_t)(nloc + h->halo_owner_ptr[p]) * B, rb, p, hs, err), err);
         }
         nccl(h->comm.group_end(err), err);
     }
     // U = cf.alpha * A Q + cf.beta * Q + cf.gamma * Z
     void spmm(double* Q, double* Uo, SpmmCoef cf, const double* Z) {
+        if (h->comm.active() && h->n_bnd_rows > 0 && !spmm_use_window) {
+            // the halo travels on the second stream while the rows that need none of it are computed; the rows that do
+            // (flagged, skipped by the first launch: Z may alias U, so they must not be written twice) follow
+            RBL_CUDA(cudaEventRecord(w.ev_q, st));
+            RBL_CUDA(cudaStreamWaitEvent(w.comm_stream, w.ev_q, 0));
+            halo(Q, w.comm_stream);
+            RBL_CUDA(cudaEventRecord(w.ev_halo, w.comm_stream));
+            launch_spmm(B, nloc, w.d_rowptr.p, w.d_colidx.p, w.d_vals.p, Q, Uo, cf, Z, st, nullptr, w.d_bnd_flag.p);
+            RBL_CUDA(cudaStreamWaitEvent(st, w.ev_halo, 0));
+            launch_spmm(B, h->n_bnd_rows, w.d_rowptr.p, w.d_colidx.p, w.d_vals.p, Q, Uo, cf, Z, st, w.d_bnd_rows.p, nullptr);
+            launches += 2;
+            ++n_spmm;
+            bytes_spmm += 12.0 * (double)h->nnz + 4.0 * (double)(nloc + 1) + 16.0 * (double)nloc * B +
+                          (cf.gamma != 0.0 ? 8.0 * (double)nloc * B : 0.0);
+            return;
+        }
         halo(Q);
         if (spmm_use_window)
             launch_spmm_window(B, nloc, nloc, w.d_rowptr.p, w.d_rel.p, w.d_vals.p, Q, Uo, cf, Z, h->spmm_wt, st);

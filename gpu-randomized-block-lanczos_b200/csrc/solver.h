@@ -107,6 +107,10 @@ struct Workspace {
     // no cudaFree / cudaStreamDestroy / cudaEventDestroy (measured: sporadic 0.4-1.8 s stalls in rbl_destroy)
     DevBuf<int> d_rowptr, d_colidx, d_send_rows, d_rel;   // d_rel: window-relative column encoding of the TMA SpMM
     DevBuf<int> d_order;                  // patch-ordered row schedule of the SpMM (spmm_sched.cu)
+    DevBuf<int> d_bnd_rows;               // row-sharded: local rows that reference halo columns
+    DevBuf<unsigned char> d_bnd_flag;     // the same as one flag per local row
+    cudaStream_t comm_stream = nullptr;   // halo exchange overlapped with the interior rows of the SpMM
+    cudaEvent_t ev_q = nullptr, ev_halo = nullptr;
     DevBuf<double> d_vals;
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> event_pool;
@@ -115,6 +119,9 @@ struct Workspace {
         for (auto e : spill_ev)
             if (e) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev_q) cudaEventDestroy(ev_q);
+        if (ev_halo) cudaEventDestroy(ev_halo);
+        if (comm_stream) cudaStreamDestroy(comm_stream);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -142,6 +149,7 @@ struct rbl_handle {
     std::vector<rbl_handle*> parts;
     std::vector<int64_t> part_rows;       // parts.size()+1 global row offsets
     double gersh_lo = 0.0, gersh_hi = 0.0;  // Gershgorin interval of A (global)
+    int64_t n_bnd_rows = 0;                // rows in d_bnd_rows (0: no overlap)
     rbl::SpmmSchedule spmm_sched;          // dims > 0: patch-scheduled gather SpMM (default for stencil matrices)
     rbl::SpmmWindows spmm_wt;              // nwin > 0: the matrix has band structure, SpMM stages Q through shared memory
     rbl::KrylovInfo last;
