@@ -73,6 +73,30 @@ bool spmm_plan_schedule(int64_t nrows, int64_t nown, const int* rowptr, const in
     else if (sc.dims == 2) { ext[0] = sc.stride[1]; ext[1] = (nrows + sc.stride[1] - 1) / sc.stride[1]; }
     else { ext[0] = sc.stride[1]; ext[1] = (sc.stride[2] + sc.stride[1] - 1) / sc.stride[1]; ext[2] = (nrows + sc.stride[2] - 1) / sc.stride[2]; }
     for (int i = 0; i < 3; ++i) sc.ext[i] = ext[i];
+    // alternative order (RBL_SPMM_ZTILE = tile height in y): strips of the x-y plane swept along z, so that the +-stride2
+    // neighbours of a row were touched one strip-plane (not one whole plane) ago - for planes too large for the L2
+    if (sc.dims == 3 && env_int("RBL_SPMM_ZTILE", 0) > 0) {
+        const int64_t ty = env_int("RBL_SPMM_ZTILE", 0);
+        std::vector<int> ord;
+        ord.reserve((size_t)nrows + slots);
+        const int64_t s1 = sc.stride[1], s2 = sc.stride[2];
+        for (int64_t y0 = 0; y0 < ext[1]; y0 += ty)
+            for (int64_t z = 0; z < ext[2]; ++z)
+                for (int64_t y = y0; y < std::min(ext[1], y0 + ty); ++y)
+                    for (int64_t x = 0; x < ext[0]; ++x) {
+                        const int64_t rem = y * s1 + x, r = z * s2 + rem;
+                        if (rem < s2 && r < nrows) ord.push_back((int)r);
+                    }
+        if ((int64_t)ord.size() != nrows) return false;
+        while (ord.size() % slots) ord.push_back(-1);
+        sc.patch[0] = (int)ext[0]; sc.patch[1] = (int)ty; sc.patch[2] = 1;
+        sc.slots = slots;
+        sc.npatch = (int64_t)ord.size() / slots;
+        sc.fetch_model = 0.0;
+        order.swap(ord);
+        if (info) *info = sc;
+        return true;
+    }
     // patch shape: minimise rows of Q fetched per row, prod_i (1 + 2 halo_i / p_i), times the slot padding, over shapes
     // with p0*p1*p2 <= slots; x runs of at least 8 rows (1 KB contiguous pieces of every stream) when the grid allows
     double best = 1e300;

@@ -174,8 +174,12 @@ def test_multi_gpu_group_handle_equals_single_gpu(gpu, case):
         D2, V2, st2 = gpu.RBL_gpu(L, k, b, Omega=Om, shift=sigma, precision=prec, ngpus=ng, return_stats=True, **kw)
         A = matrices.shifted(L, sigma) if sigma is not None else L
         assert st2.converged
-        # row-sharded solves never wait at a check point: the accepting check may belong to a slightly later step
-        assert -4 <= st2.iterations - st1.iterations <= 24
+        # row-sharded solves never wait at a check point: the accepting check may belong to a slightly later step (restarted
+        # solves: in every cycle, and the cycles then lock different numbers of pairs)
+        if "restart" in case:
+            assert abs(st2.iterations - st1.iterations) <= 0.3 * st1.iterations
+        else:
+            assert -4 <= st2.iterations - st1.iterations <= 24
         assert np.max(np.abs(D2 - D1) / np.abs(D1)) < 1e-8
         assert V2.shape == (n, k)
         assert np.max(rbl_oracle.ritz_residuals(A, D2, V2)) < 1e-6
@@ -197,6 +201,25 @@ def test_non_waiting_check_points_accept_the_same_solution(gpu):
     assert st2.iterations % 4 == 0 and st2.iterations_run >= st2.iterations
     assert np.max(np.abs(D2 - D1) / np.abs(D1)) < 1e-10
     assert np.max(rbl_oracle.ritz_residuals(matrices.shifted(L, 12.0), D2, V2, norm_a=12.0)) < 1e-6
+
+
+def test_multi_gpu_halo_exchange_overlapped_with_interior_rows(gpu, monkeypatch):
+    """RBL_HALO_OVERLAP=1: the SpMM computes the rows without halo columns while the exchange runs on a second stream, the
+    flagged rows afterwards - same block SpMM results, hence the same solve (plain and Chebyshev form, where Z aliases U)."""
+    _need_gpus(gpu, 2)
+    L = matrices.laplacian_3d(24)
+    Om = np.random.default_rng(6).standard_normal((24 ** 3, 16))
+    for kw in (dict(), dict(filter_degree=6)):
+        res = {}
+        for ov in ("0", "1"):
+            monkeypatch.setenv("RBL_HALO_OVERLAP", ov)
+            res[ov] = gpu.RBL_gpu(L, 20, 16, Omega=Om, shift=12.0, precision="fp64", ngpus=2, async_check=0, max_kryl_sz=3200,
+                                  return_stats=True, **kw)
+        assert res["0"][2].converged and res["1"][2].converged
+        assert res["0"][2].iterations == res["1"][2].iterations
+        assert np.max(np.abs(res["0"][0] - res["1"][0]) / np.abs(res["0"][0])) < 1e-13
+        exact = 12.0 - matrices.laplacian_eigs(24, 3, 20)
+        assert np.max(np.abs(res["1"][0] - exact) / exact) < 1e-8
 
 
 def test_multi_gpu_group_handle_one_based_and_device_rng(gpu):

@@ -15,6 +15,15 @@ ap.add_argument("--iters", type=int, default=20)
 a = ap.parse_args()
 if a.matrix == "lap3d":
     L = matrices.laplacian_3d(a.size).tocsr()
+elif a.matrix == "slab":          # a rank's shard of BASELINE config 5: size x size x 50 grid points (halo columns dropped)
+    import scipy.sparse as sp
+    from run_config import laplacian_3d_rows
+    N = a.size
+    r0, r1 = 100 * N * N, 150 * N * N
+    rp, ci, va = laplacian_3d_rows(N, r0, r1)
+    keep = (ci >= r0) & (ci < r1)
+    rows = np.repeat(np.arange(r1 - r0), np.diff(rp))
+    L = sp.csr_matrix((va[keep], (rows[keep], ci[keep] - r0)), shape=(r1 - r0, r1 - r0))
 else:
     from run_config import image_laplacian_fast
     L = image_laplacian_fast(a.size, a.size, seed=0).tocsr()
@@ -25,10 +34,10 @@ with B.Solver(L, options=B.default_options(precision=B.PRECISION_MIXED)) as s:
     for with_z in (0, 1):
         alg = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n * 16 + (8.0 * n * 16 if with_z else 0.0)
         for flush in (1, 0):
-            for kind in (0, 1, 2):
+            for kind in ((0, 1) if os.environ.get("LAB_QUICK") else (0, 1, 2)):
                 for sched in ((0,) if kind == 0 else (0, 16)):
-                    for pf in ((0,) if kind == 0 else (0, 1, 2) if kind == 1 else (0, 1)):
-                        for gm in ((16,) if kind == 0 else (8, 16, 32)):
+                    for pf in ((0,) if (kind == 0 or os.environ.get("LAB_QUICK")) else (0, 1, 2) if kind == 1 else (0, 1)):
+                        for gm in ((16,) if (kind == 0 or os.environ.get("LAB_QUICK")) else (8, 16, 32)):
                             us, bad = C.c_double(), C.c_int64()
                             rc = rbl_b200.lib().rbl_spmm_bench(s._h, 16, kind | sched | (pf << 8), gm, a.iters, flush, with_z, C.byref(us), C.byref(bad))
                             if rc != 0:
