@@ -1659,8 +1659,9 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
         else if (allneg) { f.a = -cut; f.b = s_hi > -cut ? s_hi : -cut + std::fabs(cut); }
         else { f.two_sided = true; f.a = -cut; f.b = cut; if (!(f.degree & 1)) ++f.degree; }
         if (!(f.e() > 0)) throw Error(RBL_BREAKDOWN, "rbl_solve: filter probe found a degenerate spectrum interval");
+        // (no dynamic-range cap here: the probe's cut lies far below the wanted end, the cap would be computed from a range
+        // p never sees among the wanted pairs; it applies from the first re-placement on, where the estimates are good)
         filt_want_degree = f.degree;
-        f.degree = f.cap_degree(r.d[0], f.degree);
         f.scale_to(r.d[kq - 1], std::fabs(r.d[0]));
         c.flt = f;
         filt_side = allpos ? 1 : (allneg ? -1 : 0);
@@ -1730,7 +1731,9 @@ int solve(rbl_handle* h, int64_t k, int64_t b_in, const SolveIO& io, double* d_o
             bool moved = false;
             if (ok_last && ok_k) {
                 const double cut_new = std::fabs(lam_last);
-                if (cut_new > cut_old + 1e-2 * std::max(filt_norm - cut_old, 0.0)) {
+                // (the cut must stay below the estimate of the last wanted eigenvalue - itself a lower bound of it - or
+                // wanted eigenvalues would be damped; inconsistent estimates leave the filter alone)
+                if (cut_new > cut_old + 1e-2 * std::max(filt_norm - cut_old, 0.0) && cut_new < std::fabs(lam_k)) {
                     if (f.two_sided) { f.a = -cut_new; f.b = cut_new; }
                     else if (filt_side > 0) f.b = cut_new;
                     else f.a = -cut_new;

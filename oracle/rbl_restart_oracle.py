@@ -264,14 +264,8 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
         norm_a = abs(pr.D[0])
         lam1_est = float(pr.D[0])
         want_degree = flt.degree
-        dc = cap_degree(flt, lam1_est, flt.degree)
-        if dc != flt.degree:
-            flt.degree = dc
-            flt.rho = 1.0
-            kq0 = min(k, len(pr.D))
-            tk = abs(float(flt.scalar(pr.D[kq0 - 1])))
-            xk = abs((pr.D[kq0 - 1] - flt.c) / flt.e)
-            flt.rho = norm_a / tk if tk > 0 and xk > 1.0 else 1.0
+        # (no dynamic-range cap at the probe: its cut lies far below the wanted end; the cap applies from the first
+        # re-placement on, where the estimates are good)
         st.operator_applications += pr.iterations
     st.filter = flt
     Y = np.zeros((n, 0))
@@ -316,7 +310,8 @@ def RBL_restarted(A, k: int, b: int, Omega: np.ndarray, *, max_blocks: int, tol:
             f2 = None
             if replace_filter and lam_last is not None and lam_k is not None:
                 cut_new = abs(lam_last)
-                if cut_new > cut_old + 1e-2 * max(norm_a - cut_old, 0.0):
+                # (the cut must stay below the estimate of the last wanted eigenvalue - itself a lower bound of it)
+                if cut_new > cut_old + 1e-2 * max(norm_a - cut_old, 0.0) and cut_new < abs(lam_k):
                     f2 = ChebFilter(degree=want_degree, a=flt.a, b=flt.b, rho=1.0, two_sided=flt.two_sided)
                     if f2.two_sided:
                         f2.a, f2.b = -cut_new, cut_new

@@ -82,6 +82,30 @@ def test_restart_with_locking_when_the_cap_binds(gpu, precision):
     assert not st2.converged
 
 
+@pytest.mark.parametrize("precision", ["fp64", "mixed"])
+def test_filtered_restart_replaces_the_filter_and_never_locks(gpu, precision):
+    """The regime of BASELINE config 5 in small: the probe places the filter badly, the cap binds.  Settling cycles re-place
+    the filter from their own Ritz values, nothing is locked (locking behind a re-placed high-degree filter returned ghost
+    pairs), the dynamic range of p stays capped - device and CPU twin follow the same procedure."""
+    N, k, b = 24, 40, 16
+    L = matrices.laplacian_3d(N)
+    A = matrices.shifted(L, 12.0)
+    Om = np.random.default_rng(1).standard_normal((N ** 3, b))
+    D, V, st = gpu.RBL_gpu(L, k, b, Omega=Om, shift=12.0, precision=precision, max_kryl_sz=16 * b, restart=True, filter_degree=16,
+                           return_stats=True)
+    Dt, Vt, tw = rr.RBL_restarted(A, k, b, Om, max_blocks=16, filter_degree=16, return_details=True)
+    exact = 12.0 - matrices.laplacian_eigs(N, 3, k)
+    assert st.converged and tw.converged
+    assert st.locked == 0 and tw.locked == 0 and st.restarts >= 1
+    assert abs(st.restarts + 1 - tw.cycles) <= 2
+    assert st.filter_cut < exact[-1] and tw.filter.b < exact[-1]            # no wanted eigenvalue inside the damped interval
+    assert abs(st.filter_cut - tw.filter.b) <= 2e-2 * (12.0 - tw.filter.b)
+    assert np.max(np.abs(D - exact) / exact) < 1e-8
+    assert np.max(np.abs(D - Dt) / np.abs(Dt)) < 1e-8
+    assert _resid(A, D, V, 12.0) < 1e-6 and st.max_residual / 12.0 < 1e-6
+    assert np.max(np.abs(V.T @ V - np.eye(k))) < (1e-5 if precision == "mixed" else 1e-8)
+
+
 def test_restart_driven_by_device_memory(gpu):
     """The cap comes from the memory plan (mem_limit_mb) instead of max_kryl_sz - the regime of configs 3 and 5."""
     N, k, b = 24, 30, 16
