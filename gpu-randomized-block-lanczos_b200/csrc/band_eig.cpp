@@ -85,6 +85,10 @@ void BandSym::matvec(const double* x, double* y) const {
 // the number of sign changes along r is the number of eigenvalues of T below the shift (Sturm).
 void BandLU::factor(const BandSym& T, double shift) {
     if (T.cancel && T.cancel->load(std::memory_order_relaxed)) throw Cancelled{};
+    while (T.pause && T.pause->load(std::memory_order_relaxed)) {
+        std::this_thread::sleep_for(std::chrono::microseconds(200));
+        if (T.cancel && T.cancel->load(std::memory_order_relaxed)) throw Cancelled{};
+    }
     N = T.N;
     kd = T.kd;
     shift_ = shift;
@@ -1192,6 +1196,12 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     stage_now = 2;
     auto since_start = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() * 1e3; };
     const double ms_stage3_begin = since_start();
+    // all k pairs from here on: every thread of the box is wanted (the accepting check is the one the device waits for)
+    struct FullFlag {
+        std::atomic<bool>* f;
+        explicit FullFlag(std::atomic<bool>* p) : f(p) { if (f) f->store(true); }
+        ~FullFlag() { if (f) f->store(false); }
+    } full_guard(full_flag);
     double ms_refined = 0, ms_validated = 0;
     std::vector<Pair> pairs;
     std::vector<Pair> known_pairs;

@@ -24,6 +24,8 @@ struct BandSym {
     double norm_inf = 0.0;
     double gersh_lo = 0.0, gersh_hi = 0.0;  // Gershgorin interval containing the spectrum
     const std::atomic<bool>* cancel = nullptr;  // polled at every factorisation; set -> Cancelled is thrown
+    const std::atomic<bool>* pause = nullptr;   // polled at every factorisation; while set the caller sleeps (the background
+                                                // tracker yields the cores to a full check of the main checker)
 
     void reset(int64_t n, int kd_);
     inline double& at(int64_t r, int64_t c) { return F[(size_t)r * (2 * kd + 1) + (size_t)(c - r + kd)]; }
@@ -86,6 +88,7 @@ class BandTopK {
 public:
     int threads = 1;
     int verbose = 0;
+    std::atomic<bool>* full_flag = nullptr;     // raised while this checker computes all k pairs (stage 3)
     int64_t total_factorizations = 0;
     int64_t resumed_factorizations = 0;
     // where the decisions came from and what they cost (seconds): [0] witness, [1] bracketed pair, [2] full

@@ -886,7 +886,9 @@ struct Run {
         RBL_CUDA(cudaMemcpyAsync(dbuf, hsend, 16, cudaMemcpyHostToDevice, st));
         allreduce(dbuf, 2);
         RBL_CUDA(cudaMemcpyAsync(hsend + 2, dbuf, 16, cudaMemcpyDeviceToHost, st));
-        if (!post_event[slot]) RBL_CUDA(cudaEventCreateWithFlags(&post_event[slot], cudaEventDisableTiming));
+        // (blocking sync: a rank that waits here - for the root, which is busy with a full check - sleeps instead of spinning on a
+        // core the check could use)
+        if (!post_event[slot]) RBL_CUDA(cudaEventCreateWithFlags(&post_event[slot], cudaEventDisableTiming | cudaEventBlockingSync));
         RBL_CUDA(cudaEventRecord(post_event[slot], st));
         post_pending = slot;
     }
@@ -977,9 +979,11 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         std::thread th;
         bool active = false, stop = false, have_req = false, have_res = false;
         std::atomic<bool> cancel{false};   // raised with `stop`: the tracker abandons the eigensolve it is in
+        std::atomic<bool> pause{false};    // raised while the main checker computes all k pairs: the tracker's threads sleep
         BandSym req;
         TopKResult res;
     } shadow;
+    checker.full_flag = &shadow.pause;
     const int shadow_verbose = opt.verbose;
     const int bb = b;
     auto shadow_loop = [&shadow, k_rem, bb, shadow_verbose](int nthreads) {
@@ -995,6 +999,7 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
                 shadow.have_req = false;
             }
             Tc.cancel = &shadow.cancel;
+            Tc.pause = &shadow.pause;
             TopKResult r;
             const double ts0 = now_s();
             const int64_t f0 = tracker.total_factorizations;
