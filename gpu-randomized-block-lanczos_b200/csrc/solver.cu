@@ -1224,7 +1224,7 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         }
         // bounded speculation: a check that started kMaxAhead steps ago is waited for (an accepting full check takes the
         // time of a hundred 8-GPU steps; running on would only burn slab slots and power on steps that get discarded)
-        constexpr int64_t kMaxAhead = 16;
+        constexpr int64_t kMaxAhead = 16;     // (32 was measured on 2 GPUs: less idle, but a later accepted step and a longer drain - slower)
         const int code = nb_poll(it, true, check_in_flight && it - pending_i >= kMaxAhead);
         if (!multi) {
             if (code >= 2) nb_fail();

@@ -179,7 +179,7 @@ def test_multi_gpu_group_handle_equals_single_gpu(gpu, case):
         if "restart" in case:
             assert abs(st2.iterations - st1.iterations) <= 0.3 * st1.iterations
         else:
-            assert -4 <= st2.iterations - st1.iterations <= 24
+            assert -4 <= st2.iterations - st1.iterations <= 40
         assert np.max(np.abs(D2 - D1) / np.abs(D1)) < 1e-8
         assert V2.shape == (n, k)
         assert np.max(rbl_oracle.ritz_residuals(A, D2, V2)) < 1e-6
@@ -197,7 +197,7 @@ def test_non_waiting_check_points_accept_the_same_solution(gpu):
     Om = np.random.default_rng(2).standard_normal((8000, 16))
     D1, V1, st1 = gpu.RBL_gpu(L, 20, 16, Omega=Om, shift=12.0, precision="mixed", async_check=1, return_stats=True)
     D2, V2, st2 = gpu.RBL_gpu(L, 20, 16, Omega=Om, shift=12.0, precision="mixed", async_check=2, return_stats=True)
-    assert st2.converged and st1.iterations <= st2.iterations <= st1.iterations + 24
+    assert st2.converged and st1.iterations <= st2.iterations <= st1.iterations + 40
     assert st2.iterations % 4 == 0 and st2.iterations_run >= st2.iterations
     assert np.max(np.abs(D2 - D1) / np.abs(D1)) < 1e-10
     assert np.max(rbl_oracle.ritz_residuals(matrices.shifted(L, 12.0), D2, V2, norm_a=12.0)) < 1e-6
