@@ -201,6 +201,22 @@ void BandLU::run_t(const BandSym& T, int64_t r_start) {
 }
 
 void BandLU::solve(double* v) const {
+    switch (kd) {
+        case 4: solve_t<4>(v); break;
+        case 8: solve_t<8>(v); break;
+        case 16: solve_t<16>(v); break;
+        case 32: solve_t<32>(v); break;
+        default: solve_t<0>(v); break;
+    }
+}
+
+// Forward: the recorded row operations applied to v (a chain of 2x2 transforms through the running entry).  Backward:
+// v[r] = (v[r] - sum_t U[r][t] v[r+t]) / U[r][0]; only the t = 1 term depends on the entry computed one row earlier, so
+// everything else is summed first, off the serial chain (a plain `s -= U[t]*v[r+t]` loop is a chain of 2kd dependent
+// fused multiply-adds per row and took longer than the whole forward sweep).
+template <int KD>
+void BandLU::solve_t(double* __restrict__ v) const {
+    const int kd = KD > 0 ? KD : this->kd;
     const int W = 2 * kd + 1;
     for (int64_t r = 0; r < N; ++r) {
         const int64_t base = r - kd;
@@ -218,12 +234,43 @@ void BandLU::solve(double* v) const {
         }
         v[r] = vr;
     }
-    for (int64_t r = N - 1; r >= 0; --r) {
-        const double* Ur = &U[(size_t)r * W];
+    const double* __restrict__ Ub = U.data();
+    int64_t r = N - 1;
+    // the last 2kd rows have short sums
+    for (; r >= 0 && r > N - 1 - (W - 1); --r) {
+        const double* Ur = Ub + (size_t)r * W;
         double s = v[r];
-        int tmax = (int)std::min<int64_t>(W - 1, N - 1 - r);
+        const int tmax = (int)(N - 1 - r);
         for (int t = 1; t <= tmax; ++t) s -= Ur[t] * v[r + t];
         v[r] = s / Ur[0];
+    }
+    if (KD >= 4) {
+        for (; r >= 0; --r) {
+            const double* __restrict__ Ur = Ub + (size_t)r * W;
+            const double* __restrict__ vv = v + r;
+            __m256d acc0 = _mm256_setzero_pd(), acc1 = _mm256_setzero_pd();
+            int t = 8;
+            for (; t + 8 <= 2 * kd; t += 8) {
+                acc0 = _mm256_fmadd_pd(_mm256_loadu_pd(Ur + t), _mm256_loadu_pd(vv + t), acc0);
+                acc1 = _mm256_fmadd_pd(_mm256_loadu_pd(Ur + t + 4), _mm256_loadu_pd(vv + t + 4), acc1);
+            }
+            for (; t + 4 <= 2 * kd; t += 4) acc0 = _mm256_fmadd_pd(_mm256_loadu_pd(Ur + t), _mm256_loadu_pd(vv + t), acc0);
+            alignas(32) double h[4];
+            _mm256_store_pd(h, _mm256_add_pd(acc0, acc1));
+            const int tl = kd >= 4 ? 2 * kd : 0;
+            double s0 = Ur[2] * vv[2] + Ur[4] * vv[4] + Ur[6] * vv[6] + (h[0] + h[1]);
+            double s1 = Ur[3] * vv[3] + Ur[5] * vv[5] + Ur[7] * vv[7] + (h[2] + h[3]);
+            s0 += Ur[tl] * vv[tl];
+            const double p = vv[0] - (s0 + s1);
+            v[r] = (p - Ur[1] * vv[1]) / Ur[0];
+        }
+    } else {
+        for (; r >= 0; --r) {
+            const double* Ur = Ub + (size_t)r * W;
+            double s = v[r];
+            for (int t = 1; t < W; ++t) s -= Ur[t] * v[r + t];
+            v[r] = s / Ur[0];
+        }
     }
 }
 
@@ -647,7 +694,74 @@ void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, boo
 struct Interval {
     double lo, hi;
     int64_t clo, chi;  // eigenvalues below lo / below hi
+    double tried = 0.0;  // width at which block_extract last failed on an ancestor (0: never tried) ...
+    int64_t tried_m = 0; // ... and the number of eigenvalues it held
 };
+
+// The q eigenpairs of a NARROW interval (lo,hi) that are not among `against` (already known eigenvectors of the interval;
+// the interval holds q + against.size() eigenvalues by its Sturm counts), all at once: block inverse iteration deflated
+// against the known vectors + Rayleigh-Ritz.
+// Bisection needs log2(width / 2e-11||T||) ~ 25-30 factorisations to squeeze an interval down to a degenerate cluster, and
+// the wanted Ritz values of the BASELINE Laplacians are ~25 such clusters (multiplicities 3 and 6): 600-1000 factorisations
+// per k = 100 eigensolve, and ~20 for every single copy of a multiple eigenvalue that is missing from a set of seeds.  When
+// the eigenvalues of the interval are bunched together and the rest of the spectrum is far away compared with the width,
+// q vectors converge in a few solves each with two factorisations (the second at the Ritz values' centre: block
+// Rayleigh-quotient iteration).  Success = q orthonormal vectors, orthogonal to the known ones, with residuals at rounding
+// level and Ritz values strictly inside the interval; anything else - slow decay because a neighbour sits just outside
+// or the interval holds several groups, a Ritz value on the edge - returns false and the caller goes on bisecting.
+bool block_extract(const BandSym& T, Work& wk, const Interval& iv, int q, const std::vector<const std::vector<double>*>& against,
+                   std::vector<Pair>& got) {
+    const int64_t N = T.N;
+    const double tn = std::max(T.norm_inf, 1e-300);
+    const double edge = std::max(1e-11 * tn, 1e-3 * (iv.hi - iv.lo));
+    std::vector<std::vector<double>> X(q);
+    for (auto& x : X) wk.random_unit(x, N);
+    mgs(X, 0, against, N);
+    std::vector<double> theta, res;
+    double prev = 1e300;
+    for (int it = 0; it < 7; ++it) {
+        if (it == 0) {
+            wk.lu.factor(T, 0.5 * (iv.lo + iv.hi));
+            ++wk.nfac;
+        } else if (it == 2) {
+            double c = 0;
+            for (double t : theta) c += t;
+            wk.lu.factor(T, c / q + 3e-15 * tn);
+            ++wk.nfac;
+        }
+        for (auto& x : X) {
+            wk.lu.solve(x.data());
+            const double nn = nrm2(x.data(), N);
+            if (!(nn > 0) || !std::isfinite(nn)) return false;
+            scal(x.data(), 1.0 / nn, N);
+        }
+        if (mgs(X, 0, against, N) < 1e-8) return false;  // the block lost rank: fewer directions than the count says
+        rayleigh_ritz(T, X, theta, res);
+        double worst = 0;
+        bool inside = true;
+        for (int j = 0; j < q; ++j) {
+            worst = std::max(worst, res[j]);
+            if (!(theta[j] > iv.lo + edge && theta[j] < iv.hi - edge)) inside = false;
+        }
+        if (std::getenv("RBL_BLOCK_DEBUG")) std::fprintf(stderr, "[blk] q=%d known=%zu width=%.3e it=%d worst=%.3e inside=%d\n", q, against.size(), iv.hi - iv.lo, it, worst / tn, (int)inside);
+        // converged: at rounding level, or stagnating just above it (the attainable residual grows with N)
+        if (worst <= 2e-13 * tn || (it >= 3 && worst <= 5e-12 * tn && worst > 0.25 * prev)) {
+            if (!inside) return false;
+            for (int j = 0; j < q; ++j) {
+                Pair p;
+                p.theta = theta[j];
+                p.res = res[j];
+                p.v.swap(X[j]);
+                got.push_back(std::move(p));
+            }
+            return true;
+        }
+        if (it >= 1 && !inside) return false;              // a Ritz value on the edge / an outside eigenvalue pulled in
+        if (it >= 1 && worst > 0.03 * prev) return false;  // several groups, or a neighbour just outside: bisect further
+        prev = worst;
+    }
+    return false;
+}
 
 // All eigenpairs with eigenvalue in (lo,hi): recursive bisection on Sturm counts until an interval
 // holds one eigenvalue (finished by inverse iteration + RQI) or a tight cluster.
@@ -705,11 +819,48 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
                     complete = true;
                 }
             }
+            // narrow interval with few eigenvalues that are not known yet: try to pull them out in one go
+            int64_t q_missing = m;
+            std::vector<const std::vector<double>*> in_known;
+            std::vector<size_t> in_idx;
+            bool edge_known = false;
+            if (!complete && !kn.empty()) {
+                auto lo_it = std::upper_bound(kn.begin(), kn.end(), std::make_pair(iv.lo + kmargin, (size_t)-1));
+                auto hi_it = std::lower_bound(kn.begin(), kn.end(), std::make_pair(iv.hi - kmargin, (size_t)0));
+                auto lo_edge = std::lower_bound(kn.begin(), kn.end(), std::make_pair(iv.lo - kmargin, (size_t)0));
+                auto hi_edge = std::upper_bound(kn.begin(), kn.end(), std::make_pair(iv.hi + kmargin, (size_t)-1));
+                edge_known = !(lo_edge == lo_it && hi_edge == hi_it) || hi_it < lo_it;
+                if (!edge_known) {
+                    for (auto it = lo_it; it != hi_it; ++it) {
+                        in_known.push_back(&(*known)[it->second].v);
+                        in_idx.push_back(it->second);
+                    }
+                    q_missing = m - (int64_t)in_known.size();
+                }
+            }
+            const bool try_block = !complete && !edge_known && q_missing >= 1 && q_missing <= 12 && m >= 2 && (iv.hi - iv.lo) > ctol &&
+                                   (iv.hi - iv.lo) <= 1e-4 * tn &&
+                                   (iv.tried == 0.0 || (iv.hi - iv.lo) <= iv.tried / 16 || m < iv.tried_m);
+            bool extracted = false;
+            if (try_block) {
+                std::vector<Pair> got;
+                if (block_extract(T, wk, iv, (int)q_missing, in_known, got)) {
+                    extracted = true;
+                    for (auto& p : got) local.push_back(std::move(p));
+                    for (size_t ki : in_idx) local.push_back((*known)[ki]);
+                    n_reused += (int64_t)in_known.size();
+                } else {
+                    iv.tried = iv.hi - iv.lo;  // the halves try again only when narrower or split
+                    iv.tried_m = m;
+                }
+            }
             if (complete) {
                 // nothing to do below this interval
             } else if (m >= 2 && (iv.hi - iv.lo) <= ctol) {
                 std::lock_guard<std::mutex> lk(mu);
                 clusters.push_back(iv);
+            } else if (extracted) {
+                // all missing pairs of the interval came out of one deflated block inverse iteration
             } else {
                 wk.lu.factor(T, mid);
                 ++wk.nfac;
@@ -744,12 +895,12 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
                             std::lock_guard<std::mutex> lk(mu);
                             clusters.push_back(Interval{lo, hi, iv.clo, iv.chi});
                         } else {
-                            push.push_back(Interval{lo, hi, iv.clo, iv.chi});
+                            push.push_back(Interval{lo, hi, iv.clo, iv.chi, iv.tried, iv.tried_m});
                         }
                     }
                 } else {
-                    if (cmid > iv.clo) push.push_back(Interval{iv.lo, mid, iv.clo, cmid});
-                    if (iv.chi > cmid) push.push_back(Interval{mid, iv.hi, cmid, iv.chi});
+                    if (cmid > iv.clo) push.push_back(Interval{iv.lo, mid, iv.clo, cmid, iv.tried, iv.tried_m});
+                    if (iv.chi > cmid) push.push_back(Interval{mid, iv.hi, cmid, iv.chi, iv.tried, iv.tried_m});
                 }
             }
             {

@@ -49,6 +49,8 @@ struct BandLU {
     void factor(const BandSym& T, double shift);
     bool resume(const BandSym& T);  // same shift, T extended at its end: re-eliminates only the last rows
     void solve(double* v) const;
+    template <int KD>
+    void solve_t(double* v) const;
     // state saved just before row N - kd (the first row that changes when T grows)
     int64_t ck_row = -1;
     std::vector<double> ck_U;
