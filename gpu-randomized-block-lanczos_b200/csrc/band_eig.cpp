@@ -1030,45 +1030,96 @@ bool BandTopK::refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pair
     const int64_t N = T.N;
     const double tn = std::max(T.norm_inf, 1e-300);
     pairs.assign(k, Pair());
-    std::atomic<int64_t> next{0};
+    // Work units: seeds whose Ritz values (of the T they come from) coincide to 1e-7 ||T|| - the copies of a multiple
+    // eigenvalue, 3 or 6 at a time for the BASELINE Laplacians - share ONE factorisation just inside their common value;
+    // each copy then costs a solve or two instead of a factorisation of its own (the factorisation is 3-4 solves' worth).
+    // Units are capped so that there are enough of them for all threads.
+    std::vector<std::vector<int64_t>> units;
+    {
+        std::vector<int64_t> ord(k);
+        for (int64_t j = 0; j < k; ++j) ord[j] = j;
+        std::sort(ord.begin(), ord.end(), [&](int64_t x, int64_t y) { return seeds_[x].theta < seeds_[y].theta; });
+        const size_t cap = (size_t)std::max<int64_t>(1, (k + std::max(1, threads) - 1) / std::max(1, threads));
+        for (int64_t t = 0; t < k; ++t) {
+            const int64_t j = ord[t];
+            const bool join = !units.empty() && units.back().size() < std::max<size_t>(cap, 2) &&
+                              std::fabs(seeds_[j].theta - seeds_[units.back().back()].theta) <= 1e-7 * tn &&
+                              (seeds_[j].theta < 0) == (seeds_[units.back().back()].theta < 0);
+            if (join) units.back().push_back(j);
+            else units.push_back({j});
+        }
+    }
+    std::atomic<size_t> next{0};
     std::atomic<int64_t> fac{0};
-    std::atomic<bool> failed{false};
     auto worker = [&]() {
         Work wk;
+        struct Member { int64_t j; std::vector<double> x; double th = 0, rs = 0; bool ok = false, shared = false; };
         for (;;) {
-            const int64_t j = next.fetch_add(1);
-            if (j >= k || failed.load()) break;
-            std::vector<double> x(N, 0.0);
-            std::copy(seeds_[j].v.begin(), seeds_[j].v.end(), x.begin());
-            const double nn = nrm2(x.data(), N);
-            if (!(nn > 0)) continue;  // dropped (pairs[j].v stays empty)
-            scal(x.data(), 1.0 / nn, N);
-            double th, rs;
-            rayleigh(T, x, wk.t, th, rs);
-            bool ok = rs <= 2e-13 * tn;
-            for (int round = 0; round < 6 && !ok; ++round) {
-                const double sg = th < 0 ? -1.0 : 1.0;
-                const double off = (rs <= 1e-6 * tn) ? 2.0 * rs : 0.0;
-                wk.lu.factor(T, th - sg * off);
-                ++wk.nfac;
+            const size_t u = next.fetch_add(1);
+            if (u >= units.size()) break;
+            std::vector<Member> mem;
+            for (int64_t j : units[u]) {
+                Member mb;
+                mb.j = j;
+                mb.x.assign(N, 0.0);
+                std::copy(seeds_[j].v.begin(), seeds_[j].v.end(), mb.x.begin());
+                const double nn = nrm2(mb.x.data(), N);
+                if (!(nn > 0)) continue;  // dropped (pairs[j].v stays empty)
+                scal(mb.x.data(), 1.0 / nn, N);
+                rayleigh(T, mb.x, wk.t, mb.th, mb.rs);
+                mb.ok = mb.rs <= 2e-13 * tn;
+                mem.push_back(std::move(mb));
+            }
+            // inverse iteration of x with the factorisation in wk.lu: up to 4 solves while the residual keeps dropping
+            auto iterate = [&](Member& mb) {
                 for (int it = 0; it < 4; ++it) {
-                    wk.y = x;
+                    wk.y = mb.x;
                     wk.lu.solve(wk.y.data());
                     const double n2 = nrm2(wk.y.data(), N);
                     if (!(n2 > 0) || !std::isfinite(n2)) break;
                     scal(wk.y.data(), 1.0 / n2, N);
-                    x.swap(wk.y);
-                    const double prev = rs;
-                    rayleigh(T, x, wk.t, th, rs);
-                    if (rs <= 2e-13 * tn) { ok = true; break; }
-                    if (rs > 0.25 * prev) break;
+                    mb.x.swap(wk.y);
+                    const double prev = mb.rs;
+                    rayleigh(T, mb.x, wk.t, mb.th, mb.rs);
+                    if (mb.rs <= 2e-13 * tn) { mb.ok = true; break; }
+                    if (mb.rs > 0.25 * prev) break;
                 }
-                if (!ok && rs <= 1e-11 * tn && round >= 1) ok = true;
+            };
+            // shared factorisation: only for copies that are already close (residual <= 1e-8 ||T||), so that the common
+            // shift - the innermost of their own "Ritz value minus twice the residual" - stays within ~1e-7 ||T|| of all of them
+            int nclose = 0;
+            double shift = 0;
+            for (auto& mb : mem)
+                if (!mb.ok && mb.rs <= 1e-8 * tn) {
+                    const double sg = mb.th < 0 ? -1.0 : 1.0;
+                    const double mine = mb.th - sg * 2.0 * mb.rs;
+                    if (nclose == 0 || std::fabs(mine) < std::fabs(shift)) shift = mine;
+                    ++nclose;
+                }
+            if (nclose >= 2) {
+                wk.lu.factor(T, shift);
+                ++wk.nfac;
+                for (auto& mb : mem)
+                    if (!mb.ok && mb.rs <= 1e-8 * tn) {
+                        iterate(mb);
+                        mb.shared = true;
+                        if (!mb.ok && mb.rs <= 1e-11 * tn) mb.ok = true;
+                    }
             }
-            if (!ok) continue;        // dropped: the caller's count-based repair looks for what is missing
-            pairs[j].theta = th;
-            pairs[j].res = rs;
-            pairs[j].v.swap(x);
+            for (auto& mb : mem) {
+                for (int round = mb.shared ? 1 : 0; round < 6 && !mb.ok; ++round) {
+                    const double sg = mb.th < 0 ? -1.0 : 1.0;
+                    const double off = (mb.rs <= 1e-6 * tn) ? 2.0 * mb.rs : 0.0;
+                    wk.lu.factor(T, mb.th - sg * off);
+                    ++wk.nfac;
+                    iterate(mb);
+                    if (!mb.ok && mb.rs <= 1e-11 * tn && round >= 1) mb.ok = true;
+                }
+                if (!mb.ok) continue;        // dropped: the caller's count-based repair looks for what is missing
+                pairs[mb.j].theta = mb.th;
+                pairs[mb.j].res = mb.rs;
+                pairs[mb.j].v.swap(mb.x);
+            }
         }
         fac += wk.nfac;
     };
@@ -1080,7 +1131,7 @@ bool BandTopK::refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pair
             rcancel = true;
         }
     };
-    const int nt = (int)std::min<int64_t>(std::max(1, threads), k);
+    const int nt = (int)std::min<int64_t>(std::max(1, threads), (int64_t)units.size());
     if (nt <= 1) {
         guarded_worker();
     } else {
