@@ -691,6 +691,35 @@ void finalize_pairs(const BandSym& T, std::vector<Pair>& out, int64_t& nfac, boo
                      std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loose).count() * 1e3, sweeps, (int)swept, out.size());
 }
 
+// Sturm counts #{lambda < x} at several shifts at once, one factorisation per shift spread over the threads.
+void parallel_below(const BandSym& T, const std::vector<double>& xs, int threads, std::vector<int64_t>& below, int64_t& nfac) {
+    below.assign(xs.size(), 0);
+    if (xs.empty()) return;
+    std::atomic<size_t> next{0};
+    std::atomic<bool> cancelled{false};
+    auto run = [&]() {
+        BandLU lu;
+        try {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= xs.size()) break;
+                lu.factor(T, xs[i]);
+                below[i] = lu.nneg;
+            }
+        } catch (const Cancelled&) {
+            cancelled = true;
+            next = xs.size();
+        }
+    };
+    const int nt = (int)std::min<size_t>((size_t)std::max(1, threads), xs.size());
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(run);
+    run();
+    for (auto& t : th) t.join();
+    if (cancelled) throw Cancelled{};
+    nfac += (int64_t)xs.size();
+}
+
 struct Interval {
     double lo, hi;
     int64_t clo, chi;  // eigenvalues below lo / below hi
@@ -785,10 +814,51 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
     std::vector<Interval> clusters;
     int active = 0;
     bool cancelled = false;  // under mu: a worker saw T.cancel; everybody drains
-    for (auto& r : roots)
-        if (r.chi > r.clo && r.hi > r.lo) queue.push_back(r);
     std::atomic<int64_t> fac{0};
+    const bool slice_timing = std::getenv("RBL_SLICE_TIMING") != nullptr;
+    const auto ts0 = std::chrono::steady_clock::now();
+    auto ms_since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - ts0).count() * 1e3; };
+    // The bisection tree starts with one interval per root, so its first ~5 levels run on one or two threads, and with
+    // `known` pairs nearly all of the range is complete anyway.  One round of Sturm counts at several points at once - in
+    // the gaps between groups of known eigenvalues, or evenly spaced - hands every thread its own interval from the start,
+    // already narrow enough for block_extract where something is missing.
+    for (auto& r : roots) {
+        if (!(r.chi > r.clo && r.hi > r.lo)) continue;
+        std::vector<double> pts;
+        const size_t want = (size_t)std::min(64, 4 * std::max(1, threads));
+        if (threads > 1 && T.N >= 400 && r.chi - r.clo >= 8) {
+            if (!kn.empty()) {
+                std::vector<std::pair<double, double>> gaps;  // (gap width, midpoint) between consecutive known values in the root
+                for (size_t i = 1; i < kn.size(); ++i) {
+                    const double a = kn[i - 1].first, b2 = kn[i].first;
+                    if (a > r.lo && b2 < r.hi && b2 - a > 64 * kmargin) gaps.push_back({b2 - a, 0.5 * (a + b2)});
+                }
+                std::sort(gaps.begin(), gaps.end(), [](const std::pair<double, double>& x, const std::pair<double, double>& y) { return x.first > y.first; });
+                if (gaps.size() > want) gaps.resize(want);
+                for (auto& gp : gaps) pts.push_back(gp.second);
+            } else {
+                for (size_t i = 1; i < want; ++i) pts.push_back(r.lo + (r.hi - r.lo) * (double)i / (double)want);
+            }
+        }
+        if (pts.empty()) { queue.push_back(r); continue; }
+        std::sort(pts.begin(), pts.end());
+        std::vector<int64_t> below;
+        int64_t nf0 = 0;
+        parallel_below(T, pts, threads, below, nf0);
+        fac += nf0;
+        double lo = r.lo;
+        int64_t clo = r.clo;
+        for (size_t i = 0; i <= pts.size(); ++i) {
+            const double hi = i < pts.size() ? pts[i] : r.hi;
+            const int64_t chi = i < pts.size() ? std::min(std::max(below[i], clo), r.chi) : r.chi;
+            if (chi > clo && hi > lo) queue.push_back(Interval{lo, hi, clo, chi});
+            lo = hi;
+            clo = chi;
+        }
+    }
 
+    const double ms_presplit = ms_since();
+    const size_t n_initial = queue.size();
     auto worker = [&](int seed) {
         Work wk;
         wk.rng.seed(987654321ull + 7919ull * seed);
@@ -934,6 +1004,7 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
         for (auto& t : th) t.join();
     }
     if (cancelled) throw Cancelled{};
+    const double ms_tree = ms_since();
 
     // tight clusters (degenerate Ritz values), in parallel: each orthogonal to the already accepted single
     // vectors within a few ctol; clusters that a bisection point split in two are repaired by the final pass
@@ -979,6 +1050,7 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
             for (auto& p : f) out.push_back(std::move(p));
     }
 
+    const double ms_clusters = ms_since();
     {
         int64_t nf2 = 0;
         finalize_pairs(T, out, nf2, nullptr, threads);
@@ -986,6 +1058,9 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
     }
     nfac += fac.load();
     if (reused) *reused = n_reused.load();
+    if (slice_timing)
+        std::fprintf(stderr, "[rbl]   slice: pre-split %.1f ms (%zu intervals), tree done at %.1f, %zu tight clusters done at %.1f, finalize done at %.1f ms; %lld factorisations\n",
+                     ms_presplit, n_initial, ms_tree, clusters.size(), ms_clusters, ms_since(), (long long)fac.load());
 }
 
 // residual bound ||B_i s[N-b..N)||, B_i row-major upper triangular b x b
@@ -1023,6 +1098,18 @@ static double seed_min_frac() {
         return (v > 0.0 && v <= 1.0) ? v : 0.70;
     }();
     return f;
+}
+
+// Seeds at least this fresh (size of the T they come from / size of T now) send a check whose witnesses have converged
+// straight to the seeded full check, skipping the serial bracket search of stage 2.
+static double seed_fresh_frac(int threads) {
+    static const double f = [] {
+        const char* e = std::getenv("RBL_SEED_FRESH_FRAC");
+        const double v = e ? std::atof(e) : 0.0;
+        return (v > 0.0 && v <= 1.0) ? v : 0.0;
+    }();
+    if (f > 0.0) return f;
+    return threads >= 4 ? 0.85 : 0.95;
 }
 
 bool BandTopK::refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pairs, int64_t& nfac) {
@@ -1330,7 +1417,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     // refinement of stage 3 costs about what a failed stage 2 costs (and runs on all threads): when the witnesses of stage 1
     // have converged - which is the situation of the accepting check - go there directly.
     const bool seeds_fresh = (int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N &&
-                             (double)seeds_[0].v.size() >= 0.95 * (double)N;
+                             (double)seeds_[0].v.size() >= seed_fresh_frac(threads) * (double)N;
     if (!force_full && bi && k >= 1 && !seeds_fresh) {
         const int64_t margin = std::max<int64_t>(1, std::min<int64_t>(k / 6, k - 1));
         struct Target { int64_t lo, hi; double* x; double* step; };
@@ -1498,6 +1585,27 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     std::vector<Interval> roots;
     const bool hinted = false;
     if (!hinted) {
+        // one-sided spectra (nothing below -x for the x in question: the shifted BASELINE operators) with several threads:
+        // multi-section - `threads` Sturm counts per round, all at once - instead of one bisection step after the other
+        const double x_onesided = std::max(0.0, -T.gersh_lo) * (1.0 + 1e-12) + 1e-300;  // above this nothing lies below -x
+        while (!from_seeds && threads > 1 && N >= 400 && !(c_lo.above >= k && c_lo.above <= k + std::max<int64_t>(2, k / 8)) &&
+               x_hi - std::max(x_lo, x_onesided) > 1e-10 * tn) {
+            const double lo_eff = std::max(x_lo, x_onesided);
+            const int np = std::min(threads, 16);
+            std::vector<double> xs;
+            for (int i = (lo_eff > x_lo ? 0 : 1); i <= np; ++i) xs.push_back(lo_eff + (x_hi - lo_eff) * (double)i / (double)(np + 1));
+            std::vector<int64_t> below;
+            int64_t nf0 = 0;
+            parallel_below(T, xs, threads, below, nf0);
+            wk.nfac += (int)nf0;
+            bool moved = false;
+            for (size_t i = 0; i < xs.size(); ++i) {
+                const int64_t above = N - below[i];
+                if (above >= k) { x_lo = xs[i]; c_lo = Cnt{below[i], 0, above}; have_clo = true; moved = true; }
+                else { x_hi = xs[i]; break; }
+            }
+            if (!moved && lo_eff > x_lo) break;  // the k-th value lies where the spectrum is two-sided: bisection below
+        }
         for (int it = 0; it < 60 && !from_seeds; ++it) {
             if (c_lo.above >= k && c_lo.above <= k + std::max<int64_t>(2, k / 8)) break;
             if (x_hi - x_lo <= 1e-13 * tn) break;
