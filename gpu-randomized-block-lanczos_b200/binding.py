@@ -89,7 +89,7 @@ SIGNATURES = {
     "rbl_checker_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "rbl_checker_check": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _PD, C.c_int64, _PD, C.c_int64, C.c_double, C.c_int,
                                     _PD, _PD, _PD, _P32, _P32, _P64]),
-    "rbl_checker_set_seeds": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _PD, _PD]),
+    "rbl_checker_set_seeds": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _PD, _PD, _PD]),
     "rbl_checker_destroy": (C.c_int, [C.c_void_p]),
     "rbl_band_count_below": (C.c_int, [C.c_int64, C.c_int64, _PD, C.c_double, _P64]),
     "rbl_partition_rows": (C.c_int, [C.c_int64, C.c_int, _P64]),
@@ -350,11 +350,13 @@ class Checker:
         return dict(converged=bool(conv.value), have_all=bool(have.value), D=D, S=S, resid=res,
                     factorizations=int(st[0]), full=bool(st[1]))
 
-    def set_seeds(self, D, S):
-        """k Ritz pairs (D, S: n_seed x k) of an earlier T: starting points of the next full check (the tracker's hand-over)."""
+    def set_seeds(self, D, S, resid=None):
+        """k Ritz pairs (D, S: n_seed x k) of an earlier T: starting points of the next full check (the tracker's hand-over);
+        resid: their residual bounds at that time (the worst few become witnesses)."""
         D = np.ascontiguousarray(D, dtype=np.float64)
         S = np.asfortranarray(S, dtype=np.float64)
-        _check(lib().rbl_checker_set_seeds(self._c, S.shape[0], S.shape[1], _pd(D), _pd(S)))
+        r = None if resid is None else np.ascontiguousarray(resid, dtype=np.float64)
+        _check(lib().rbl_checker_set_seeds(self._c, S.shape[0], S.shape[1], _pd(D), _pd(S), _pd(r) if r is not None else None))
 
     def close(self):
         if self._c:

@@ -1077,16 +1077,127 @@ double resid_bound(const double* bi, int b, const std::vector<double>& s) {
     return std::sqrt(acc);
 }
 
+// One witness followed on its own (thread-safe: no state shared with the checker): the zero-padded old Ritz vector is
+// refined by inverse iteration with the shift kept on the inner side of the Ritz value, so that the Sturm count of the
+// last factorisation bounds from above the number of eigenvalues of larger magnitude (the pair's rank).
+struct Followed {
+    bool ok = false;
+    double theta = 0, res = 0, rho = 0;
+    int64_t larger = 0;
+    std::vector<double> x;
+    int nfac = 0;
+};
+
+Followed follow_witness(const BandSym& T, const std::vector<double>& w, const double* bi, int b) {
+    Followed f;
+    const int64_t N = T.N;
+    const double tn = std::max(T.norm_inf, 1e-300);
+    if ((int64_t)w.size() > N) return f;
+    f.x.assign(N, 0.0);
+    std::copy(w.begin(), w.end(), f.x.begin());
+    const double nn = nrm2(f.x.data(), N);
+    if (!(nn > 0)) return f;
+    scal(f.x.data(), 1.0 / nn, N);
+    Work wk;
+    double th, rs;
+    rayleigh(T, f.x, wk.t, th, rs);
+    double sigma = 0;
+    int64_t cnt = 0;
+    bool ok = false;
+    for (int round = 0; round < 7 && !ok; ++round) {
+        const double sg = th < 0 ? -1.0 : 1.0;
+        const double off = (rs <= 1e-6 * tn) ? 2.0 * rs : 0.0;
+        sigma = th - sg * off;
+        wk.lu.factor(T, sigma);
+        ++f.nfac;
+        cnt = wk.lu.nneg;
+        for (int it = 0; it < 4; ++it) {
+            wk.y = f.x;
+            wk.lu.solve(wk.y.data());
+            const double n2 = nrm2(wk.y.data(), N);
+            if (!(n2 > 0) || !std::isfinite(n2)) break;
+            scal(wk.y.data(), 1.0 / n2, N);
+            f.x.swap(wk.y);
+            const double prev = rs;
+            rayleigh(T, f.x, wk.t, th, rs);
+            if (rs <= 2e-13 * tn) { ok = true; break; }
+            if (rs > 0.25 * prev) break;
+        }
+        if (!ok && rs <= 1e-11 * tn && round >= 1) ok = true;
+    }
+    if (!ok) return f;
+    const double margin = 1e-13 * tn;
+    const double delta = std::max(1e-10 * std::fabs(th), 1e-12 * tn);
+    if (th >= 0) {
+        if (!(sigma < th - margin)) {
+            wk.lu.factor(T, th - delta);
+            ++f.nfac;
+            cnt = wk.lu.nneg;
+        }
+        int64_t neg = 0;
+        if (!(-std::fabs(th) < T.gersh_lo)) {
+            wk.lu.factor(T, -std::fabs(th));
+            ++f.nfac;
+            neg = wk.lu.nneg;
+        }
+        f.larger = (N - cnt - 1) + neg;
+    } else {
+        if (!(sigma > th + margin)) {
+            wk.lu.factor(T, th + delta);
+            ++f.nfac;
+            cnt = wk.lu.nneg;
+        }
+        int64_t pos = 0;
+        if (std::fabs(th) <= T.gersh_hi) {
+            wk.lu.factor(T, std::fabs(th));
+            ++f.nfac;
+            pos = N - wk.lu.nneg;
+        }
+        f.larger = (cnt - 1) + pos;
+    }
+    f.theta = th;
+    f.res = rs;
+    f.rho = resid_bound(bi, b, f.x);
+    f.ok = true;
+    return f;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ BandTopK
-void BandTopK::set_seeds(const std::vector<double>& d, const std::vector<double>& svec, int64_t Ns, int64_t k) {
+void BandTopK::set_seeds(const std::vector<double>& d, const std::vector<double>& svec, int64_t Ns, int64_t k,
+                         const std::vector<double>* resid) {
     if ((int64_t)d.size() < k || (int64_t)svec.size() < Ns * k) return;
+    // (pairs of an older T than the ones in hand - a tracker pass that started before this checker's own last full check -
+    // would only make the next full check slower)
+    if ((int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() >= Ns) return;
     seeds_.clear();
     seeds_.resize(k);
     for (int64_t j = 0; j < k; ++j) {
         seeds_[j].theta = d[j];
         seeds_[j].v.assign(svec.begin() + (size_t)j * Ns, svec.begin() + (size_t)(j + 1) * Ns);
+    }
+    // The pairs that were furthest from convergence when the seeds were computed are the ones that will converge last
+    // (the bounds of the unconverged pairs decay at similar rates): they join the witness list, so that "all witnesses have
+    // converged" - the trigger of the full k-pair check - almost always means that everything has.  The witness this
+    // checker is following stays first (its factorisation is extended from check to check).
+    if (resid && (int64_t)resid->size() >= k) {
+        std::vector<int64_t> ord(k);
+        for (int64_t j = 0; j < k; ++j) ord[j] = j;
+        std::sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b2) { return (*resid)[a] > (*resid)[b2]; });
+        if (wit_.size() > 1) { wit_.resize(1); wit_theta_.resize(1); }
+        for (int64_t t = 0; t < k && (int)wit_.size() < 1 + kExtraWitnesses; ++t) {
+            const int64_t j = ord[t];
+            if (!((*resid)[j] > 0.0)) break;
+            if (!wit_.empty()) {  // the same pair as the witness in hand?
+                const int64_t n = std::min<int64_t>((int64_t)wit_[0].size(), Ns);
+                const double ov = dot(wit_[0].data(), seeds_[j].v.data(), n);
+                const double na = nrm2(wit_[0].data(), (int64_t)wit_[0].size()), nb = nrm2(seeds_[j].v.data(), Ns);
+                if (na > 0 && nb > 0 && std::fabs(ov) >= 0.9 * na * nb) continue;
+            }
+            wit_.push_back(seeds_[j].v);
+            wit_theta_.push_back(seeds_[j].theta);
+        }
     }
 }
 
@@ -1378,10 +1489,21 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         }
         return true;
     };
-    auto reject_with = [&](std::vector<double>& x, double th, double rho, const char* how) {
+    // the rejecting pair becomes the first witness of the next check; `keep`: other witnesses still worth following
+    auto reject_with = [&](std::vector<double>& x, double th, double rho, const char* how,
+                           std::vector<std::vector<double>>* keep = nullptr, std::vector<double>* keep_theta = nullptr) {
         if (std::strcmp(how, "witness") != 0) wlu_.ck_row = -1;
-        wit_.assign(1, x);
-        wit_theta_.assign(1, th);
+        std::vector<std::vector<double>> nw;
+        std::vector<double> nt;
+        nw.push_back(x);
+        nt.push_back(th);
+        if (keep)
+            for (size_t i = 0; i < keep->size(); ++i) {
+                nw.push_back(std::move((*keep)[i]));
+                nt.push_back((*keep_theta)[i]);
+            }
+        wit_.swap(nw);
+        wit_theta_.swap(nt);
         R.witness_rho = rho;
         R.witness_theta = th;
         if (verbose > 1)
@@ -1391,20 +1513,69 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     };
 
     // ---- stage 1: witnesses of the previous check (zero-padded old Ritz vectors) -------------------------
-    if (!force_full && bi) {
-        for (size_t wi = 0; wi < wit_.size(); ++wi) {
-            if ((int64_t)wit_[wi].size() > N) continue;
+    // The first one - the pair this checker has been following - is refined here with its factorisation extended from the
+    // previous check.  Only when it has converged are the others looked at, all at once on their own threads.
+    if (!force_full && bi && !wit_.empty()) {
+        if ((int64_t)wit_[0].size() <= N) {
             std::vector<double> x(N, 0.0);
-            std::copy(wit_[wi].begin(), wit_[wi].end(), x.begin());
+            std::copy(wit_[0].begin(), wit_[0].end(), x.begin());
             const double nn = nrm2(x.data(), N);
-            if (!(nn > 0)) continue;
-            scal(x.data(), 1.0 / nn, N);
-            Refined rf;
-            const bool rok = refine(wi == 0 ? wlu_ : wk.lu, wi == 0, x, false, 0.0, 0, rf);
-            if (verbose > 2) std::fprintf(stderr, "[rbl]   stage1 w%zu ok=%d theta=%.10g res=%.2e larger=%lld rho=%.3e\n", wi, (int)rok, rf.theta, rf.res, (long long)rf.larger, rok ? resid_bound(bi, b, x) : -1.0);
-            if (!rok) continue;
-            const double rho = resid_bound(bi, b, x);
-            if (rho > tol && rf.larger < k) return reject_with(x, rf.theta, rho, "witness");
+            if (nn > 0) {
+                scal(x.data(), 1.0 / nn, N);
+                Refined rf;
+                const bool rok = refine(wlu_, true, x, false, 0.0, 0, rf);
+                if (verbose > 2) std::fprintf(stderr, "[rbl]   stage1 w0 ok=%d theta=%.10g res=%.2e larger=%lld rho=%.3e\n", (int)rok, rf.theta, rf.res, (long long)rf.larger, rok ? resid_bound(bi, b, x) : -1.0);
+                if (rok) {
+                    const double rho = resid_bound(bi, b, x);
+                    if (rho > tol && rf.larger < k) {
+                        std::vector<std::vector<double>> keep(wit_.begin() + 1, wit_.end());
+                        std::vector<double> keep_theta(wit_theta_.begin() + 1, wit_theta_.end());
+                        return reject_with(x, rf.theta, rho, "witness", &keep, &keep_theta);
+                    }
+                }
+            }
+        }
+        const size_t nw = wit_.size() - 1;
+        if (nw > 0) {
+            std::vector<Followed> fw(nw);
+            std::atomic<size_t> next{0};
+            std::atomic<bool> cancelled{false};
+            auto run = [&]() {
+                try {
+                    for (;;) {
+                        const size_t i = next.fetch_add(1);
+                        if (i >= nw) break;
+                        fw[i] = follow_witness(T, wit_[i + 1], bi, b);
+                    }
+                } catch (const Cancelled&) {
+                    cancelled = true;
+                    next = nw;
+                }
+            };
+            const int nt = (int)std::min<size_t>((size_t)std::max(1, threads), nw);
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) th.emplace_back(run);
+            run();
+            for (auto& t : th) t.join();
+            if (cancelled) throw Cancelled{};
+            int best = -1;
+            for (size_t i = 0; i < nw; ++i) {
+                wk.nfac += fw[i].nfac;
+                if (verbose > 2) std::fprintf(stderr, "[rbl]   stage1 w%zu ok=%d theta=%.10g res=%.2e larger=%lld rho=%.3e\n", i + 1, (int)fw[i].ok, fw[i].theta, fw[i].res, (long long)fw[i].larger, fw[i].ok ? fw[i].rho : -1.0);
+                if (fw[i].ok && fw[i].rho > tol && fw[i].larger < k && (best < 0 || fw[i].rho > fw[best].rho)) best = (int)i;
+            }
+            if (best >= 0) {
+                // the slowest unconverged one is followed from now on; the other unconverged ones stay on the list
+                std::vector<std::vector<double>> keep;
+                std::vector<double> keep_theta;
+                for (size_t i = 0; i < nw; ++i)
+                    if ((int)i != best && fw[i].ok && fw[i].rho > tol && fw[i].larger < k) {
+                        keep.push_back(std::move(fw[i].x));
+                        keep_theta.push_back(fw[i].theta);
+                    }
+                wlu_.ck_row = -1;  // the kept factorisation belongs to the converged first witness
+                return reject_with(fw[best].x, fw[best].theta, fw[best].rho, "witness", &keep, &keep_theta);
+            }
         }
     }
 
@@ -1651,7 +1822,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     std::sort(order.begin(), order.end(), [](const std::pair<double, int64_t>& a, const std::pair<double, int64_t>& b2) { return a.first > b2.first; });
     wit_.clear();
     wit_theta_.clear();
-    for (size_t j = 0; j < order.size() && j < 3; ++j) {
+    for (size_t j = 0; j < order.size() && j < (size_t)(1 + kExtraWitnesses); ++j) {
         wit_.push_back(pairs[order[j].second].v);
         wit_theta_.push_back(pairs[order[j].second].theta);
     }

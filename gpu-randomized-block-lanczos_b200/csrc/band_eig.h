@@ -103,7 +103,10 @@ public:
     TopKResult check(const BandSym& T, const double* bi, int b, int64_t k, double tol, bool force_full);
     void reset() { wit_.clear(); wit_theta_.clear(); xA_ = xB_ = stepA_ = stepB_ = 0; seeds_.clear(); }
     // k Ritz pairs of an EARLIER T (d: k values, svec: Ns x k column-major): starting points of the next full check
-    void set_seeds(const std::vector<double>& d, const std::vector<double>& svec, int64_t Ns, int64_t k);
+    // resid (optional): the k residual bounds of those pairs at the time they were computed; the worst few join the witnesses
+    void set_seeds(const std::vector<double>& d, const std::vector<double>& svec, int64_t Ns, int64_t k,
+                   const std::vector<double>* resid = nullptr);
+    static constexpr int kExtraWitnesses = 8;
     bool has_seeds() const { return !seeds_.empty(); }
 
 private:

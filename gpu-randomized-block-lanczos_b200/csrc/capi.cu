@@ -620,10 +620,12 @@ int rbl_checker_check(rbl_checker* c, int64_t N, int64_t kd, const double* ab, i
     });
 }
 
-int rbl_checker_set_seeds(rbl_checker* c, int64_t n_seed, int64_t k, const double* d, const double* s) {
+int rbl_checker_set_seeds(rbl_checker* c, int64_t n_seed, int64_t k, const double* d, const double* s, const double* resid) {
     return guarded([&] {
         if (!c || n_seed < 1 || k < 1 || !d || !s) throw Error(RBL_INVALID, "rbl_checker_set_seeds: bad arguments");
-        c->chk.set_seeds(std::vector<double>(d, d + k), std::vector<double>(s, s + (size_t)n_seed * k), n_seed, k);
+        std::vector<double> rv;
+        if (resid) rv.assign(resid, resid + k);
+        c->chk.set_seeds(std::vector<double>(d, d + k), std::vector<double>(s, s + (size_t)n_seed * k), n_seed, k, resid ? &rv : nullptr);
         return (int)RBL_OK;
     });
 }

@@ -981,6 +981,9 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         std::atomic<bool> cancel{false};   // raised with `stop`: the tracker abandons the eigensolve it is in
         std::atomic<bool> pause{false};    // raised while the main checker computes all k pairs: the tracker's threads sleep
         BandSym req;
+        std::vector<double> req_bi;        // B_i of that snapshot: the tracker's pairs come back with their residual bounds
+        bool have_gift = false;            // all k pairs of a full check of the main checker: fresher starting points than
+        TopKResult gift;                   // the tracker's own previous pass
         TopKResult res;
     } shadow;
     checker.full_flag = &shadow.pause;
@@ -991,20 +994,31 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         tracker.threads = nthreads;
         for (;;) {
             BandSym Tc;
+            std::vector<double> bic;
+            TopKResult gift;
+            bool got_gift = false;
             {
                 std::unique_lock<std::mutex> lk(shadow.mu);
                 shadow.cv.wait(lk, [&] { return shadow.stop || shadow.have_req; });
                 if (shadow.stop) return;
                 Tc = std::move(shadow.req);
+                bic = shadow.req_bi;
                 shadow.have_req = false;
+                if (shadow.have_gift) {
+                    gift = std::move(shadow.gift);
+                    shadow.have_gift = false;
+                    got_gift = true;
+                }
             }
+            if (got_gift) tracker.set_seeds(gift.d, gift.s, gift.N, k_rem);  // (ignored when older than its own)
             Tc.cancel = &shadow.cancel;
             Tc.pause = &shadow.pause;
             TopKResult r;
             const double ts0 = now_s();
             const int64_t f0 = tracker.total_factorizations;
             try {
-                r = tracker.check(Tc, nullptr, bb, k_rem, 0.0, true);
+                // (tolerance 0: nothing counts as converged, the bounds are only reported)
+                r = tracker.check(Tc, bic.size() == (size_t)bb * bb ? bic.data() : nullptr, bb, k_rem, 0.0, true);
             } catch (const Cancelled&) {
                 return;
             } catch (...) {
@@ -1040,7 +1054,8 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         if (shadow.active && kwant == k_rem) {
             std::lock_guard<std::mutex> lk(shadow.mu);
             if (shadow.have_res) {
-                checker.set_seeds(shadow.res.d, shadow.res.s, shadow.res.N, k_rem);
+                checker.set_seeds(shadow.res.d, shadow.res.s, shadow.res.N, k_rem,
+                                  shadow.res.resid.size() == (size_t)k_rem ? &shadow.res.resid : nullptr);
                 shadow.have_res = false;
             }
         }
@@ -1057,7 +1072,14 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
             {
                 std::lock_guard<std::mutex> lk(shadow.mu);
                 shadow.req = T;  // snapshot (a few MB)
+                shadow.req_bi = Bi;
                 shadow.have_req = true;
+                if (r.have_all && kwant == k_rem && (int64_t)r.d.size() >= k_rem) {
+                    shadow.gift.d = r.d;
+                    shadow.gift.s = r.s;
+                    shadow.gift.N = r.N;
+                    shadow.have_gift = true;
+                }
             }
             shadow.cv.notify_all();
         }

@@ -255,8 +255,9 @@ int rbl_checker_check(rbl_checker* c, int64_t N, int64_t kd, const double* ab, i
                       double tol, int force_full, double* d_out, double* s_out, double* resid_out,
                       int32_t* converged_out, int32_t* have_all_out, int64_t* stats_out);
 /* Hands the checker k Ritz pairs of an EARLIER (smaller) T as starting points of its next full check - what the solver's
- * background tracker thread does between checks (d: k values, s: n_seed x k column-major). */
-int rbl_checker_set_seeds(rbl_checker* c, int64_t n_seed, int64_t k, const double* d, const double* s);
+ * background tracker thread does between checks (d: k values, s: n_seed x k column-major).  resid (may be NULL): their k
+ * residual bounds at that time; the pairs with the largest ones join the checker's witnesses. */
+int rbl_checker_set_seeds(rbl_checker* c, int64_t n_seed, int64_t k, const double* d, const double* s, const double* resid);
 int rbl_checker_destroy(rbl_checker* c);
 
 /* Number of eigenvalues of the band matrix strictly below x (Sturm count by row-wise elimination). */

@@ -335,3 +335,61 @@ def test_seeded_paths_on_random_bands(rbl, trial):
     S = r["S"]
     assert np.max(np.abs(S.T @ S - np.eye(k))) < 1e-8
     assert np.max(np.linalg.norm(M2 @ S - S * r["D"][None, :], axis=0)) < 1e-9 * tn
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_band_eig_clusters_large_threaded(rbl, threads):
+    """Degenerate clusters at a size where the threaded slicing pre-splits its roots and pulls narrow intervals out by
+    deflated block inverse iteration (N >= 400): 3-fold eigenvalues, compared with LAPACK."""
+    rng = np.random.default_rng(21)
+    kd, nb, copies = 8, 180, 3
+    blk = rng.standard_normal((nb, nb))
+    blk = np.triu(np.tril(blk + blk.T, kd), -kd)
+    N = nb * copies
+    M = np.zeros((N, N))
+    for i in range(copies):
+        M[i * nb:(i + 1) * nb, i * nb:(i + 1) * nb] = blk
+    ab = _band(M, kd)
+    k = 45
+    D, S, res, conv = rbl.band_eig_topk(ab, k, threads=threads)
+    ref = _topk_ref(ab, k)
+    sc = np.max(np.abs(ref))
+    assert np.max(np.abs(np.sort(np.abs(D)) - np.sort(np.abs(ref)))) < 1e-12 * sc
+    assert np.max(np.abs(S.T @ S - np.eye(k))) < 1e-9
+    assert np.max(np.linalg.norm(M @ S - S * D[None, :], axis=0)) < 1e-11 * sc
+
+
+def test_tracker_seeds_and_witnesses_keep_the_decisions(rbl):
+    """The solver's arrangement in miniature: a main checker that sees every check and a tracker that hands it, every
+    third check, the k pairs of an earlier T together with their residual bounds (the worst of which become witnesses).
+    Every decision must equal dsbev + sort_eig_abs + check_convergence, and stale hand-overs must not displace fresher
+    seeds."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from tools.replay_checks import capture
+    N, k, b = 14, 30, 8
+    A = matrices.shifted(matrices.laplacian_3d(N), 12.0)
+    Om = np.random.default_rng(4).standard_normal((N ** 3, b))
+    Ts, Bs, oks = capture(A, k, b, Om)
+    assert oks[-1] and len(Ts) > 8
+    main = rbl.Checker(threads=4)
+    tracker = rbl.Checker(threads=3)
+    handed = []
+    for n, (T, Bi, ok) in enumerate(zip(Ts, Bs, oks)):
+        if n >= 3 and n % 3 == 0:
+            Told, Bold = Ts[n - 2], Bs[n - 2]
+            q = tracker.check(Told, k, Bold, tol=0.0, force_full=True)
+            assert q["have_all"] and not q["converged"]
+            main.set_seeds(q["D"], q["S"], q["resid"])
+            handed.append(Told.shape[1])
+            if n % 6 == 0:      # an older hand-over arriving late: must be ignored
+                main.set_seeds(q["D"][:k], q["S"][: Ts[n - 3].shape[1], :k].copy(), None)
+        r = main.check(T, k, Bi)
+        w, z = rbl_oracle.dsbev(T)
+        Dr, Vr = rbl_oracle.sort_eig_abs(w, z, k)
+        rr = rbl_oracle.residual_bounds(Bi, Vr, b)
+        if np.min(np.abs(rr - 1e-7)) > 1e-9:
+            assert r["converged"] == ok, (n, T.shape[1])
+        if r["have_all"]:
+            assert np.max(np.abs(np.sort(r["D"]) - np.sort(Dr))) < 1e-11 * 12
+    assert handed

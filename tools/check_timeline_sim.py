@@ -22,6 +22,9 @@ import numpy as np
 import rbl_b200
 from tools.replay_dump import band, load
 
+if os.environ.get("RBL_LIB"):        # compare builds: RBL_LIB=/path/to/other/librbl_b200.so
+    rbl_b200.load_library(os.environ["RBL_LIB"])
+
 MAX_AHEAD = 16
 CHECK_PERIOD = 4
 
@@ -34,7 +37,7 @@ def simulate(path, step_ms, threads, k=100, verbose=True, last_step=None):
     zeros = np.zeros((b, b))
     requests = []            # (time posted, step) snapshots offered to the tracker, newest wins
     results = []             # (time done, step, D, S) finished tracker passes
-    st = dict(tracker_free=0.0, consumed=0, handed=-1)
+    st = dict(tracker_free=0.0, consumed=0, handed=-1, gifts=[])
     log = []
 
     def advance_tracker(until):
@@ -47,12 +50,16 @@ def simulate(path, step_ms, threads, k=100, verbose=True, last_step=None):
             it = requests[cand[-1]][1]
             st["consumed"] = cand[-1] + 1
             ab = band(hA, hB, b, it)
+            gifts = [g for g in st["gifts"] if g[0] <= start]          # full checks of the main checker seed the tracker too
+            if gifts:
+                tracker.set_seeds(gifts[-1][1], gifts[-1][2])
+                st["gifts"] = [g for g in st["gifts"] if g[0] > start]
             t0 = time.perf_counter()
-            r = tracker.check(ab, k, zeros, tol=0.0, force_full=True)
+            r = tracker.check(ab, k, hB[it - 1][:b, :b], tol=0.0, force_full=True)
             d = (time.perf_counter() - t0) * 1e3
             st["tracker_free"] = start + d
             if r["have_all"]:
-                results.append((start + d, it, r["D"], r["S"]))
+                results.append((start + d, it, r["D"], r["S"], r["resid"]))
             log.append(("tracker", it, start, d, r["factorizations"]))
 
     def run_main(it, now):
@@ -61,8 +68,8 @@ def simulate(path, step_ms, threads, k=100, verbose=True, last_step=None):
         seed_it = None
         if done and done[-1] > st["handed"]:
             st["handed"] = done[-1]
-            _, seed_it, D, S = results[done[-1]]
-            main.set_seeds(D, S)
+            _, seed_it, D, S, rho = results[done[-1]]
+            main.set_seeds(D, S, rho if os.environ.get("SIM_NO_SEED_WITNESSES") is None else None)
         ab = band(hA, hB, b, it)
         t0 = time.perf_counter()
         r = main.check(ab, k, hB[it - 1][:b, :b])
@@ -92,8 +99,10 @@ def simulate(path, step_ms, threads, k=100, verbose=True, last_step=None):
         if in_flight is None:
             r, d = run_main(i, t_dev)
             in_flight = (i, t_dev + d, r)
-            if not r["converged"] and not r["full"] and i * b >= 2 * k:
+            if not r["converged"] and i * b >= 2 * k:
                 requests.append((t_dev + d, i))            # the solver posts the snapshot when the check returns
+                if r["have_all"]:
+                    st["gifts"].append((t_dev + d, r["D"], r["S"]))
     if accepted is None and in_flight:
         it0, tdone, r = in_flight
         idle += max(0.0, tdone - t_dev)
