@@ -1695,8 +1695,23 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
             } else {
                 std::vector<double> f(kf);
                 for (int64_t j = 0; j < kf; ++j) f[j] = pairs[j].theta;
+                // the two counts of the validation (just above / just below the k-th value) are taken at once on two
+                // threads and remembered: when nothing is missing the "final validation" below asks for the same points
+                std::vector<std::pair<double, int64_t>> memo;
+                {
+                    std::vector<double> xs;
+                    for (double x : {tk + delta, std::max(0.0, tk - delta)})
+                        if (x <= T.gersh_hi) xs.push_back(x);
+                    std::vector<int64_t> below;
+                    int64_t nf0 = 0;
+                    parallel_below(T, xs, threads, below, nf0);
+                    wk.nfac += (int)nf0;
+                    for (size_t i = 0; i < xs.size(); ++i) memo.push_back({xs[i], N - below[i]});
+                }
                 auto above = [&](double x) -> int64_t {  // #{lambda > x}
                     if (x > T.gersh_hi) return 0;
+                    for (auto& mm : memo)
+                        if (mm.first == x) return mm.second;
                     wk.lu.factor(T, x);
                     ++wk.nfac;
                     return N - wk.lu.nneg;

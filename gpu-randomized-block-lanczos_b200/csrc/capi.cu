@@ -1,5 +1,6 @@
 // extern "C" entry points declared in include/rbl_b200.h.
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -602,7 +603,11 @@ int rbl_checker_check(rbl_checker* c, int64_t N, int64_t kd, const double* ab, i
         for (int r = 0; r < b; ++r)
             for (int cc = 0; cc < b; ++cc) bir[(size_t)r * b + cc] = bi[(size_t)cc * b + r];
         const int full_before = c->chk.full_checks;
+        const auto tc0 = std::chrono::steady_clock::now();
         TopKResult r = c->chk.check(T, bir.data(), (int)b, k, tol, force_full != 0);
+        if (c->chk.verbose > 1)
+            std::fprintf(stderr, "[rbl]   rbl_checker_check: check() took %.1f ms\n",
+                         std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count() * 1e3);
         if (converged_out) *converged_out = r.converged ? 1 : 0;
         if (have_all_out) *have_all_out = r.have_all ? 1 : 0;
         if (stats_out) {
