@@ -90,6 +90,7 @@ SIGNATURES = {
     "rbl_checker_check": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _PD, C.c_int64, _PD, C.c_int64, C.c_double, C.c_int,
                                     _PD, _PD, _PD, _P32, _P32, _P64]),
     "rbl_checker_set_seeds": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _PD, _PD, _PD]),
+    "rbl_checker_set_need_seeds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rbl_checker_destroy": (C.c_int, [C.c_void_p]),
     "rbl_band_count_below": (C.c_int, [C.c_int64, C.c_int64, _PD, C.c_double, _P64]),
     "rbl_partition_rows": (C.c_int, [C.c_int64, C.c_int, _P64]),
@@ -357,6 +358,11 @@ class Checker:
         S = np.asfortranarray(S, dtype=np.float64)
         r = None if resid is None else np.ascontiguousarray(resid, dtype=np.float64)
         _check(lib().rbl_checker_set_seeds(self._c, S.shape[0], S.shape[1], _pd(D), _pd(S), _pd(r) if r is not None else None))
+
+    def set_need_seeds(self, fn):
+        """fn(N) is called when a full check is about to start without usable seeds (it may call set_seeds)."""
+        self._need_cb = C.CFUNCTYPE(None, C.c_void_p, C.c_int64)(lambda user, N: fn(int(N))) if fn else None
+        _check(lib().rbl_checker_set_need_seeds(self._c, C.cast(self._need_cb, C.c_void_p) if fn else None, None))
 
     def close(self):
         if self._c:

@@ -1656,6 +1656,14 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     stage_now = 2;
     auto since_start = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() * 1e3; };
     const double ms_stage3_begin = since_start();
+    auto seeds_usable = [&]() {
+        return (int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N &&
+               (double)seeds_[0].v.size() >= seed_min_frac() * (double)N;  // staler seeds rarely survive the refinement
+    };
+    // No usable seeds: before solving from scratch, the owner gets a chance to hand some over (the solver waits here for
+    // the tracker's pass in flight - finishing that pass and refining its pairs is never slower than starting over with
+    // the tracker paused, and usually several times faster).
+    if (!seeds_usable() && need_seeds && !force_full) need_seeds(N);
     // all k pairs from here on: every thread of the box is wanted (the accepting check is the one the device waits for)
     struct FullFlag {
         std::atomic<bool>* f;
@@ -1666,8 +1674,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     std::vector<Pair> pairs;
     std::vector<Pair> known_pairs;
     bool from_seeds = false;
-    if ((int64_t)seeds_.size() == k && !seeds_.empty() && (int64_t)seeds_[0].v.size() <= N &&
-        (double)seeds_[0].v.size() >= seed_min_frac() * (double)N) {  // staler seeds rarely survive the refinement
+    if (seeds_usable()) {
         // Fast path: the k pairs of an earlier full solve are refined in parallel (seeds that do not converge or that
         // collapse onto the same eigenvector are dropped).  Sturm counts then say exactly how many eigenvalues are
         // missing and where - above the smallest value found (Ritz values that entered the wanted set), inside its

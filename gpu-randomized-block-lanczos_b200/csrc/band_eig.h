@@ -9,6 +9,7 @@
 #pragma once
 #include <atomic>
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 namespace rbl {
@@ -91,6 +92,8 @@ public:
     int threads = 1;
     int verbose = 0;
     std::atomic<bool>* full_flag = nullptr;     // raised while this checker computes all k pairs (stage 3)
+    // called (with the size of T) when a full check is about to start without usable seeds: last chance for set_seeds
+    std::function<void(int64_t)> need_seeds;
     int64_t total_factorizations = 0;
     int64_t resumed_factorizations = 0;
     // where the decisions came from and what they cost (seconds): [0] witness, [1] bracketed pair, [2] full

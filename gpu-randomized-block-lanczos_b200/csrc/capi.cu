@@ -635,6 +635,15 @@ int rbl_checker_set_seeds(rbl_checker* c, int64_t n_seed, int64_t k, const doubl
     });
 }
 
+int rbl_checker_set_need_seeds(rbl_checker* c, rbl_need_seeds_fn fn, void* user) {
+    return guarded([&] {
+        if (!c) throw Error(RBL_INVALID, "rbl_checker_set_need_seeds: null checker");
+        if (fn) c->chk.need_seeds = [fn, user](int64_t N) { fn(user, N); };
+        else c->chk.need_seeds = nullptr;
+        return (int)RBL_OK;
+    });
+}
+
 int rbl_checker_destroy(rbl_checker* c) {
     delete c;
     return RBL_OK;

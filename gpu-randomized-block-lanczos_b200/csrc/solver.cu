@@ -978,6 +978,9 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         std::condition_variable cv;
         std::thread th;
         bool active = false, stop = false, have_req = false, have_res = false;
+        bool busy = false;                 // a pass is running ...
+        int64_t busy_N = 0;                // ... on a snapshot of this size
+        std::condition_variable cv_done;   // signalled at the end of every pass
         std::atomic<bool> cancel{false};   // raised with `stop`: the tracker abandons the eigensolve it is in
         std::atomic<bool> pause{false};    // raised while the main checker computes all k pairs: the tracker's threads sleep
         BandSym req;
@@ -987,6 +990,21 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         TopKResult res;
     } shadow;
     checker.full_flag = &shadow.pause;
+    // a full check without usable seeds waits for the tracker's pass in flight (if its snapshot is recent enough to help)
+    // and takes its pairs, instead of pausing the tracker and solving from scratch
+    checker.need_seeds = [&shadow, &checker, k_rem](int64_t Nnow) {
+        std::unique_lock<std::mutex> lk(shadow.mu);
+        if (!shadow.active) return;
+        if (!shadow.have_res) {
+            if (!shadow.busy || (double)shadow.busy_N < 0.75 * (double)Nnow) return;
+            shadow.cv_done.wait(lk, [&] { return !shadow.busy || shadow.stop; });
+        }
+        if (shadow.have_res) {
+            checker.set_seeds(shadow.res.d, shadow.res.s, shadow.res.N, k_rem,
+                              shadow.res.resid.size() == (size_t)k_rem ? &shadow.res.resid : nullptr);
+            shadow.have_res = false;
+        }
+    };
     const int shadow_verbose = opt.verbose;
     const int bb = b;
     auto shadow_loop = [&shadow, k_rem, bb, shadow_verbose](int nthreads) {
@@ -1004,6 +1022,8 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
                 Tc = std::move(shadow.req);
                 bic = shadow.req_bi;
                 shadow.have_req = false;
+                shadow.busy = true;
+                shadow.busy_N = Tc.N;
                 if (shadow.have_gift) {
                     gift = std::move(shadow.gift);
                     shadow.have_gift = false;
@@ -1013,6 +1033,16 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
             if (got_gift) tracker.set_seeds(gift.d, gift.s, gift.N, k_rem);  // (ignored when older than its own)
             Tc.cancel = &shadow.cancel;
             Tc.pause = &shadow.pause;
+            struct BusyGuard {   // whatever way the pass ends, nobody keeps waiting for it
+                Shadow& s;
+                ~BusyGuard() {
+                    {
+                        std::lock_guard<std::mutex> lk(s.mu);
+                        s.busy = false;
+                    }
+                    s.cv_done.notify_all();
+                }
+            } busy_guard{shadow};
             TopKResult r;
             const double ts0 = now_s();
             const int64_t f0 = tracker.total_factorizations;

@@ -258,6 +258,10 @@ int rbl_checker_check(rbl_checker* c, int64_t N, int64_t kd, const double* ab, i
  * background tracker thread does between checks (d: k values, s: n_seed x k column-major).  resid (may be NULL): their k
  * residual bounds at that time; the pairs with the largest ones join the checker's witnesses. */
 int rbl_checker_set_seeds(rbl_checker* c, int64_t n_seed, int64_t k, const double* d, const double* s, const double* resid);
+/* fn(user, N) is called when a full check is about to start without usable seeds (N = size of T): the last moment at which
+ * rbl_checker_set_seeds still helps.  The solver uses the same hook to wait for its tracker's pass in flight. */
+typedef void (*rbl_need_seeds_fn)(void* user, int64_t N);
+int rbl_checker_set_need_seeds(rbl_checker* c, rbl_need_seeds_fn fn, void* user);
 int rbl_checker_destroy(rbl_checker* c);
 
 /* Number of eigenvalues of the band matrix strictly below x (Sturm count by row-wise elimination). */

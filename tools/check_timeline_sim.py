@@ -71,9 +71,26 @@ def simulate(path, step_ms, threads, k=100, verbose=True, last_step=None):
             _, seed_it, D, S, rho = results[done[-1]]
             main.set_seeds(D, S, rho if os.environ.get("SIM_NO_SEED_WITNESSES") is None else None)
         ab = band(hA, hB, b, it)
+        waited = [0.0, 0.0]
+
+        def need_seeds(N):
+            # the solver's hook: a full check without usable seeds waits for the tracker's pass in flight
+            tw0 = time.perf_counter()
+            elapsed = (tw0 - t0) * 1e3
+            advance_tracker(now + elapsed)                 # passes that start before this moment (runs the one in flight)
+            cand = [j for j, r_ in enumerate(results) if j > st["handed"] and r_[1] * b >= 0.75 * N]
+            if cand:
+                j = cand[-1]
+                st["handed"] = j
+                waited[0] = max(0.0, results[j][0] - (now + elapsed))      # virtual wait until that pass is done
+                main.set_seeds(results[j][2], results[j][3], results[j][4])
+            waited[1] = (time.perf_counter() - tw0) * 1e3                  # real time spent emulating: not the check's
+
+        if os.environ.get("SIM_NO_WAIT") is None:
+            main.set_need_seeds(need_seeds)
         t0 = time.perf_counter()
         r = main.check(ab, k, hB[it - 1][:b, :b])
-        d = (time.perf_counter() - t0) * 1e3
+        d = (time.perf_counter() - t0) * 1e3 - waited[1] + waited[0]
         log.append(("main", it, now, d, r["factorizations"], int(r["full"]), int(r["converged"]), seed_it))
         return r, d
 
