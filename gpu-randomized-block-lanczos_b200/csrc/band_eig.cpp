@@ -1512,6 +1512,52 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
         return finish(false);
     };
 
+    // the witnesses after the first, each followed on its own thread; true (and R filled by reject_with) when one of them
+    // is a wanted pair that has not converged
+    auto follow_extras = [&]() -> bool {
+        if (wit_.size() < 2) return false;
+        const size_t nw = wit_.size() - 1;
+        std::vector<Followed> fw(nw);
+        std::atomic<size_t> next{0};
+        std::atomic<bool> cancelled{false};
+        auto run = [&]() {
+            try {
+                for (;;) {
+                    const size_t i = next.fetch_add(1);
+                    if (i >= nw) break;
+                    fw[i] = follow_witness(T, wit_[i + 1], bi, b);
+                }
+            } catch (const Cancelled&) {
+                cancelled = true;
+                next = nw;
+            }
+        };
+        const int nt = (int)std::min<size_t>((size_t)std::max(1, threads), nw);
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(run);
+        run();
+        for (auto& t : th) t.join();
+        if (cancelled) throw Cancelled{};
+        int best = -1;
+        for (size_t i = 0; i < nw; ++i) {
+            wk.nfac += fw[i].nfac;
+            if (verbose > 2) std::fprintf(stderr, "[rbl]   stage1 w%zu ok=%d theta=%.10g res=%.2e larger=%lld rho=%.3e\n", i + 1, (int)fw[i].ok, fw[i].theta, fw[i].res, (long long)fw[i].larger, fw[i].ok ? fw[i].rho : -1.0);
+            if (fw[i].ok && fw[i].rho > tol && fw[i].larger < k && (best < 0 || fw[i].rho > fw[best].rho)) best = (int)i;
+        }
+        if (best < 0) return false;
+        // the slowest unconverged one is followed from now on; the other unconverged ones stay on the list
+        std::vector<std::vector<double>> keep;
+        std::vector<double> keep_theta;
+        for (size_t i = 0; i < nw; ++i)
+            if ((int)i != best && fw[i].ok && fw[i].rho > tol && fw[i].larger < k) {
+                keep.push_back(std::move(fw[i].x));
+                keep_theta.push_back(fw[i].theta);
+            }
+        wlu_.ck_row = -1;  // the kept factorisation belongs to the converged first witness
+        reject_with(fw[best].x, fw[best].theta, fw[best].rho, "witness", &keep, &keep_theta);
+        return true;
+    };
+
     // ---- stage 1: witnesses of the previous check (zero-padded old Ritz vectors) -------------------------
     // The first one - the pair this checker has been following - is refined here with its factorisation extended from the
     // previous check.  Only when it has converged are the others looked at, all at once on their own threads.
@@ -1535,48 +1581,7 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
                 }
             }
         }
-        const size_t nw = wit_.size() - 1;
-        if (nw > 0) {
-            std::vector<Followed> fw(nw);
-            std::atomic<size_t> next{0};
-            std::atomic<bool> cancelled{false};
-            auto run = [&]() {
-                try {
-                    for (;;) {
-                        const size_t i = next.fetch_add(1);
-                        if (i >= nw) break;
-                        fw[i] = follow_witness(T, wit_[i + 1], bi, b);
-                    }
-                } catch (const Cancelled&) {
-                    cancelled = true;
-                    next = nw;
-                }
-            };
-            const int nt = (int)std::min<size_t>((size_t)std::max(1, threads), nw);
-            std::vector<std::thread> th;
-            for (int t = 1; t < nt; ++t) th.emplace_back(run);
-            run();
-            for (auto& t : th) t.join();
-            if (cancelled) throw Cancelled{};
-            int best = -1;
-            for (size_t i = 0; i < nw; ++i) {
-                wk.nfac += fw[i].nfac;
-                if (verbose > 2) std::fprintf(stderr, "[rbl]   stage1 w%zu ok=%d theta=%.10g res=%.2e larger=%lld rho=%.3e\n", i + 1, (int)fw[i].ok, fw[i].theta, fw[i].res, (long long)fw[i].larger, fw[i].ok ? fw[i].rho : -1.0);
-                if (fw[i].ok && fw[i].rho > tol && fw[i].larger < k && (best < 0 || fw[i].rho > fw[best].rho)) best = (int)i;
-            }
-            if (best >= 0) {
-                // the slowest unconverged one is followed from now on; the other unconverged ones stay on the list
-                std::vector<std::vector<double>> keep;
-                std::vector<double> keep_theta;
-                for (size_t i = 0; i < nw; ++i)
-                    if ((int)i != best && fw[i].ok && fw[i].rho > tol && fw[i].larger < k) {
-                        keep.push_back(std::move(fw[i].x));
-                        keep_theta.push_back(fw[i].theta);
-                    }
-                wlu_.ck_row = -1;  // the kept factorisation belongs to the converged first witness
-                return reject_with(fw[best].x, fw[best].theta, fw[best].rho, "witness", &keep, &keep_theta);
-            }
-        }
+        if (follow_extras()) return R;
     }
 
     stage_now = 1;
@@ -1663,7 +1668,13 @@ TopKResult BandTopK::check(const BandSym& T, const double* bi, int b, int64_t k,
     // No usable seeds: before solving from scratch, the owner gets a chance to hand some over (the solver waits here for
     // the tracker's pass in flight - finishing that pass and refining its pairs is never slower than starting over with
     // the tracker paused, and usually several times faster).
-    if (!seeds_usable() && need_seeds && !force_full) need_seeds(N);
+    if (!seeds_usable() && need_seeds && !force_full) {
+        const size_t had = seeds_.empty() ? 0 : seeds_[0].v.size();
+        need_seeds(N);
+        // fresh seeds bring fresh witnesses (the pairs that were slowest when the seeds were computed): they get their turn
+        // before all k pairs are refined
+        if (bi && !seeds_.empty() && seeds_[0].v.size() != had && follow_extras()) return R;
+    }
     // all k pairs from here on: every thread of the box is wanted (the accepting check is the one the device waits for)
     struct FullFlag {
         std::atomic<bool>* f;

@@ -1073,6 +1073,7 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
                 s.cancel = true;
             }
             s.cv.notify_all();
+            s.cv_done.notify_all();
             if (s.th.joinable()) s.th.join();
         }
     } shadow_join{shadow};
