@@ -102,6 +102,8 @@ struct Workspace {
     DevBuf<double> ctrl, share;           // row-sharded runs: decision flag and the shared (D, S) of the accepting check
     PinnedBuf<double> h_ctrl;
     PinnedBuf<double> hA, hB;
+    PinnedBuf<unsigned char> d2h_pin;     // two staging chunks of the pageable-destination download of V
+    cudaEvent_t d2h_ev[2] = {nullptr, nullptr};
     PinnedBuf<QrState> hqr;
     // what a handle needs besides the solve buffers: parked with the workspace so that a create / destroy cycle does
     // no cudaFree / cudaStreamDestroy / cudaEventDestroy (measured: sporadic 0.4-1.8 s stalls in rbl_destroy)
@@ -117,6 +119,8 @@ struct Workspace {
     ~Workspace() {
         for (auto e : event_pool) cudaEventDestroy(e);
         for (auto e : spill_ev)
+            if (e) cudaEventDestroy(e);
+        for (auto e : d2h_ev)
             if (e) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (ev_q) cudaEventDestroy(ev_q);
