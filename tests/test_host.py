@@ -393,3 +393,22 @@ def test_tracker_seeds_and_witnesses_keep_the_decisions(rbl):
         if r["have_all"]:
             assert np.max(np.abs(np.sort(r["D"]) - np.sort(Dr))) < 1e-11 * 12
     assert handed
+
+
+def test_check_timeline_tools_run_end_to_end(tmp_path, rbl):
+    """tools/make_T_dump.py -> tools/check_timeline_sim.py (the CPU-side tuning loop of the host check): a small solve's T is
+    generated, replayed against a virtual device clock, and accepted at a check point at which dsbev agrees."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from tools import check_timeline_sim, make_T_dump
+    from tools.replay_dump import band, load
+    path = str(tmp_path / "T.bin")
+    make_T_dump.run(12, 8, 70, path, seed=3)
+    out = check_timeline_sim.simulate(path, step_ms=0.5, threads=2, k=24, verbose=False)
+    assert out["accepted_step"] is not None and out["accepted_step"] % 4 == 0
+    m, B, b, final_i, hA, hB = load(path)
+    it = out["accepted_step"]
+    w, z = rbl_oracle.dsbev(band(hA, hB, b, it))
+    Dr, Vr = rbl_oracle.sort_eig_abs(w, z, 24)
+    assert rbl_oracle.check_convergence(hB[it - 1][:b, :b], Vr, b, 24, 1e-7)
+    assert out["idle_ms"] >= 0 and out["checks"] >= 1
