@@ -1308,8 +1308,16 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
             check_in_flight = false;
             try {
                 const double t0 = now_s();
+                double idle_from = -1.0;   // device idle = from the moment everything enqueued has run, as in harvest()
+                if (block)
+                    while (pending.wait_for(std::chrono::microseconds(200)) != std::future_status::ready)
+                        if (idle_from < 0 && cudaEventQuery(tail_event) == cudaSuccess) idle_from = now_s();
                 TopKResult r = pending.get();
-                if (block) { t_blocked += now_s() - t0; t_idle += now_s() - t0; }
+                if (block) {
+                    const double t1 = now_s();
+                    t_blocked += t1 - t0;
+                    if (idle_from >= 0) t_idle += t1 - idle_from;
+                }
                 ++checks;
                 if (r.converged) {
                     have_accept = true;
