@@ -772,7 +772,8 @@ bool block_extract(const BandSym& T, Work& wk, const Interval& iv, int q, const 
             worst = std::max(worst, res[j]);
             if (!(theta[j] > iv.lo + edge && theta[j] < iv.hi - edge)) inside = false;
         }
-        if (std::getenv("RBL_BLOCK_DEBUG")) std::fprintf(stderr, "[blk] q=%d known=%zu width=%.3e it=%d worst=%.3e inside=%d\n", q, against.size(), iv.hi - iv.lo, it, worst / tn, (int)inside);
+        static const bool block_debug = std::getenv("RBL_BLOCK_DEBUG") != nullptr;
+        if (block_debug) std::fprintf(stderr, "[blk] q=%d known=%zu width=%.3e it=%d worst=%.3e inside=%d\n", q, against.size(), iv.hi - iv.lo, it, worst / tn, (int)inside);
         // converged: at rounding level, or stagnating just above it (the attainable residual grows with N)
         if (worst <= 2e-13 * tn || (it >= 3 && worst <= 5e-12 * tn && worst > 0.25 * prev)) {
             if (!inside) return false;
@@ -815,7 +816,7 @@ void slice(const BandSym& T, const std::vector<Interval>& roots, int threads, st
     int active = 0;
     bool cancelled = false;  // under mu: a worker saw T.cancel; everybody drains
     std::atomic<int64_t> fac{0};
-    const bool slice_timing = std::getenv("RBL_SLICE_TIMING") != nullptr;
+    static const bool slice_timing = std::getenv("RBL_SLICE_TIMING") != nullptr;
     const auto ts0 = std::chrono::steady_clock::now();
     auto ms_since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - ts0).count() * 1e3; };
     // The bisection tree starts with one interval per root, so its first ~5 levels run on one or two threads, and with
