@@ -1284,6 +1284,26 @@ bool BandTopK::refine_seeds(const BandSym& T, int64_t k, std::vector<Pair>& pair
                     if (mb.rs > 0.25 * prev) break;
                 }
             };
+            // stale seeds (residual up to 1e-4 ||T||) of one multiple value: a first shared round at their mean Rayleigh quotient
+            // brings them close enough for the shared round below; without it every copy pays two factorisations of its own
+            {
+                int nfar = 0;
+                double sum = 0, spread_lo = 1e300, spread_hi = -1e300, rmax = 0;
+                for (auto& mb : mem)
+                    if (!mb.ok && mb.rs > 1e-8 * tn && mb.rs <= 1e-4 * tn) {
+                        ++nfar;
+                        sum += mb.th;
+                        spread_lo = std::min(spread_lo, mb.th);
+                        spread_hi = std::max(spread_hi, mb.th);
+                        rmax = std::max(rmax, mb.rs);
+                    }
+                if (nfar >= 2 && spread_hi - spread_lo <= 10.0 * rmax) {
+                    wk.lu.factor(T, sum / nfar);
+                    ++wk.nfac;
+                    for (auto& mb : mem)
+                        if (!mb.ok && mb.rs > 1e-8 * tn && mb.rs <= 1e-4 * tn) iterate(mb);
+                }
+            }
             // shared factorisation: only for copies that are already close (residual <= 1e-8 ||T||), so that the common
             // shift - the innermost of their own "Ritz value minus twice the residual" - stays within ~1e-7 ||T|| of all of them
             int nclose = 0;
