@@ -1062,7 +1062,8 @@ CycleOut Run::cycle(int64_t nlb, int64_t k_rem, int64_t kk_end, bool probe, int6
         if (!shadow.active) return;
         if (!shadow.have_res) {
             if (!shadow.busy || (double)shadow.busy_N < 0.75 * (double)Nnow) return;
-            shadow.cv_done.wait(lk, [&] { return !shadow.busy || shadow.stop; });
+            // (bounded: a pass takes tens to hundreds of milliseconds; the full check works without its pairs)
+            shadow.cv_done.wait_for(lk, std::chrono::seconds(2), [&] { return !shadow.busy || shadow.stop; });
         }
         if (shadow.have_res) {
             checker.set_seeds(shadow.res.d, shadow.res.s, shadow.res.N, k_rem,
